@@ -1,0 +1,686 @@
+// engine.cu -- device state object + the C ABI of include/damavand_b200.h.
+//
+// Replaces /root/reference/damavand-gpu/rust_communication.cu (process-global state, OpenMP loop
+// over GPUs, int32 sizes, exit() on error) and quantum_amplitudes.cu (SoA re/im arrays, one
+// cudaDeviceSynchronize per gate).  One dvd_state drives one GPU; amplitudes are interleaved
+// complex128 in one allocation; gates are queued and executed as fused passes.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/damavand_b200.h"
+#include "kernels.h"
+#include "nccl_dyn.h"
+#include "planner.h"
+
+using namespace dvd;
+
+static thread_local std::string g_last_error;
+static NcclApi g_nccl;
+
+static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(DVD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
+    } while (0)
+#define NC(call)                                                                              \
+    do {                                                                                      \
+        ncclResult_t r__ = (call);                                                            \
+        if (r__ != ncclSuccess)                                                               \
+            return fail(DVD_ERR_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r__)); \
+    } while (0)
+#define TRY(call)                     \
+    do {                              \
+        int rc__ = (call);            \
+        if (rc__ != DVD_OK) return rc__; \
+    } while (0)
+
+struct dvd_state {
+    int n_qubits = 0, n_local = 0, rank = 0, world = 1, device = 0;
+    uint64_t n_amps = 0;        // local amplitudes
+    uint64_t rank_bits = 0;     // rank << n_local
+    cplx* amp = nullptr;
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_pack[2] = {nullptr, nullptr}, ev_comm[2] = {nullptr, nullptr};
+    std::vector<HostGate> pending;
+    std::vector<int> perm;      // logical -> physical (identity between flushes)
+    DevOp* d_ops = nullptr; size_t d_ops_cap = 0;
+    DevOp* h_ops = nullptr; size_t h_ops_cap = 0;
+    double* d_tree = nullptr; bool tree_valid = false;
+    double* d_scratch = nullptr; size_t scratch_doubles = 0;
+    ncclComm_t comm = nullptr;
+    cplx* swap_buf[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t swap_chunk = 0;
+    dvd_stats stats;
+    bool unfused = false;
+    PlanOptions opt;
+};
+
+static int ensure_scratch(dvd_state* s, size_t doubles) {
+    if (s->scratch_doubles >= doubles) return DVD_OK;
+    if (s->d_scratch) CU(cudaFree(s->d_scratch));
+    s->d_scratch = nullptr; s->scratch_doubles = 0;
+    CU(cudaMalloc(&s->d_scratch, doubles * sizeof(double)));
+    s->scratch_doubles = doubles;
+    return DVD_OK;
+}
+
+static int set_zero_state(dvd_state* s) {
+    CU(cudaMemsetAsync(s->amp, 0, s->n_amps * sizeof(cplx), s->stream));
+    if (s->rank == 0) {   // amplitude 0 lives on the first rank (circuit.rs:168-170, kernels.cu:62-81)
+        CU(launch_set_basis_state(s->amp, 0, s->stream));
+        s->stats.kernel_launches++;
+    }
+    s->tree_valid = false;
+    return DVD_OK;
+}
+
+static int create_common(int n_qubits, int device, int rank, int world, const void* nccl_id, dvd_state** out) {
+    if (!out) return fail(DVD_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (world < 1 || (world & (world - 1))) return fail(DVD_ERR_ARG, "world must be a power of two");
+    int g = 0; while ((1 << g) < world) ++g;
+    if (n_qubits < 1 || n_qubits > 40) return fail(DVD_ERR_ARG, "n_qubits out of range [1,40]");
+    if (n_qubits - g < 1) return fail(DVD_ERR_ARG, "need at least one local qubit per rank");
+    if (rank < 0 || rank >= world) return fail(DVD_ERR_ARG, "bad rank");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) return fail(DVD_ERR_CUDA, "Could not find any GPU.");   // circuit.rs:143-145
+    if (device < 0 || device >= ndev) return fail(DVD_ERR_ARG, "bad device index");
+    CU(cudaSetDevice(device));
+    CU(kernels_init());
+    dvd_state* s = new dvd_state();
+    std::memset(&s->stats, 0, sizeof(s->stats));
+    s->n_qubits = n_qubits; s->n_local = n_qubits - g; s->rank = rank; s->world = world; s->device = device;
+    s->n_amps = 1ull << s->n_local;
+    s->rank_bits = (uint64_t)rank << s->n_local;
+    s->perm.resize(n_qubits);
+    for (int q = 0; q < n_qubits; ++q) s->perm[q] = q;
+    auto cleanup = [&](int code) { dvd_destroy(s); return code; };
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && s->n_amps * sizeof(cplx) > free_b) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "System requires more memory to simulate %d qubits: need %.1f GiB on device %d, %.1f GiB free",
+                 n_qubits, s->n_amps * 16.0 / 1073741824.0, device, free_b / 1073741824.0);
+        return cleanup(fail(DVD_ERR_ARG, buf));    // mirrors the panic at circuit.rs:123-128
+    }
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&s->ev_t0) != cudaSuccess || cudaEventCreate(&s->ev_t1) != cudaSuccess)
+        return cleanup(fail(DVD_ERR_CUDA, "stream/event creation failed"));
+    for (int i = 0; i < 2; ++i)
+        if (cudaEventCreateWithFlags(&s->ev_pack[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->ev_comm[i], cudaEventDisableTiming) != cudaSuccess)
+            return cleanup(fail(DVD_ERR_CUDA, "event creation failed"));
+    cudaError_t e = cudaMalloc(&s->amp, s->n_amps * sizeof(cplx));
+    if (e != cudaSuccess) return cleanup(fail(DVD_ERR_CUDA, std::string("cudaMalloc(state): ") + cudaGetErrorString(e)));
+    e = cudaMalloc(&s->d_tree, tree_size(s->n_local) * sizeof(double));
+    if (e != cudaSuccess) return cleanup(fail(DVD_ERR_CUDA, std::string("cudaMalloc(tree): ") + cudaGetErrorString(e)));
+    if (world > 1) {
+        std::string why = g_nccl.load();
+        if (!why.empty()) return cleanup(fail(DVD_ERR_NCCL, why));
+        if (!nccl_id) return cleanup(fail(DVD_ERR_ARG, "nccl_id is null"));
+        ncclUniqueId id;
+        static_assert(sizeof(ncclUniqueId) == DVD_NCCL_ID_BYTES, "ncclUniqueId size");
+        std::memcpy(&id, nccl_id, sizeof id);
+        ncclResult_t r = g_nccl.CommInitRank(&s->comm, world, id, rank);
+        if (r != ncclSuccess) return cleanup(fail(DVD_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)));
+    }
+    int rc = set_zero_state(s);
+    if (rc != DVD_OK) return cleanup(rc);
+    *out = s;
+    return DVD_OK;
+}
+
+extern "C" {
+
+int dvd_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+double dvd_device_mem_mib(int device) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    return (double)p.totalGlobalMem / 1048576.0;
+}
+
+int dvd_peer_access_allowed(int a, int b) {
+    int ok = 0;
+    if (cudaDeviceCanAccessPeer(&ok, a, b) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return ok;
+}
+
+const char* dvd_last_error(void) { return g_last_error.c_str(); }
+
+int dvd_create(int n_qubits, int device, dvd_state** out) { return create_common(n_qubits, device, 0, 1, nullptr, out); }
+
+int dvd_create_distributed(int n_qubits, int device, int rank, int world, const void* nccl_id, dvd_state** out) {
+    return create_common(n_qubits, device, rank, world, nccl_id, out);
+}
+
+int dvd_nccl_unique_id(void* out_id) {
+    if (!out_id) return fail(DVD_ERR_ARG, "out_id is null");
+    std::string why = g_nccl.load();
+    if (!why.empty()) return fail(DVD_ERR_NCCL, why);
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    std::memcpy(out_id, &id, sizeof id);
+    return DVD_OK;
+}
+
+int dvd_destroy(dvd_state* s) {
+    if (!s) return DVD_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
+    if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+    if (s->amp) cudaFree(s->amp);
+    if (s->d_tree) cudaFree(s->d_tree);
+    if (s->d_scratch) cudaFree(s->d_scratch);
+    if (s->d_ops) cudaFree(s->d_ops);
+    if (s->h_ops) cudaFreeHost(s->h_ops);
+    for (auto& b : s->swap_buf) if (b) cudaFree(b);
+    for (int i = 0; i < 2; ++i) {
+        if (s->ev_pack[i]) cudaEventDestroy(s->ev_pack[i]);
+        if (s->ev_comm[i]) cudaEventDestroy(s->ev_comm[i]);
+    }
+    if (s->ev_t0) cudaEventDestroy(s->ev_t0);
+    if (s->ev_t1) cudaEventDestroy(s->ev_t1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+    delete s;
+    return DVD_OK;
+}
+
+int dvd_reset_zero_state(dvd_state* s) {
+    if (!s) return fail(DVD_ERR_ARG, "null state");
+    CU(cudaSetDevice(s->device));
+    s->pending.clear();
+    return set_zero_state(s);
+}
+
+int dvd_apply_gate(dvd_state* s, const double m_re[4], const double m_im[4], int control, int target) {
+    if (!s || !m_re || !m_im) return fail(DVD_ERR_ARG, "null argument");
+    if (target < 0 || target >= s->n_qubits) return fail(DVD_ERR_ARG, "target qubit out of range");
+    if (control < -1 || control >= s->n_qubits || control == target) return fail(DVD_ERR_ARG, "control qubit out of range");
+    HostGate g;
+    g.target = target; g.control = control; g.gate_idx = (int)s->pending.size();
+    for (int k = 0; k < 4; ++k) { g.m[2 * k] = m_re[k]; g.m[2 * k + 1] = m_im[k]; }
+    s->pending.push_back(g);
+    return DVD_OK;
+}
+
+int dvd_apply_circuit(dvd_state* s, const dvd_gate* gates, int64_t n) {
+    if (!s || (!gates && n > 0)) return fail(DVD_ERR_ARG, "null argument");
+    for (int64_t i = 0; i < n; ++i) {
+        const dvd_gate& in = gates[i];
+        if (in.target < 0 || in.target >= s->n_qubits) return fail(DVD_ERR_ARG, "target qubit out of range");
+        if (in.control < -1 || in.control >= s->n_qubits || in.control == in.target)
+            return fail(DVD_ERR_ARG, "control qubit out of range");
+    }
+    s->pending.reserve(s->pending.size() + (size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        HostGate g;
+        g.target = gates[i].target; g.control = gates[i].control; g.gate_idx = (int)s->pending.size();
+        std::memcpy(g.m, gates[i].m, sizeof g.m);
+        s->pending.push_back(g);
+    }
+    return DVD_OK;
+}
+
+}  // extern "C"
+
+// ---- flush ---------------------------------------------------------------------------------------
+static DevOp simple_op(const HostGate& g) {
+    DevOp op;
+    std::memset(&op, 0, sizeof op);
+    std::memcpy(op.m, g.m, sizeof op.m);
+    classify_gate(g.m, &op.kind, &op.d0_is_one);
+    op.group = -1; op.tpos = -1; op.cpos = -1;
+    op.tbit = (int8_t)g.target; op.cbit = (int8_t)g.control; op.gate_idx = g.gate_idx;
+    return op;
+}
+
+static int ensure_swap_buffers(dvd_state* s) {
+    if (s->swap_buf[0]) return DVD_OK;
+    const uint64_t half = s->n_amps / 2;
+    uint64_t chunk = 1ull << 22;   // 64 MiB of complex128 per message
+    if (const char* e = getenv("DVD_SWAP_CHUNK_LOG2")) { int v = atoi(e); if (v >= 4 && v <= 30) chunk = 1ull << v; }
+    s->swap_chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(half, 1));
+    for (auto& b : s->swap_buf) CU(cudaMalloc(&b, s->swap_chunk * sizeof(cplx)));
+    return DVD_OK;
+}
+
+// Exchange physical rank-index qubit gq with physical local qubit lq: the half of the chunk whose bit
+// lq differs from this rank's bit gq trades places with the partner rank's complementary half
+// (partner = rank ^ 2^(gq-n_local) == Circuit::compute_partner_rank, circuit.rs:781-795).  Half a
+// chunk crosses NVLink each way, against the reference's whole chunk both ways
+// (rust_communication.cu:106-141).  Chunked and double buffered: pack k+1 / unpack k-1 on the compute
+// stream overlap the ncclSend/ncclRecv of chunk k on the communication stream.
+static int global_swap(dvd_state* s, int gq, int lq) {
+    TRY(ensure_swap_buffers(s));
+    const int j = gq - s->n_local;
+    const int b = (s->rank >> j) & 1;
+    const int partner = s->rank ^ (1 << j);
+    const int mybit = 1 - b;    // the half that leaves: local bit lq != my rank bit
+    const uint64_t half = s->n_amps / 2, C = s->swap_chunk;
+    const uint64_t nchunks = (half + C - 1) / C;
+    cplx** sendb = &s->swap_buf[0];
+    cplx** recvb = &s->swap_buf[2];
+    for (uint64_t k = 0; k < nchunks; ++k) {
+        const int slot = (int)(k & 1);
+        const uint64_t first = k * C, cnt = std::min(C, half - first);
+        CU(launch_pack_half(s->amp, lq, mybit, first, cnt, sendb[slot], s->stream));
+        s->stats.kernel_launches++;
+        CU(cudaEventRecord(s->ev_pack[slot], s->stream));
+        CU(cudaStreamWaitEvent(s->comm_stream, s->ev_pack[slot], 0));
+        NC(g_nccl.GroupStart());
+        NC(g_nccl.Send(sendb[slot], cnt * 2, ncclDouble, partner, s->comm, s->comm_stream));
+        NC(g_nccl.Recv(recvb[slot], cnt * 2, ncclDouble, partner, s->comm, s->comm_stream));
+        NC(g_nccl.GroupEnd());
+        CU(cudaEventRecord(s->ev_comm[slot], s->comm_stream));
+        if (k >= 1) {
+            const int ps = (int)((k - 1) & 1);
+            const uint64_t pf = (k - 1) * C, pc = std::min(C, half - pf);
+            CU(cudaStreamWaitEvent(s->stream, s->ev_comm[ps], 0));
+            CU(launch_unpack_half(s->amp, lq, mybit, pf, pc, recvb[ps], s->stream));
+            s->stats.kernel_launches++;
+        }
+    }
+    {
+        const uint64_t k = nchunks - 1;
+        const int ps = (int)(k & 1);
+        const uint64_t pf = k * C, pc = std::min(C, half - pf);
+        CU(cudaStreamWaitEvent(s->stream, s->ev_comm[ps], 0));
+        CU(launch_unpack_half(s->amp, lq, mybit, pf, pc, recvb[ps], s->stream));
+        s->stats.kernel_launches++;
+    }
+    s->stats.global_swaps++;
+    s->stats.swap_bytes_sent += (int64_t)(half * sizeof(cplx));
+    return DVD_OK;
+}
+
+static int flush_impl(dvd_state* s) {
+    if (s->pending.empty()) return DVD_OK;
+    CU(cudaSetDevice(s->device));
+    std::vector<DistStep> steps;
+    try {
+        if (s->world > 1) {
+            steps = plan_distributed(s->pending, s->n_qubits, s->n_local, s->perm, /*restore_identity=*/true);
+        } else {
+            DistStep st; st.kind = DistStep::LOCAL_GATES; st.gates = s->pending;
+            steps.push_back(std::move(st));
+        }
+    } catch (const std::exception& e) {
+        return fail(DVD_ERR_INTERNAL, std::string("planner: ") + e.what());
+    }
+    const bool tiled = !s->unfused && s->n_local >= TILE_BITS;
+    // plan every local step up front so that all ops go to the device in one copy
+    std::vector<std::vector<Pass>> plans(steps.size());
+    size_t total_ops = 0;
+    if (tiled) {
+        try {
+            for (size_t i = 0; i < steps.size(); ++i)
+                if (steps[i].kind == DistStep::LOCAL_GATES) {
+                    plans[i] = plan_local(steps[i].gates, s->n_local, s->n_qubits, s->opt);
+                    for (auto& p : plans[i]) total_ops += p.ops.size();
+                }
+        } catch (const std::exception& e) {
+            return fail(DVD_ERR_INTERNAL, std::string("planner: ") + e.what());
+        }
+        if (total_ops > s->h_ops_cap) {
+            CU(cudaStreamSynchronize(s->stream));
+            if (s->h_ops) CU(cudaFreeHost(s->h_ops));
+            if (s->d_ops) CU(cudaFree(s->d_ops));
+            s->h_ops = nullptr; s->d_ops = nullptr; s->h_ops_cap = s->d_ops_cap = 0;
+            const size_t cap = std::max<size_t>(total_ops * 2, 4096);
+            CU(cudaMallocHost(&s->h_ops, cap * sizeof(DevOp)));
+            CU(cudaMalloc(&s->d_ops, cap * sizeof(DevOp)));
+            s->h_ops_cap = s->d_ops_cap = cap;
+        } else {
+            CU(cudaStreamSynchronize(s->stream));   // the pinned staging buffer may still be in flight
+        }
+        size_t at = 0;
+        for (auto& pl : plans)
+            for (auto& p : pl) { std::memcpy(s->h_ops + at, p.ops.data(), p.ops.size() * sizeof(DevOp)); at += p.ops.size(); }
+        if (total_ops) CU(cudaMemcpyAsync(s->d_ops, s->h_ops, total_ops * sizeof(DevOp), cudaMemcpyHostToDevice, s->stream));
+    }
+    size_t at = 0;
+    const double chunk_bytes = (double)s->n_amps * 16.0;
+    for (size_t i = 0; i < steps.size(); ++i) {
+        DistStep& st = steps[i];
+        if (st.kind == DistStep::GLOBAL_SWAP) { TRY(global_swap(s, st.gq, st.lq)); continue; }
+        for (const HostGate& g : st.gates) {
+            if (g.gate_idx < 0) continue;   // layout-restoring CNOTs are not user gates
+            s->stats.gates_applied++;
+            s->stats.gate_algorithmic_bytes += (g.control >= 0 ? 1.0 : 2.0) * chunk_bytes;
+        }
+        if (tiled) {
+            for (auto& p : plans[i]) {
+                PassDesc pd = p.desc;
+                pd.rank_bits = s->rank_bits;
+                CU(launch_tile_pass(s->amp, s->d_ops + at, pd, s->stream));
+                at += p.ops.size();
+                s->stats.kernel_launches++; s->stats.tile_passes++;
+                s->stats.stage_switches += p.n_switches;
+                s->stats.pass_bytes += 2.0 * chunk_bytes;
+            }
+        } else {
+            for (const HostGate& g : st.gates) {
+                CU(launch_simple_gate(s->amp, s->n_local, s->rank_bits, simple_op(g), s->stream));
+                s->stats.kernel_launches++; s->stats.simple_passes++;
+                s->stats.pass_bytes += (g.control >= 0 ? 1.0 : 2.0) * chunk_bytes;
+            }
+        }
+    }
+    s->pending.clear();
+    s->tree_valid = false;
+    return DVD_OK;
+}
+
+static int ensure_tree(dvd_state* s) {
+    TRY(flush_impl(s));
+    if (s->tree_valid) return DVD_OK;
+    CU(launch_build_tree(s->amp, s->n_local, s->d_tree, s->stream));
+    s->stats.kernel_launches += 1 + std::max(0, s->n_local - BLK_BITS);
+    s->tree_valid = true;
+    return DVD_OK;
+}
+
+extern "C" {
+
+int dvd_flush(dvd_state* s) {
+    if (!s) return fail(DVD_ERR_ARG, "null state");
+    return flush_impl(s);
+}
+
+int dvd_synchronize(dvd_state* s) {
+    if (!s) return fail(DVD_ERR_ARG, "null state");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaStreamSynchronize(s->comm_stream));
+    return DVD_OK;
+}
+
+int dvd_probabilities(dvd_state* s, double* out, int64_t first, int64_t count) {
+    if (!s || (!out && count > 0)) return fail(DVD_ERR_ARG, "null argument");
+    if (first < 0 || count < 0 || (uint64_t)(first + count) > s->n_amps) return fail(DVD_ERR_ARG, "range outside the local chunk");
+    TRY(flush_impl(s));
+    const uint64_t CH = 1ull << 24;
+    TRY(ensure_scratch(s, std::min<uint64_t>(CH, std::max<int64_t>(count, 1))));
+    for (uint64_t done = 0; done < (uint64_t)count; done += CH) {
+        const uint64_t c = std::min<uint64_t>(CH, count - done);
+        CU(launch_probabilities(s->amp, first + done, c, s->d_scratch, s->stream));
+        s->stats.kernel_launches++;
+        CU(cudaMemcpyAsync(out + done, s->d_scratch, c * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return DVD_OK;
+}
+
+int dvd_norm(dvd_state* s, double* out) {
+    if (!s || !out) return fail(DVD_ERR_ARG, "null argument");
+    TRY(ensure_tree(s));
+    const double* root = s->d_tree + tree_level_offset(s->n_local, s->n_local);
+    if (s->world > 1) {
+        TRY(ensure_scratch(s, 1));
+        NC(g_nccl.AllReduce(root, s->d_scratch, 1, ncclDouble, ncclSum, s->comm, s->stream));
+        root = s->d_scratch;
+    }
+    CU(cudaMemcpyAsync(out, root, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return DVD_OK;
+}
+
+int dvd_sample(dvd_state* s, const double* uniforms, int64_t shots, uint64_t* out) {
+    if (!s || ((!uniforms || !out) && shots > 0)) return fail(DVD_ERR_ARG, "null argument");
+    if (shots < 0) return fail(DVD_ERR_ARG, "negative shot count");
+    TRY(ensure_tree(s));
+    if (shots == 0) return DVD_OK;
+    // scratch layout (in doubles): [u: shots][out: shots (u64)][sel: shots (i32, padded)][totals: world]
+    const size_t need = (size_t)shots * 3 + s->world + 8;
+    TRY(ensure_scratch(s, need));
+    double* d_u = s->d_scratch;
+    unsigned long long* d_out = reinterpret_cast<unsigned long long*>(s->d_scratch + shots);
+    int32_t* d_sel = reinterpret_cast<int32_t*>(s->d_scratch + 2 * shots);
+    double* d_tot = s->d_scratch + 3 * shots;
+    if (s->world == 1) {
+        CU(cudaMemcpyAsync(d_u, uniforms, shots * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CU(launch_sample(s->amp, s->n_local, s->d_tree, d_u, nullptr, 0, 0, shots, d_out, s->stream));
+        s->stats.kernel_launches++;
+    } else {
+        // sample_distributed, circuit_distributed.rs:42-129: per-rank totals -> rank per shot (first
+        // draw) -> local index on that rank (second draw) -> index + amps_per_rank * rank.
+        const double* root = s->d_tree + tree_level_offset(s->n_local, s->n_local);
+        NC(g_nccl.AllGather(root, d_tot, 1, ncclDouble, s->comm, s->stream));
+        std::vector<double> tot(s->world);
+        CU(cudaMemcpyAsync(tot.data(), d_tot, s->world * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        std::vector<double> cum(s->world + 1, 0.0);
+        for (int r = 0; r < s->world; ++r) cum[r + 1] = cum[r] + tot[r];        // utils.rs:270-274
+        std::vector<int32_t> sel(shots);
+        for (int64_t k = 0; k < shots; ++k) {
+            const double xsi = uniforms[k] * cum[s->world];                       // utils.rs:260
+            int idx = 0;
+            while (idx <= s->world && !(xsi <= cum[idx])) ++idx;                   // utils.rs:262-266
+            sel[k] = idx == 0 ? 0 : std::min(idx - 1, s->world - 1);
+        }
+        CU(cudaMemcpyAsync(d_u, uniforms + shots, shots * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(d_sel, sel.data(), shots * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemsetAsync(d_out, 0, shots * sizeof(unsigned long long), s->stream));
+        CU(launch_sample(s->amp, s->n_local, s->d_tree, d_u, d_sel, s->rank, (uint64_t)s->rank * s->n_amps,
+                         shots, d_out, s->stream));
+        s->stats.kernel_launches++;
+        NC(g_nccl.AllReduce(d_out, d_out, shots, ncclUint64, ncclSum, s->comm, s->stream));
+        CU(cudaStreamSynchronize(s->stream));   // sel must outlive the copy
+    }
+    CU(cudaMemcpyAsync(out, d_out, shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return DVD_OK;
+}
+
+int dvd_extract_expectation_values(dvd_state* s, const uint64_t* samples, int64_t shots,
+                                   const int32_t* qubits, int32_t n_obs, double* out) {
+    if (!s) return fail(DVD_ERR_ARG, "null state");
+    if (shots < 0 || n_obs < 0) return fail(DVD_ERR_ARG, "negative size");
+    if (shots == 0 || n_obs == 0) return DVD_OK;
+    if (!samples || !qubits || !out) return fail(DVD_ERR_ARG, "null argument");
+    for (int o = 0; o < n_obs; ++o)
+        if (qubits[o] < 0 || qubits[o] >= 64) return fail(DVD_ERR_ARG, "observable qubit out of range");
+    CU(cudaSetDevice(s->device));
+    const size_t total = (size_t)shots * n_obs;
+    const size_t need = total + shots + (n_obs + 1) / 2 + 4;
+    TRY(ensure_scratch(s, need));
+    double* d_out = s->d_scratch;
+    unsigned long long* d_samples = reinterpret_cast<unsigned long long*>(s->d_scratch + total);
+    int* d_q = reinterpret_cast<int*>(s->d_scratch + total + shots);
+    CU(cudaMemcpyAsync(d_samples, samples, shots * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(d_q, qubits, n_obs * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CU(launch_extract_expectation(d_samples, shots, d_q, n_obs, d_out, s->stream));
+    s->stats.kernel_launches++;
+    CU(cudaMemcpyAsync(out, d_out, total * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return DVD_OK;
+}
+
+int dvd_expectation_z(dvd_state* s, double* out) {
+    if (!s || !out) return fail(DVD_ERR_ARG, "null argument");
+    TRY(flush_impl(s));
+    TRY(ensure_scratch(s, ez_partial_size() + 128));
+    double* d_out = s->d_scratch + ez_partial_size();
+    CU(launch_expectation_z(s->amp, s->n_local, s->n_qubits, s->rank_bits, s->d_scratch, d_out, s->stream));
+    s->stats.kernel_launches += 2;
+    if (s->world > 1) NC(g_nccl.AllReduce(d_out, d_out, s->n_qubits, ncclDouble, ncclSum, s->comm, s->stream));
+    CU(cudaMemcpyAsync(out, d_out, s->n_qubits * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return DVD_OK;
+}
+
+int dvd_read_state(dvd_state* s, double* re, double* im, int64_t first, int64_t count) {
+    if (!s || ((!re || !im) && count > 0)) return fail(DVD_ERR_ARG, "null argument");
+    if (first < 0 || count < 0 || (uint64_t)(first + count) > s->n_amps) return fail(DVD_ERR_ARG, "range outside the local chunk");
+    TRY(flush_impl(s));
+    const uint64_t CH = 1ull << 22;
+    std::vector<cplx> tmp(std::min<uint64_t>(CH, std::max<int64_t>(count, 1)));
+    for (uint64_t done = 0; done < (uint64_t)count; done += CH) {
+        const uint64_t c = std::min<uint64_t>(CH, count - done);
+        CU(cudaMemcpyAsync(tmp.data(), s->amp + first + done, c * sizeof(cplx), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        for (uint64_t i = 0; i < c; ++i) { re[done + i] = tmp[i].x; im[done + i] = tmp[i].y; }
+    }
+    return DVD_OK;
+}
+
+int dvd_load_state(dvd_state* s, const double* re, const double* im, int64_t first, int64_t count) {
+    if (!s || ((!re || !im) && count > 0)) return fail(DVD_ERR_ARG, "null argument");
+    if (first < 0 || count < 0 || (uint64_t)(first + count) > s->n_amps) return fail(DVD_ERR_ARG, "range outside the local chunk");
+    TRY(flush_impl(s));
+    const uint64_t CH = 1ull << 22;
+    std::vector<cplx> tmp(std::min<uint64_t>(CH, std::max<int64_t>(count, 1)));
+    for (uint64_t done = 0; done < (uint64_t)count; done += CH) {
+        const uint64_t c = std::min<uint64_t>(CH, count - done);
+        for (uint64_t i = 0; i < c; ++i) { tmp[i].x = re[done + i]; tmp[i].y = im[done + i]; }
+        CU(cudaMemcpyAsync(s->amp + first + done, tmp.data(), c * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    s->tree_valid = false;
+    return DVD_OK;
+}
+
+int dvd_fidelity(dvd_state* a, dvd_state* b, double* out) {
+    if (!a || !b || !out) return fail(DVD_ERR_ARG, "null argument");
+    if (a->n_qubits != b->n_qubits || a->world != b->world || a->rank != b->rank || a->device != b->device)
+        return fail(DVD_ERR_ARG, "states have different shapes");
+    TRY(flush_impl(a));
+    TRY(flush_impl(b));
+    CU(cudaStreamSynchronize(b->stream));
+    TRY(ensure_scratch(a, 148 * 4 * 2 + 8));
+    double* d_out = a->d_scratch + 148 * 4 * 2;
+    CU(launch_dot(a->amp, b->amp, a->n_amps, a->d_scratch, d_out, a->stream));
+    a->stats.kernel_launches += 2;
+    if (a->world > 1) NC(g_nccl.AllReduce(d_out, d_out, 2, ncclDouble, ncclSum, a->comm, a->stream));
+    double h[2];
+    CU(cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, a->stream));
+    CU(cudaStreamSynchronize(a->stream));
+    *out = h[0] * h[0] + h[1] * h[1];   // norm_sqr of the complex overlap, circuit_metrics.rs:24
+    return DVD_OK;
+}
+
+int dvd_copy_state(dvd_state* dst, dvd_state* src) {
+    if (!dst || !src) return fail(DVD_ERR_ARG, "null argument");
+    if (dst->n_qubits != src->n_qubits || dst->world != src->world || dst->device != src->device)
+        return fail(DVD_ERR_ARG, "states have different shapes");
+    TRY(flush_impl(src));
+    dst->pending.clear();
+    CU(cudaStreamSynchronize(src->stream));
+    CU(cudaMemcpyAsync(dst->amp, src->amp, src->n_amps * sizeof(cplx), cudaMemcpyDeviceToDevice, dst->stream));
+    dst->tree_valid = false;
+    return DVD_OK;
+}
+
+int dvd_num_qubits(const dvd_state* s) { return s ? s->n_qubits : -1; }
+int dvd_num_local_qubits(const dvd_state* s) { return s ? s->n_local : -1; }
+int dvd_rank(const dvd_state* s) { return s ? s->rank : -1; }
+int dvd_world(const dvd_state* s) { return s ? s->world : -1; }
+
+int dvd_get_stats(const dvd_state* s, dvd_stats* out) {
+    if (!s || !out) return fail(DVD_ERR_ARG, "null argument");
+    *out = s->stats;
+    return DVD_OK;
+}
+int dvd_stats_reset(dvd_state* s) {
+    if (!s) return fail(DVD_ERR_ARG, "null state");
+    std::memset(&s->stats, 0, sizeof s->stats);
+    return DVD_OK;
+}
+int dvd_timer_begin(dvd_state* s) {
+    if (!s) return fail(DVD_ERR_ARG, "null state");
+    CU(cudaSetDevice(s->device));
+    CU(cudaEventRecord(s->ev_t0, s->stream));
+    return DVD_OK;
+}
+int dvd_timer_end(dvd_state* s, double* ms) {
+    if (!s || !ms) return fail(DVD_ERR_ARG, "null argument");
+    CU(cudaEventRecord(s->ev_t1, s->stream));
+    CU(cudaEventSynchronize(s->ev_t1));
+    float f = 0.f;
+    CU(cudaEventElapsedTime(&f, s->ev_t0, s->ev_t1));
+    *ms = f;
+    return DVD_OK;
+}
+int dvd_set_unfused(dvd_state* s, int unfused) {
+    if (!s) return fail(DVD_ERR_ARG, "null state");
+    s->unfused = unfused != 0;
+    return DVD_OK;
+}
+
+// ---- planner inspection ---------------------------------------------------------------------
+static std::vector<HostGate> to_host_gates(const dvd_gate* gates, int64_t n) {
+    std::vector<HostGate> v((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        v[i].target = gates[i].target; v[i].control = gates[i].control; v[i].gate_idx = (int)i;
+        std::memcpy(v[i].m, gates[i].m, sizeof v[i].m);
+    }
+    return v;
+}
+
+int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates, int32_t* out, int64_t cap) {
+    try {
+        PlanOptions opt;
+        std::vector<Pass> passes = plan_local(to_host_gates(gates, n_gates), n_local, n_total, opt);
+        std::vector<int32_t> v;
+        v.push_back((int32_t)passes.size());
+        for (auto& p : passes) {
+            for (int k = 0; k < TILE_BITS; ++k) v.push_back(p.desc.tile_q[k]);
+            v.push_back(p.n_switches);
+            v.push_back((int32_t)p.ops.size());
+            for (auto& op : p.ops) {
+                v.push_back(op.gate_idx); v.push_back(op.kind); v.push_back(op.group);
+                v.push_back(op.tpos); v.push_back(op.cpos);
+            }
+        }
+        if ((int64_t)v.size() > cap) return -(int64_t)v.size();
+        std::memcpy(out, v.data(), v.size() * sizeof(int32_t));
+        return (int64_t)v.size();
+    } catch (const std::exception& e) {
+        g_last_error = std::string("planner: ") + e.what();
+        return INT64_MIN;
+    }
+}
+
+int64_t dvd_plan_distributed_debug(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates,
+                                   int32_t* perm_io, int restore_identity, int32_t* out, int64_t cap) {
+    try {
+        std::vector<int> perm(perm_io, perm_io + n_total);
+        std::vector<DistStep> steps = plan_distributed(to_host_gates(gates, n_gates), n_total, n_local, perm,
+                                                       restore_identity != 0);
+        for (int q = 0; q < n_total; ++q) perm_io[q] = perm[q];
+        std::vector<int32_t> v;
+        v.push_back((int32_t)steps.size());
+        for (auto& st : steps) {
+            v.push_back((int32_t)st.kind);
+            v.push_back(st.gq); v.push_back(st.lq);
+            v.push_back((int32_t)st.gates.size());
+            for (auto& g : st.gates) { v.push_back(g.gate_idx); v.push_back(g.target); v.push_back(g.control); }
+        }
+        if ((int64_t)v.size() > cap) return -(int64_t)v.size();
+        std::memcpy(out, v.data(), v.size() * sizeof(int32_t));
+        return (int64_t)v.size();
+    } catch (const std::exception& e) {
+        g_last_error = std::string("planner: ") + e.what();
+        return INT64_MIN;
+    }
+}
+
+}  // extern "C"

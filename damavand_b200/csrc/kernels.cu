@@ -1,0 +1,470 @@
+// kernels.cu -- hand-written sm_100a kernels of the statevector hot path.
+//
+// Reference kernels these replace (all in /root/reference/damavand-gpu/kernels.cu):
+//   apply_one_qubit_gate_kernel_local        :120-172  -> k_tile_pass (fused) / k_simple_gate
+//   apply_one_qubit_gate_kernel_distributed  :174-230  -> k_pack_half / k_unpack_half around an NVLink
+//                                                         exchange, then k_tile_pass on local qubits
+//   measure_amplitudes_on_device_global      :44-60    -> k_probabilities, k_block_sums (+ tree), k_sample
+//   init_zero_state_on_{first,other}_gpu     :62-96    -> cudaMemsetAsync + k_set_basis_state
+// The path is HBM-bound complex128 streaming work: no tensor cores by design.
+#include "kernels.h"
+
+namespace dvd {
+
+// =================================================================================================
+// Tiled multi-gate pass
+// =================================================================================================
+constexpr int OPS_CHUNK = 32;
+
+__device__ __forceinline__ void switch_stage(cplx* tile, cplx (&a)[NREG], int tid, int from, int to) {
+    __syncthreads();  // everybody finished reading the tile in the previous switch
+#pragma unroll
+    for (int j = 0; j < NREG; ++j) tile[swz(stage_idx(from, tid, j))] = a[j];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NREG; ++j) a[j] = tile[swz(stage_idx(to, tid, j))];
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_constant__ PassDesc pd) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* tile = reinterpret_cast<cplx*>(smem_raw);
+    __shared__ DevOp sops[OPS_CHUNK];
+
+    const int tid = threadIdx.x;
+    const uint64_t base = cta_base(pd, (uint64_t)blockIdx.x);
+    const uint64_t gbase = base | pd.rank_bits;
+
+    // global <-> register layout = IO_GROUP stage: lanes run over tile positions 0..4, i.e. over
+    // >= 128 contiguous bytes (tile positions 0..2 are always physical qubits 0..2)
+    const int tb_io = stage_idx(IO_GROUP, tid, 0);
+    cplx* p0 = amp + base + tile_offset(pd, tb_io);
+    uint64_t hs[REG_BITS];
+#pragma unroll
+    for (int k = 0; k < REG_BITS; ++k) hs[k] = 1ull << pd.tile_q[IO_GROUP * REG_BITS + k];
+
+    cplx a[NREG];
+#pragma unroll
+    for (int j = 0; j < NREG; ++j) {
+        uint64_t off = 0;
+#pragma unroll
+        for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += hs[k];
+        a[j] = p0[off];
+    }
+
+    int cur = IO_GROUP;
+    int tbase = tb_io;
+    for (int c0 = 0; c0 < pd.n_ops; c0 += OPS_CHUNK) {
+        const int n = min(OPS_CHUNK, pd.n_ops - c0);
+        __syncthreads();  // previous chunk fully consumed
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(ops + c0);
+            uint4* dst = reinterpret_cast<uint4*>(sops);
+            const int n16 = n * (int)(sizeof(DevOp) / 16);
+            for (int i = tid; i < n16; i += NTHREADS) dst[i] = src[i];
+        }
+        __syncthreads();
+        for (int k = 0; k < n; ++k) {
+            const DevOp& op = sops[k];
+            const int g = op.group;
+            if (g >= 0 && g != cur) {
+                switch_stage(tile, a, tid, cur, g);
+                cur = g;
+                tbase = stage_idx(g, tid, 0);
+            }
+            apply_op(a, op, cur, tbase, gbase);
+        }
+    }
+    if (cur != IO_GROUP) switch_stage(tile, a, tid, cur, IO_GROUP);
+
+#pragma unroll
+    for (int j = 0; j < NREG; ++j) {
+        uint64_t off = 0;
+#pragma unroll
+        for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += hs[k];
+        p0[off] = a[j];
+    }
+}
+
+// =================================================================================================
+// One gate per pass (small states, debug path)
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+k_simple_gate(cplx* __restrict__ amp, int n_local, uint64_t rank_bits, const __grid_constant__ DevOp op) {
+    const uint64_t n = 1ull << n_local;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = op.tbit, c = op.cbit;
+    if (t < n_local) {
+        const uint64_t pairs = n >> 1;
+        for (uint64_t k = gtid; k < pairs; k += stride) {
+            const uint64_t i0 = ((k >> t) << (t + 1)) | (k & ((1ull << t) - 1));
+            const uint64_t i1 = i0 | (1ull << t);
+            if (c >= 0 && !(((i0 | rank_bits) >> c) & 1ull)) continue;
+            const cplx x = amp[i0], y = amp[i1];
+            cplx nx, ny;
+            nx.x = x.x * op.m[0] - x.y * op.m[1] + y.x * op.m[2] - y.y * op.m[3];
+            nx.y = x.x * op.m[1] + x.y * op.m[0] + y.x * op.m[3] + y.y * op.m[2];
+            ny.x = x.x * op.m[4] - x.y * op.m[5] + y.x * op.m[6] - y.y * op.m[7];
+            ny.y = x.x * op.m[5] + x.y * op.m[4] + y.x * op.m[7] + y.y * op.m[6];
+            amp[i0] = nx; amp[i1] = ny;
+        }
+    } else {
+        // rank-index target: only diagonal gates get here; the whole chunk sees one matrix entry
+        const int bit = (int)((rank_bits >> t) & 1ull);
+        const double dr = bit ? op.m[6] : op.m[0], di = bit ? op.m[7] : op.m[1];
+        for (uint64_t i = gtid; i < n; i += stride) {
+            if (c >= 0 && !(((i | rank_bits) >> c) & 1ull)) continue;
+            amp[i] = cmul(amp[i], dr, di);
+        }
+    }
+}
+
+__global__ void k_set_basis_state(cplx* amp, uint64_t index) { amp[index] = cplx{1.0, 0.0}; }
+
+// =================================================================================================
+// Probabilities, pairwise summation tree, sampler
+// =================================================================================================
+// |a|^2 exactly as the reference computes it (norm_sqr = re*re + im*im, no contraction):
+// src/qubit_backend/circuit.rs:579-581
+__device__ __forceinline__ double norm_sqr(cplx a) { return __dadd_rn(__dmul_rn(a.x, a.x), __dmul_rn(a.y, a.y)); }
+
+__global__ void __launch_bounds__(256)
+k_probabilities(const cplx* __restrict__ amp, uint64_t first, uint64_t count, double* __restrict__ probs) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        probs[i] = norm_sqr(amp[first + i]);
+}
+
+// Level-BLK_BITS sums: one value per block of 1024 amplitudes, summed as a binary pairwise tree
+// (xor-butterfly == pairwise tree because fp addition is commutative).
+__global__ void __launch_bounds__(256)
+k_block_sums(const cplx* __restrict__ amp, uint64_t n_blocks, double* __restrict__ out) {
+    __shared__ double wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint64_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        const cplx* src = amp + (b << BLK_BITS);
+        double v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = norm_sqr(src[k * 256 + tid]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) v[k] = __dadd_rn(v[k], __shfl_xor_sync(0xffffffffu, v[k], off));
+            if (lane == 0) wsum[k * 8 + warp] = v[k];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double w = wsum[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) w = __dadd_rn(w, __shfl_xor_sync(0xffffffffu, w, off));
+            if (lane == 0) out[b] = w;
+        }
+        __syncthreads();
+    }
+}
+
+// Whole tree of a state smaller than one block (n_local < BLK_BITS): root only.
+__global__ void __launch_bounds__(256)
+k_small_root(const cplx* __restrict__ amp, int n_local, double* __restrict__ out) {
+    __shared__ double buf[2][1 << (BLK_BITS - 1)];
+    const int n = 1 << n_local;
+    if (n == 1) { if (threadIdx.x == 0) out[0] = norm_sqr(amp[0]); return; }
+    for (int j = threadIdx.x; j < n / 2; j += blockDim.x)
+        buf[0][j] = __dadd_rn(norm_sqr(amp[2 * j]), norm_sqr(amp[2 * j + 1]));
+    __syncthreads();
+    int cur = 0;
+    for (int cnt = n / 4; cnt >= 1; cnt >>= 1) {
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x)
+            buf[cur ^ 1][j] = __dadd_rn(buf[cur][2 * j], buf[cur][2 * j + 1]);
+        __syncthreads();
+        cur ^= 1;
+    }
+    if (threadIdx.x == 0) out[0] = buf[cur][0];
+}
+
+__global__ void __launch_bounds__(256)
+k_tree_level(const double* __restrict__ in, double* __restrict__ out, uint64_t cnt) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += stride)
+        out[j] = __dadd_rn(in[2 * j], in[2 * j + 1]);
+}
+
+uint64_t tree_level_offset(int n_local, int level) {
+    const int nb = n_local < BLK_BITS ? n_local : BLK_BITS;
+    uint64_t off = 0;
+    for (int l = nb; l < level; ++l) off += 1ull << (n_local - l);
+    return off;
+}
+uint64_t tree_size(int n_local) { return tree_level_offset(n_local, n_local) + 1; }
+
+struct TreeOffsets { uint64_t off[64]; };
+
+// One warp per shot.  Upper levels are read from the stored tree, the last nb levels are rebuilt
+// from the amplitudes of the one block the shot lands in (same pairwise order as k_block_sums).
+constexpr int SAMPLE_WARPS = 4;
+__global__ void __launch_bounds__(SAMPLE_WARPS * 32)
+k_sample(const cplx* __restrict__ amp, int n_local, int nb, const double* __restrict__ tree,
+         const __grid_constant__ TreeOffsets offs, const double* __restrict__ u,
+         const int32_t* __restrict__ sel, int32_t sel_value, uint64_t index_offset, uint64_t shots,
+         unsigned long long* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* lv = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (2ull << nb);
+    const double total = tree[offs.off[n_local]];
+    const uint64_t n_warps = (uint64_t)gridDim.x * SAMPLE_WARPS;
+    const int bn = 1 << nb;
+    for (uint64_t s = (uint64_t)blockIdx.x * SAMPLE_WARPS + warp; s < shots; s += n_warps) {
+        if (sel != nullptr && sel[s] != sel_value) continue;
+        const double xsi = __dmul_rn(u[s], total);
+        double basev = 0.0;
+        uint64_t j = 0;
+        for (int l = n_local; l > nb; --l) {
+            const double c = __dadd_rn(basev, tree[offs.off[l - 1] + 2 * j]);
+            if (xsi <= c) j = 2 * j; else { basev = c; j = 2 * j + 1; }
+        }
+        const cplx* src = amp + (j << nb);
+        for (int i = lane; i < bn; i += 32) lv[i] = norm_sqr(src[i]);
+        __syncwarp();
+        // level l of the block lives at lv + (2^(nb+1) - 2^(nb-l+1)), i.e. levels are packed back to back
+        int in_off = 0;
+        for (int l = 1; l <= nb; ++l) {
+            const int cnt = bn >> l;
+            const int out_off = in_off + (bn >> (l - 1));
+            for (int i = lane; i < cnt; i += 32) lv[out_off + i] = __dadd_rn(lv[in_off + 2 * i], lv[in_off + 2 * i + 1]);
+            __syncwarp();
+            in_off = out_off;
+        }
+        // in_off now points at level nb (one entry).  Walk back down.
+        uint32_t k = 0;
+        int lvl_off = in_off;
+        for (int l = nb; l >= 1; --l) {
+            lvl_off -= bn >> (l - 1);  // offset of level l-1
+            const double c = __dadd_rn(basev, lv[lvl_off + 2 * k]);
+            if (xsi <= c) k = 2 * k; else { basev = c; k = 2 * k + 1; }
+        }
+        if (lane == 0) out[s] = index_offset + (j << nb) + k;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_extract_expectation(const unsigned long long* __restrict__ samples, uint64_t shots, const int* __restrict__ qubits,
+                      int n_obs, double* __restrict__ out) {
+    const uint64_t total = shots * (uint64_t)n_obs;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const uint64_t s = e / n_obs;
+        const int o = (int)(e - s * n_obs);
+        out[e] = ((samples[s] >> qubits[o]) & 1ull) ? -1.0 : 1.0;   // circuit.rs:503-508
+    }
+}
+
+// =================================================================================================
+// Exact <Z_q> (extension): warp-shuffle + block reduction, deterministic second stage
+// =================================================================================================
+constexpr int EZ_CTAS = 148 * 4;
+constexpr int EZ_Q = 64;
+uint64_t ez_partial_size() { return (uint64_t)EZ_CTAS * EZ_Q; }
+
+__global__ void __launch_bounds__(256)
+k_expect_z_partial(const cplx* __restrict__ amp, int n_local, double* __restrict__ partial) {
+    __shared__ double red[8][33];
+    double acc[33];
+#pragma unroll
+    for (int q = 0; q < 33; ++q) acc[q] = 0.0;
+    const uint64_t n = 1ull << n_local;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double p = norm_sqr(amp[i]);
+        acc[32] += p;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) acc[q] += ((i >> q) & 1ull) ? -p : p;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 33; ++q) {
+        double v = acc[q];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) red[warp][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 33) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        partial[(uint64_t)blockIdx.x * EZ_Q + threadIdx.x] = v;
+    }
+}
+
+__global__ void k_expect_z_final(const double* __restrict__ partial, int n_ctas, int n_local, int n_total,
+                                 uint64_t rank_bits, double* __restrict__ out) {
+    const int q = threadIdx.x;
+    if (q >= n_total) return;
+    const int src = q < n_local ? q : 32;
+    double v = 0.0;
+    for (int c = 0; c < n_ctas; ++c) v += partial[(uint64_t)c * EZ_Q + src];
+    if (q >= n_local && ((rank_bits >> q) & 1ull)) v = -v;
+    out[q] = v;
+}
+
+// =================================================================================================
+// Swap staging and dot product
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+k_pack_half(const cplx* __restrict__ amp, int lq, int bitval, uint64_t first, uint64_t count, cplx* __restrict__ buf) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride)
+        buf[e] = amp[half_index(first + e, lq, bitval)];
+}
+__global__ void __launch_bounds__(256)
+k_unpack_half(cplx* __restrict__ amp, int lq, int bitval, uint64_t first, uint64_t count, const cplx* __restrict__ buf) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride)
+        amp[half_index(first + e, lq, bitval)] = buf[e];
+}
+
+constexpr int DOT_CTAS = 148 * 4;
+__global__ void __launch_bounds__(256)
+k_dot_partial(const cplx* __restrict__ a, const cplx* __restrict__ b, uint64_t count, double* __restrict__ partial) {
+    __shared__ double red[8][2];
+    double re = 0.0, im = 0.0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const cplx x = a[i], y = b[i];      // conj(x) * y
+        re += x.x * y.x + x.y * y.y;
+        im += x.x * y.y - x.y * y.x;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        re += __shfl_xor_sync(0xffffffffu, re, off);
+        im += __shfl_xor_sync(0xffffffffu, im, off);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[warp][0] = re; red[warp][1] = im; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0.0, m = 0.0;
+        for (int w = 0; w < 8; ++w) { r += red[w][0]; m += red[w][1]; }
+        partial[2 * blockIdx.x] = r; partial[2 * blockIdx.x + 1] = m;
+    }
+}
+__global__ void k_dot_final(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    double r = 0.0, m = 0.0;
+    for (int c = 0; c < n; ++c) { r += partial[2 * c]; m += partial[2 * c + 1]; }
+    out[0] = r; out[1] = m;
+}
+
+// =================================================================================================
+// Launchers
+// =================================================================================================
+static inline unsigned grid_for(uint64_t work_items, int per_cta, unsigned cap) {
+    uint64_t g = (work_items + per_cta - 1) / per_cta;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (unsigned)g;
+}
+constexpr unsigned STREAM_CAP = 148 * 32;  // grid-stride kernels: a multiple of the SM count
+
+cudaError_t kernels_init() {
+    cudaError_t e = cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TILE_AMPS * (int)sizeof(cplx));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                SAMPLE_WARPS * (2 << BLK_BITS) * (int)sizeof(double));
+}
+
+cudaError_t launch_tile_pass(cplx* amp, const DevOp* ops, const PassDesc& pd, cudaStream_t s) {
+    const uint64_t ctas = 1ull << (pd.n_local - TILE_BITS);
+    k_tile_pass<<<(unsigned)ctas, NTHREADS, TILE_AMPS * sizeof(cplx), s>>>(amp, ops, pd);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_simple_gate(cplx* amp, int n_local, uint64_t rank_bits, const DevOp& op, cudaStream_t s) {
+    const uint64_t items = op.tbit < n_local ? (1ull << n_local) / 2 : (1ull << n_local);
+    k_simple_gate<<<grid_for(items, 256, STREAM_CAP), 256, 0, s>>>(amp, n_local, rank_bits, op);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_set_basis_state(cplx* amp, uint64_t index, cudaStream_t s) {
+    k_set_basis_state<<<1, 1, 0, s>>>(amp, index);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_probabilities(const cplx* amp, uint64_t first, uint64_t count, double* probs, cudaStream_t s) {
+    if (count == 0) return cudaSuccess;
+    k_probabilities<<<grid_for(count, 256, STREAM_CAP), 256, 0, s>>>(amp, first, count, probs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_tree(const cplx* amp, int n_local, double* tree, cudaStream_t s) {
+    if (n_local < BLK_BITS) {
+        k_small_root<<<1, 256, 0, s>>>(amp, n_local, tree);
+        return cudaGetLastError();
+    }
+    const uint64_t n_blocks = 1ull << (n_local - BLK_BITS);
+    k_block_sums<<<grid_for(n_blocks, 1, 148 * 8 * 4), 256, 0, s>>>(amp, n_blocks, tree);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    for (int l = BLK_BITS + 1; l <= n_local; ++l) {
+        const uint64_t cnt = 1ull << (n_local - l);
+        k_tree_level<<<grid_for(cnt, 256, STREAM_CAP), 256, 0, s>>>(tree + tree_level_offset(n_local, l - 1),
+                                                                  tree + tree_level_offset(n_local, l), cnt);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_sample(const cplx* amp, int n_local, const double* tree, const double* u,
+                          const int32_t* sel, int32_t sel_value, uint64_t index_offset,
+                          uint64_t shots, unsigned long long* out, cudaStream_t s) {
+    if (shots == 0) return cudaSuccess;
+    const int nb = n_local < BLK_BITS ? n_local : BLK_BITS;
+    TreeOffsets offs;
+    for (int l = 0; l < 64; ++l) offs.off[l] = (l >= nb && l <= n_local) ? tree_level_offset(n_local, l) : 0;
+    const size_t smem = (size_t)SAMPLE_WARPS * (2ull << nb) * sizeof(double);
+    k_sample<<<grid_for(shots, SAMPLE_WARPS, 148 * 3), SAMPLE_WARPS * 32, smem, s>>>(
+        amp, n_local, nb, tree, offs, u, sel, sel_value, index_offset, shots, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_extract_expectation(const unsigned long long* samples, uint64_t shots, const int* qubits,
+                                       int n_obs, double* out, cudaStream_t s) {
+    const uint64_t total = shots * (uint64_t)n_obs;
+    if (total == 0) return cudaSuccess;
+    k_extract_expectation<<<grid_for(total, 256, STREAM_CAP), 256, 0, s>>>(samples, shots, qubits, n_obs, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_expectation_z(const cplx* amp, int n_local, int n_total, uint64_t rank_bits,
+                                 double* partial, double* out, cudaStream_t s) {
+    const int ctas = (int)grid_for(1ull << n_local, 256, EZ_CTAS);
+    k_expect_z_partial<<<ctas, 256, 0, s>>>(amp, n_local, partial);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_expect_z_final<<<1, 64, 0, s>>>(partial, ctas, n_local, n_total, rank_bits, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_half(const cplx* amp, int lq, int bitval, uint64_t first, uint64_t count, cplx* buf, cudaStream_t s) {
+    if (count == 0) return cudaSuccess;
+    k_pack_half<<<grid_for(count, 256, STREAM_CAP), 256, 0, s>>>(amp, lq, bitval, first, count, buf);
+    return cudaGetLastError();
+}
+cudaError_t launch_unpack_half(cplx* amp, int lq, int bitval, uint64_t first, uint64_t count, const cplx* buf, cudaStream_t s) {
+    if (count == 0) return cudaSuccess;
+    k_unpack_half<<<grid_for(count, 256, STREAM_CAP), 256, 0, s>>>(amp, lq, bitval, first, count, buf);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dot(const cplx* a, const cplx* b, uint64_t count, double* partial, double* out, cudaStream_t s) {
+    const int ctas = (int)grid_for(count, 256, DOT_CTAS);
+    k_dot_partial<<<ctas, 256, 0, s>>>(a, b, count, partial);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_dot_final<<<1, 1, 0, s>>>(partial, ctas, out);
+    return cudaGetLastError();
+}
+
+}  // namespace dvd

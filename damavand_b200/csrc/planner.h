@@ -1,0 +1,65 @@
+// planner.h -- host-side gate scheduler (pure C++, no CUDA calls).
+//
+// Takes the reference's per-gate stream (one FFI call per gate in
+// /root/reference/src/qubit_backend/circuit.rs:346-368) and turns it into a short list of passes
+// over HBM.  Three levels:
+//   1. distributed level (plan_distributed): logical->physical qubit map, global<->local qubit
+//      swaps replacing the reference's per-gate full-chunk exchange
+//      (src/qubit_backend/circuit_distributed_gpu.rs:40-147);
+//   2. pass level (plan_local): choose TILE_BITS physical qubits per pass and pull every gate that
+//      commutes its way to the front and fits the tile;
+//   3. stage level: order the gates of a pass so that consecutive gates share a register group.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "tile_core.cuh"
+
+namespace dvd {
+
+struct HostGate {
+    int target;     // qubit index (logical on input to plan_distributed, physical for plan_local)
+    int control;    // -1 = none
+    double m[8];    // row-major complex 2x2
+    int gate_idx;   // caller's index
+};
+
+struct Pass {
+    PassDesc desc;
+    std::vector<DevOp> ops;
+    int n_switches = 0;        // stage switches inside the pass (shared-memory transposes)
+    int n_controlled = 0;
+};
+
+struct PlanOptions {
+    int min_low = 3;           // tile always contains physical qubits [0, min_low): 128 B segments
+    int window = 16384;        // look-ahead (gates) when filling a pass
+    int max_ops_per_pass = 1 << 20;
+};
+
+// Classify a 2x2 by exact zero / one tests on its entries.
+void classify_gate(const double m[8], int32_t* kind, int8_t* d0_is_one);
+inline bool is_diagonal(const double m[8]) { return m[2] == 0.0 && m[3] == 0.0 && m[4] == 0.0 && m[5] == 0.0; }
+
+// Plan gates that are all executable locally: every non-diagonal gate has target < n_local.
+// Qubits >= n_local (rank-index qubits) may appear as controls or as targets of diagonal gates.
+// Requires n_local >= TILE_BITS.
+std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, int n_total,
+                             const PlanOptions& opt);
+
+// ---- distributed level ---------------------------------------------------------------------------
+struct DistStep {
+    enum Kind { LOCAL_GATES = 0, GLOBAL_SWAP = 1 } kind;
+    // LOCAL_GATES: gates rewritten to physical qubits, all locally executable
+    std::vector<HostGate> gates;
+    // GLOBAL_SWAP: exchange physical global qubit `gq` (>= n_local) with physical local qubit `lq`
+    int gq = -1, lq = -1;
+};
+
+// perm[logical] = physical, updated in place.  When `restore_identity` is set, trailing swaps bring
+// the layout back to perm[q] = q (needed before measure / sample / readback, whose semantics are
+// defined on the reference's contiguous-chunk layout, circuit.rs:135-136).
+std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n_total, int n_local,
+                                       std::vector<int>& perm, bool restore_identity);
+
+}  // namespace dvd

@@ -1,0 +1,150 @@
+// emu.cpp -- CPU replay of the CUDA tile kernel and of the distributed swap schedule.
+//
+// TEST INFRASTRUCTURE ONLY (there is no GPU in the build container).  It includes the very same
+// __host__ __device__ header the kernel is built from (damavand_b200/csrc/tile_core.cuh) and the
+// real planner, and replays k_tile_pass thread by thread: same index arithmetic, same swizzle,
+// same op decoding.  It cannot catch missing __syncthreads, but it does catch planner, commutation,
+// tile-layout, stage-switch and control/target decoding bugs before a GPU is involved.
+// Never loaded by the product.
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+#include "../../damavand_b200/csrc/planner.cpp"
+#include "../../include/damavand_b200.h"
+
+using namespace dvd;
+
+static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
+    PassDesc pd = pass.desc;
+    pd.rank_bits = rank_bits;
+    const uint64_t ctas = 1ull << (pd.n_local - TILE_BITS);
+    std::vector<cplx> tile(TILE_AMPS);
+    static cplx regs[NTHREADS][NREG];
+    for (uint64_t cta = 0; cta < ctas; ++cta) {
+        const uint64_t base = cta_base(pd, cta);
+        const uint64_t gbase = base | pd.rank_bits;
+        for (int tid = 0; tid < NTHREADS; ++tid)
+            for (int j = 0; j < NREG; ++j) regs[tid][j] = amp[base + tile_offset(pd, stage_idx(IO_GROUP, tid, j))];
+        int cur = IO_GROUP;
+        auto do_switch = [&](int to) {
+            for (int tid = 0; tid < NTHREADS; ++tid)
+                for (int j = 0; j < NREG; ++j) tile[swz(stage_idx(cur, tid, j))] = regs[tid][j];
+            for (int tid = 0; tid < NTHREADS; ++tid)
+                for (int j = 0; j < NREG; ++j) regs[tid][j] = tile[swz(stage_idx(to, tid, j))];
+            cur = to;
+        };
+        for (const DevOp& op : pass.ops) {
+            if (op.group >= 0 && op.group != cur) do_switch(op.group);
+            if (op.kind != K_DIAG && (op.tpos < 0 || (op.tpos >> 2) != cur)) throw std::runtime_error("emu: op not in its register group");
+            for (int tid = 0; tid < NTHREADS; ++tid) apply_op(regs[tid], op, cur, stage_idx(cur, tid, 0), gbase);
+        }
+        if (cur != IO_GROUP) do_switch(IO_GROUP);
+        for (int tid = 0; tid < NTHREADS; ++tid)
+            for (int j = 0; j < NREG; ++j) amp[base + tile_offset(pd, stage_idx(IO_GROUP, tid, j))] = regs[tid][j];
+    }
+}
+
+static void run_simple(cplx* amp, int n_local, uint64_t rank_bits, const HostGate& g) {
+    const uint64_t n = 1ull << n_local;
+    const int t = g.target, c = g.control;
+    if (t < n_local) {
+        for (uint64_t k = 0; k < n / 2; ++k) {
+            const uint64_t i0 = ((k >> t) << (t + 1)) | (k & ((1ull << t) - 1)), i1 = i0 | (1ull << t);
+            if (c >= 0 && !(((i0 | rank_bits) >> c) & 1ull)) continue;
+            const cplx x = amp[i0], y = amp[i1];
+            amp[i0] = cplx{x.x * g.m[0] - x.y * g.m[1] + y.x * g.m[2] - y.y * g.m[3], x.x * g.m[1] + x.y * g.m[0] + y.x * g.m[3] + y.y * g.m[2]};
+            amp[i1] = cplx{x.x * g.m[4] - x.y * g.m[5] + y.x * g.m[6] - y.y * g.m[7], x.x * g.m[5] + x.y * g.m[4] + y.x * g.m[7] + y.y * g.m[6]};
+        }
+    } else {
+        const int bit = (int)((rank_bits >> t) & 1ull);
+        for (uint64_t i = 0; i < n; ++i) {
+            if (c >= 0 && !(((i | rank_bits) >> c) & 1ull)) continue;
+            amp[i] = cmul(amp[i], bit ? g.m[6] : g.m[0], bit ? g.m[7] : g.m[1]);
+        }
+    }
+}
+
+static std::vector<HostGate> conv(const dvd_gate* gates, int64_t n) {
+    std::vector<HostGate> v((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        v[i].target = gates[i].target; v[i].control = gates[i].control; v[i].gate_idx = (int)i;
+        std::memcpy(v[i].m, gates[i].m, sizeof v[i].m);
+    }
+    return v;
+}
+
+extern "C" {
+
+// Whole state on `world` emulated ranks (world = 1: single GPU).  state: 2^n interleaved complex128,
+// rank r's chunk is the contiguous slice r.  Returns 0, or -1 on planner error (message via emu_error).
+static std::string g_err;
+const char* emu_error() { return g_err.c_str(); }
+
+int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, double* state, int64_t* stats /*[4]*/) {
+    try {
+        int g = 0; while ((1 << g) < world) ++g;
+        const int n_local = n_qubits - g;
+        const uint64_t chunk = 1ull << n_local;
+        cplx* amp = reinterpret_cast<cplx*>(state);
+        std::vector<int> perm(n_qubits);
+        for (int q = 0; q < n_qubits; ++q) perm[q] = q;
+        std::vector<DistStep> steps;
+        std::vector<HostGate> hg = conv(gates, n_gates);
+        if (world > 1) steps = plan_distributed(hg, n_qubits, n_local, perm, true);
+        else { DistStep st; st.kind = DistStep::LOCAL_GATES; st.gates = hg; steps.push_back(st); }
+        for (int q = 0; q < n_qubits; ++q) if (perm[q] != q) throw std::runtime_error("emu: layout not restored");
+        int64_t n_pass = 0, n_swap = 0, n_switch = 0, n_ops = 0;
+        PlanOptions opt;
+        for (auto& st : steps) {
+            if (st.kind == DistStep::GLOBAL_SWAP) {
+                ++n_swap;
+                const int j = st.gq - n_local;
+                if (st.gq < n_local || st.gq >= n_qubits || st.lq < 0 || st.lq >= n_local) throw std::runtime_error("emu: bad swap");
+                for (int r = 0; r < world; ++r) {
+                    const int b = (r >> j) & 1, partner = r ^ (1 << j);
+                    if (partner < r) continue;
+                    // rank r sends its half with bit lq == 1-b; partner sends its half with bit lq == b
+                    for (uint64_t h = 0; h < chunk / 2; ++h) {
+                        cplx& mine = amp[(uint64_t)r * chunk + half_index(h, st.lq, 1 - b)];
+                        cplx& theirs = amp[(uint64_t)partner * chunk + half_index(h, st.lq, b)];
+                        std::swap(mine, theirs);
+                    }
+                }
+                continue;
+            }
+            if (n_local >= TILE_BITS) {
+                std::vector<Pass> passes = plan_local(st.gates, n_local, n_qubits, opt);
+                for (auto& p : passes) { ++n_pass; n_switch += p.n_switches; n_ops += (int64_t)p.ops.size(); }
+                for (int r = 0; r < world; ++r)
+                    for (auto& p : passes) run_pass(amp + (uint64_t)r * chunk, p, (uint64_t)r << n_local);
+            } else {
+                for (int r = 0; r < world; ++r)
+                    for (auto& gte : st.gates) run_simple(amp + (uint64_t)r * chunk, n_local, (uint64_t)r << n_local, gte);
+                n_ops += (int64_t)st.gates.size();
+            }
+        }
+        if (stats) { stats[0] = n_pass; stats[1] = n_swap; stats[2] = n_switch; stats[3] = n_ops; }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// shared-memory bank check of the three stage layouts: returns the worst conflict degree of a
+// quarter-warp (8 lanes x 16 B) over all stages and registers; 1 = conflict free.
+int emu_max_bank_conflict() {
+    int worst = 0;
+    for (int g = 0; g < NGROUPS; ++g)
+        for (int j = 0; j < NREG; ++j)
+            for (int q0 = 0; q0 < NTHREADS; q0 += 8) {
+                int cnt[8] = {0};
+                for (int l = 0; l < 8; ++l) cnt[swz(stage_idx(g, q0 + l, j)) & 7]++;
+                for (int b = 0; b < 8; ++b) worst = cnt[b] > worst ? cnt[b] : worst;
+            }
+    return worst;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+"""Shared helpers for the parity tests (test infrastructure; may use oracle/)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from damavand_b200 import _lib, gates as pgates
+from oracle.oracle import OracleCircuit
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_LIB = os.path.join(EMU_DIR, "libdvd_emu.so")
+_emu = None
+
+
+class Recorder:
+    """Records add_* calls so the same circuit can be replayed on several backends."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        if name.startswith("add_"):
+            def f(*a):
+                self.calls.append((name, a))
+            return f
+        raise AttributeError(name)
+
+    def replay(self, circ):
+        for name, a in self.calls:
+            getattr(circ, name)(*a)
+        return circ
+
+
+def gate_array(circ):
+    """(ctypes Gate array, n) of a circuit object exposing .gates/.observables in oracle format."""
+    obs = set(circ.observables)
+    todo = [g for i, g in enumerate(circ.gates) if i not in obs]
+    arr = (_lib.Gate * max(1, len(todo)))()
+    for k, g in enumerate(todo):
+        arr[k].target = g.target
+        arr[k].control = -1 if g.control is None else g.control
+        arr[k].m[:] = pgates.matrix(g.name, g.parameter)
+    return arr, len(todo)
+
+
+def emu():
+    global _emu
+    if _emu is None:
+        src = os.path.join(EMU_DIR, "emu.cpp")
+        deps = [src] + [os.path.join(ROOT, "damavand_b200", "csrc", f) for f in ("planner.cpp", "planner.h", "tile_core.cuh")]
+        if not os.path.exists(EMU_LIB) or any(os.path.getmtime(d) > os.path.getmtime(EMU_LIB) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", EMU_LIB, src])
+        L = ctypes.CDLL(EMU_LIB)
+        L.emu_run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(_lib.Gate), ctypes.c_int64,
+                              ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
+        L.emu_run.restype = ctypes.c_int
+        L.emu_error.restype = ctypes.c_char_p
+        L.emu_max_bank_conflict.restype = ctypes.c_int
+        _emu = L
+    return _emu
+
+
+def emu_run(oracle_circ: OracleCircuit, world: int = 1, state=None):
+    """Run the recorded gates of `oracle_circ` through the CPU replay of the CUDA path."""
+    n = oracle_circ.num_qubits
+    arr, ng = gate_array(oracle_circ)
+    if state is None:
+        state = np.zeros(2 << n, dtype=np.float64)
+        state[0] = 1.0
+    stats = (ctypes.c_int64 * 4)()
+    rc = emu().emu_run(n, world, arr, ng, state.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stats)
+    if rc != 0:
+        raise RuntimeError(emu().emu_error().decode())
+    return state.view(np.complex128), dict(passes=stats[0], swaps=stats[1], switches=stats[2], ops=stats[3])
+
+
+def rel_err(a: np.ndarray, b: np.ndarray) -> float:
+    """max |a-b| relative to the largest magnitude (amplitudes of a normalised state)."""
+    scale = max(np.abs(b).max(), 1e-300)
+    return float(np.abs(a - b).max() / scale)

@@ -1,0 +1,108 @@
+"""Planner + tile-kernel logic, replayed on the CPU (tests/emu) against the oracle.
+
+No GPU here: the replay includes the same tile_core.cuh the CUDA kernel is compiled from and the
+real planner, so a failure means the CUDA path would be wrong too."""
+import numpy as np
+import pytest
+
+from damavand_b200 import circuits
+from oracle.oracle import OracleCircuit
+from tests.helpers import emu, emu_run, rel_err
+
+TOL = 1e-12
+
+
+def _check(circ: OracleCircuit, world=1):
+    got, stats = emu_run(circ, world)
+    circ.forward()
+    assert rel_err(got, circ.amplitudes()) < TOL
+    return stats
+
+
+def test_bank_conflict_free_layouts():
+    assert emu().emu_max_bank_conflict() == 1
+
+
+def test_golden_vector_small_state():
+    c = OracleCircuit(2); c.add_hadamard_gate(0); c.add_hadamard_gate(1); c.add_cnot_gate(0, 1)
+    got, _ = emu_run(c)
+    assert np.abs(got - 0.5).max() < 1e-15
+
+
+@pytest.mark.parametrize("n", [12, 14])
+def test_every_target_every_control(n):
+    # a dense prefix so that every amplitude is non-zero and distinct, then ONE gate under test
+    for t in range(n):
+        for c in [None] + [q for q in range(n) if q != t]:
+            circ = OracleCircuit(n)
+            for q in range(n):
+                circ.add_rotation_y_gate(q, 0.3 + 0.11 * q); circ.add_rotation_z_gate(q, 0.2 + 0.07 * q)
+            if c is None:
+                circ.add_rotation_x_gate(t, 1.234)
+            else:
+                circ.add_cnot_gate(c, t)
+            circ.add_rotation_z_gate((t + 1) % n, 0.5)      # a diagonal gate after it
+            _check(circ)
+
+
+@pytest.mark.parametrize("kind", ["H", "X", "Y", "Z", "RX", "RY", "RZ", "S", "T"])
+def test_every_gate_kind_every_position(kind):
+    n = 13
+    for t in range(n):
+        circ = OracleCircuit(n)
+        for q in range(n):
+            circ.add_rotation_y_gate(q, 0.4 + 0.1 * q)
+        add = {"H": lambda: circ.add_hadamard_gate(t), "X": lambda: circ.add_pauli_x_gate(t, False),
+               "Y": lambda: circ.add_pauli_y_gate(t, False), "Z": lambda: circ.add_pauli_z_gate(t, False),
+               "RX": lambda: circ.add_rotation_x_gate(t, 0.77), "RY": lambda: circ.add_rotation_y_gate(t, 0.77),
+               "RZ": lambda: circ.add_rotation_z_gate(t, 0.77),
+               "S": lambda: circ.gates.append(__import__("oracle.oracle", fromlist=["_Gate"])._Gate("S", t)),
+               "T": lambda: circ.gates.append(__import__("oracle.oracle", fromlist=["_Gate"])._Gate("T", t))}[kind]
+        add()
+        _check(circ)
+
+
+@pytest.mark.parametrize("n,gates,seed", [(12, 300, 1), (13, 400, 2), (15, 500, 3), (16, 300, 4)])
+def test_random_circuits(n, gates, seed):
+    circ = OracleCircuit(n)
+    circuits.random_circuit(circ, n, gates, seed)
+    stats = _check(circ)
+    assert stats["ops"] == gates and stats["passes"] < gates
+
+
+def test_workload_shapes_small():
+    c = OracleCircuit(13); g = circuits.qft_like(c, 13); s = _check(c)
+    assert s["ops"] == g and s["passes"] <= 4
+    c = OracleCircuit(14); g = circuits.hea(c, 14, 6); s = _check(c)
+    assert s["ops"] == g
+    c = OracleCircuit(12); g = circuits.layered(c, 12, 3); s = _check(c)
+    assert s["ops"] == g
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("n", [15, 16])
+def test_distributed_replay(world, n):
+    circ = OracleCircuit(n)
+    circuits.random_circuit(circ, n, 200, seed=10 + world)
+    stats = _check(circ, world)
+    assert stats["swaps"] >= 1          # gates on rank-index qubits force exchanges
+    circ = OracleCircuit(n); circuits.qft_like(circ, n); _check(circ, world)
+    circ = OracleCircuit(n); circuits.hea(circ, n, 3); _check(circ, world)
+
+
+def test_distributed_small_chunks_use_simple_kernel():
+    circ = OracleCircuit(8)
+    circuits.random_circuit(circ, 8, 120, seed=3)
+    _check(circ, 4)      # n_local = 6 < TILE_BITS
+    circ = OracleCircuit(13)
+    circuits.random_circuit(circ, 13, 120, seed=4)
+    _check(circ, 8)      # n_local = 10
+
+
+def test_forward_twice_accumulates():
+    c = OracleCircuit(12); circuits.random_circuit(c, 12, 50, 9)
+    st, _ = emu_run(c)
+    flat = np.ascontiguousarray(st).view(np.float64).copy()
+    st2, _ = emu_run(c, state=flat)
+    c.forward(); c.forward()
+    assert rel_err(st2, c.amplitudes()) < TOL
