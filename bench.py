@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the statevector hot path (BASELINE.json `metric`).
+
+    python bench.py --gpus 1 --steps K --warmup W          # 30-qubit QFT-style circuit, 1 GPU (cfg 3)
+    torchrun ... bench.py --gpus N --steps K --warmup W    # 32-qubit random circuit, strong scaling (cfg 4)
+    python bench.py --impl reference ...                   # the CPU `multithreading` path (oracle port)
+
+A step = one pass of the hot path over one circuit: reset to |0..0>, apply every gate (forward).
+`value` = gates/s with everything resident in HBM, timed with CUDA events on the engine's stream.
+`e2e`  = the same metric through the public Python API with host buffers: gate list in (H2D),
+forward, 1000-shot sample and expectation values out (D2H).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+WORKLOAD_DESC = {
+    "qft30": "30-qubit QFT-style circuit (H + RZ/CNOT/RZ/CNOT/RZ controlled-phase decomposition, target-major), 2205 gates, 16 GiB fp64 state",
+    "hea28": "28-qubit hardware-efficient ansatz, 50 layers (RY,RZ + CNOT chain), 4150 gates, 4 GiB",
+    "random32": "32-qubit random circuit over {H,RX,RY,RZ,CNOT}, 640 gates, 64 GiB total (strong scaling)",
+    "hea34": "34-qubit hardware-efficient ansatz, 10 layers, 1010 gates, 256 GiB total",
+    "layered20": "20-qubit layered circuit (H + RX/RY/RZ + CNOT ring, 10 layers), 1000 gates",
+}
+WORKLOAD_QUBITS = {"qft30": 30, "hea28": 28, "random32": 32, "hea34": 34, "layered20": 20}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+        except Exception:
+            return out
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for k, name in enumerate(names):
+                if r[5 + k].strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def build_workload(circ, name):
+    from damavand_b200 import circuits
+    return circuits.WORKLOADS[name](circ)
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's restatement of the reference `multithreading` method on a bounded sample
+# --------------------------------------------------------------------------------------------------
+def cpu_sample_gates(name: str, n: int, mem_gib: float):
+    """Pick the qubit count the host can hold (state + clone = 32 B/amp) and the gates per step."""
+    need = 32.0 * (1 << n) / 2**30
+    n_cpu = n
+    while need + 4 > mem_gib and n_cpu > 20:
+        n_cpu -= 1
+        need /= 2
+    return n_cpu
+
+
+def host_mem_gib():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return float(line.split()[1]) / 2**20
+    except Exception:
+        pass
+    return 16.0
+
+
+def run_cpu(name: str, steps: int, warmup: int, gates_per_step: int):
+    """Time the CPU path: `steps` steps of `gates_per_step` consecutive gates of the workload's circuit.
+    Returns (gates_per_sec, seconds_per_step, description, cores)."""
+    from oracle.oracle import OracleCircuit
+    from damavand_b200 import circuits
+    n = WORKLOAD_QUBITS[name]
+    n_cpu = cpu_sample_gates(name, n, host_mem_gib())
+    o = OracleCircuit(n_cpu)
+    if n_cpu == n:
+        circuits.WORKLOADS[name](o)
+    else:   # same generator, fewer qubits (host RAM cannot hold state + clone)
+        gen = {"qft30": lambda c: circuits.qft_like(c, n_cpu), "hea28": lambda c: circuits.hea(c, n_cpu, 50),
+               "random32": lambda c: circuits.random_circuit(c, n_cpu, 640), "hea34": lambda c: circuits.hea(c, n_cpu, 10),
+               "layered20": lambda c: circuits.layered(c, n_cpu, 10)}[name]
+        gen(o)
+    all_gates = [g for i, g in enumerate(o.gates) if i not in set(o.observables)]
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    total_needed = (steps + warmup) * gates_per_step
+    # cycle through the circuit's gates in order
+    times = []
+    k = 0
+    for s in range(steps + warmup):
+        o.gates = [all_gates[(k + i) % len(all_gates)] for i in range(gates_per_step)]
+        o.observables = []
+        k += gates_per_step
+        t0 = time.perf_counter()
+        o.forward()
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    sec = float(np.sum(times))
+    gps = steps * gates_per_step / sec
+    scale = "" if n_cpu == n else f" at {n_cpu} qubits (host RAM cannot hold the {n}-qubit state + clone)"
+    desc = (f"{steps} steps x {gates_per_step} consecutive gates of the {name} circuit{scale}, "
+            f"oracle port of circuit_multithreading.rs:9-54 (clone + per-amplitude update), OpenMP {cores} threads")
+    return gps, sec / steps, desc, cores, n_cpu
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    name = args.workload or ("qft30" if args.gpus == 1 else "random32")
+    n = WORKLOAD_QUBITS[name]
+    gates_per_step = args.cpu_gates_per_step or (2 if n >= 30 else 4 if n >= 28 else 50)
+    gps, sec_step, desc, cores, n_cpu = run_cpu(name, args.steps, args.warmup, gates_per_step)
+    line = {
+        "impl": "reference", "metric": "gates_per_sec", "value": gps, "unit": "gates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_step * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{name}: {WORKLOAD_DESC[name]}", "cpu_qubits": n_cpu, "gates_per_step": gates_per_step},
+        "cpu_baseline": {"value": gps, "unit": "gates/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": gps, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOAD_DESC))
+    ap.add_argument("--cpu-gates-per-step", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="one kernel per gate (no fusion) for comparison")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    from damavand_b200 import Circuit, distributed
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks"}))
+            return 2
+    rank = int(os.environ.get("RANK", "0"))
+    name = args.workload or ("qft30" if args.gpus == 1 else "random32")
+    n = WORKLOAD_QUBITS[name]
+    method = "gpu" if args.gpus == 1 else "distributed_gpu"
+    if args.gpus > 1:
+        import torch
+        import torch.distributed as dist
+        distributed.initialize("nccl")
+
+    circ = Circuit(n, method)
+    if args.unfused:
+        circ.set_unfused(True)
+    n_gates = build_workload(circ, name)
+    n_obs_gates = len(circ.observables)
+    device = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def barrier():
+        if args.gpus > 1:
+            import torch
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+        circ.synchronize()
+
+    def one_step():
+        circ.reset_amplitudes()
+        circ.forward_async()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    circ.stats_reset()
+    sampler = ClockSampler(device)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    circ.timer_begin()
+    for _ in range(args.steps):
+        one_step()
+    ms = circ.timer_end()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    st = circ.stats()
+    if args.gpus > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sec = ms / 1e3
+    value = args.steps * n_gates / sec
+
+    # forward-only timing for the roofline of the dominant kernel (k_tile_pass): one circuit, events around
+    # the passes only (the reset memset is outside)
+    circ.reset_amplitudes(); circ.synchronize()
+    circ.stats_reset()
+    barrier()
+    circ.timer_begin()
+    circ.forward_async()
+    fwd_ms = circ.timer_end()
+    st1 = circ.stats()
+    launches_fwd = st1["tile_passes"] + st1["simple_passes"]
+    peak, peak_src, _ = measured_peaks()
+    # algorithmic bytes per launch of the pass kernel: read + write of every local amplitude once
+    n_local = n - int(np.log2(args.gpus))
+    pass_bytes = 32.0 * (1 << n_local)
+    roofline = None
+    if launches_fwd > 0 and st1["global_swaps"] == 0:
+        achieved = st1["pass_bytes"] / (fwd_ms / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_tile_pass" if st1["tile_passes"] else "k_simple_gate",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src,
+                    "launches_per_circuit": launches_fwd, "avg_launch_ms": fwd_ms / launches_fwd,
+                    "algorithmic_bytes_per_launch": st1["pass_bytes"] / launches_fwd,
+                    "effective_gate_gbs": st1["gate_algorithmic_bytes"] / (fwd_ms / 1e3) / 1e9,
+                    "note": "achieved = (launches x 32 B x 2^n_local) / CUDA-event time of one forward; "
+                            "effective_gate_gbs counts 32*2^n B per gate (16*2^n if controlled) and exceeds the "
+                            "HBM peak because several gates share one pass"}
+    elif launches_fwd > 0:
+        achieved = st1["pass_bytes"] / (fwd_ms / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_tile_pass + NVLink swaps", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "global_swaps": st1["global_swaps"], "swap_bytes_sent_per_rank": st1["swap_bytes_sent"],
+                    "note": "forward time includes the NVLink exchanges; HBM fraction of the whole forward"}
+
+    # e2e through the public API with host buffers: gates in, samples + expectation values out
+    e2e = None
+    if not args.no_e2e:
+        shots = 1000
+        if not circ.observables:
+            for q in range(n):
+                circ.add_pauli_z_gate(q, True)
+        per_shot = 2 if args.gpus > 1 else 1
+        u = np.random.default_rng(1235).random(shots * per_shot)
+        k_e2e = max(1, min(args.steps, 3))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            circ.reset_amplitudes()
+            circ.forward()
+            s = circ.sample_numpy(shots, u)
+            ev = circ.extract_expectation_values_numpy(s)
+            float(ev.mean())
+        barrier()
+        dt = (time.perf_counter() - t0) / k_e2e
+        if args.gpus > 1:
+            import torch
+            import torch.distributed as dist
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = 80 * n_gates + 8 * shots * per_shot + 8 * shots + 4 * n
+        d2h = 8 * shots + 8 * shots * n
+        e2e = {"value": n_gates / dt, "unit": "gates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt * 1e3,
+               "what": "reset + Circuit.forward() (plan, upload gate list, fused passes) + sample(1000) + extract_expectation_values, host buffers, wall clock"}
+
+    cpu_baseline = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+        try:
+            gps_step = args.cpu_gates_per_step or (2 if n >= 30 else 4 if n >= 28 else 50)
+            gps, sec_step, desc, cores, n_cpu = run_cpu(name, 3, 1, gps_step)
+            cpu_baseline = {"value": gps, "unit": "gates/s", "cores": cores, "kind": "port", "sample": desc}
+        except Exception as e:  # the CPU leg must never break the GPU number
+            cpu_baseline = {"value": None, "unit": "gates/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        line = {
+            "metric": "gates_per_sec", "value": value, "unit": "gates/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{name}: {WORKLOAD_DESC[name]}", "apply_method": method,
+                       "step": "reset to |0..0> + forward of the whole circuit",
+                       "l2": "state (>= 4 GiB per GPU) is far larger than the 126 MB L2; no flush needed",
+                       "fused": not args.unfused, "wall_s_timed_region": t_wall},
+            "gpu_launches": int(st["kernel_launches"]),
+            "passes_per_circuit": int(st["tile_passes"] // max(1, args.steps)),
+            "global_swaps_per_circuit": int(st["global_swaps"] // max(1, args.steps)),
+            "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    circ.close()
+    if args.gpus > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

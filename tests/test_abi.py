@@ -1,0 +1,96 @@
+"""The C-ABI library loads without a GPU, exports every declared symbol and fails loudly."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from damavand_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b([a-z_][a-z0-9_]*)\s*\(", txt)) - {"defined"})
+
+
+def test_every_declared_symbol_is_exported():
+    L = _lib.load()
+    names = _declared("damavand_b200.h")
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), n
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+
+
+def test_reference_export_names_are_exported():
+    L = _lib.load()
+    names = [n for n in _declared("damavand_gpu_compat.h")]
+    # the 14 names of /root/reference/damavand-gpu/rust_communication.cu
+    for n in ["get_number_of_available_gpus", "get_memory_for_gpu", "peer_access_allowed", "print_timers",
+              "exchange_amplitudes_between_gpus", "init_quantum_state", "sequential_measure_on_gpu",
+              "concurrent_measure_on_gpu", "measure_on_gpu", "apply_one_qubit_gate_gpu_local",
+              "apply_one_qubit_gate_gpu_distributed", "load_amplitudes_local_on_device",
+              "split_amplitudes_between_gpus", "retrieve_amplitudes_on_host"]:
+        assert n in names and hasattr(L, n), n
+
+
+def test_no_silent_fallback_without_gpu():
+    L = _lib.load()
+    if L.dvd_device_count() > 0:
+        pytest.skip("a GPU is present")
+    h = ctypes.c_void_p()
+    rc = L.dvd_create(4, 0, ctypes.byref(h))
+    assert rc != 0 and not h
+    assert b"GPU" in L.dvd_last_error() or len(L.dvd_last_error()) > 0
+    from damavand_b200 import Circuit, DamavandError
+    with pytest.raises(DamavandError):
+        Circuit(4, "gpu")
+
+
+def test_apply_method_strings():
+    from damavand_b200 import Circuit
+    for m in ("brute_force", "shuffle", "multithreading", "distributed_cpu", None):
+        with pytest.raises(NotImplementedError):
+            Circuit(3, m)
+    with pytest.raises(ValueError, match="Apply method not recognized"):
+        Circuit(3, "element_wise")       # the reference panics on this (circuit.rs:112,878)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "damavand_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("the CPU oracle", "").replace("CPU oracle", ""), os.path.join(dirpath, f)
+
+
+def test_planner_debug_entry_points():
+    L = _lib.load()
+    n = 14
+    gates = (_lib.Gate * 3)()
+    from damavand_b200 import gates as pg
+    gates[0].target, gates[0].control = 13, -1; gates[0].m[:] = pg.hadamard()
+    gates[1].target, gates[1].control = 13, 2; gates[1].m[:] = pg.pauli_x()
+    gates[2].target, gates[2].control = 5, -1; gates[2].m[:] = pg.rotation_z(0.3)
+    out = (ctypes.c_int32 * 256)()
+    k = L.dvd_plan_debug(n, n, gates, 3, out, 256)
+    assert k > 0 and out[0] == 1              # one pass
+    tile = list(out[1:13])
+    assert 13 in tile and tile[:3] == [0, 1, 2]
+    assert out[14] == 3                        # three ops
+    # distributed planner: gate on a rank-index qubit forces a swap, identity restored afterwards
+    perm = (ctypes.c_int32 * n)(*range(n))
+    k = L.dvd_plan_distributed_debug(n, n - 1, gates, 3, perm, 1, out, 256)
+    assert k > 0 and list(perm) == list(range(n))
+    steps = out[0]
+    assert steps >= 3
+    # too-small buffer reports the needed size
+    assert L.dvd_plan_debug(n, n, gates, 3, out, 2) < 0
+    # bad input is an error, not a crash
+    gates[0].target = 99
+    assert L.dvd_plan_debug(n, n, gates, 3, out, 256) < -10**9

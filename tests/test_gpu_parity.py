@@ -1,0 +1,270 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Needs a B200: -m gpu.
+
+Tolerances (BASELINE.json north_star): amplitudes and probabilities within 1e-12 relative,
+sampled indices bit-exact under injected uniforms."""
+import math
+
+import numpy as np
+import pytest
+
+from damavand_b200 import circuits
+from oracle import oracle
+from oracle.oracle import OracleCircuit
+from tests.helpers import Recorder, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def gpu_circuit(n):
+    from damavand_b200 import Circuit
+    return Circuit(n, "gpu")
+
+
+def both(n, build):
+    rec = Recorder(); build(rec)
+    g = rec.replay(gpu_circuit(n)); o = rec.replay(OracleCircuit(n))
+    g.forward(); o.forward()
+    return g, o
+
+
+def test_reference_golden_vector():
+    g, _ = both(2, lambda c: (c.add_hadamard_gate(0), c.add_hadamard_gate(1), c.add_cnot_gate(0, 1)))
+    assert np.abs(g.state_numpy() - 0.5).max() < 1e-15
+    assert g.get_real_part_state() == pytest.approx([0.5] * 4, abs=1e-15)
+    assert g.get_imaginary_part_state() == [0.0] * 4
+
+
+def test_known_answers():
+    r = 1 / math.sqrt(2)
+    g, _ = both(2, lambda c: (c.add_hadamard_gate(0), c.add_cnot_gate(0, 1)))
+    assert np.allclose(g.state_numpy(), [r, 0, 0, r], atol=1e-15)
+    g, _ = both(1, lambda c: c.add_rotation_x_gate(0, math.pi))
+    assert np.allclose(g.state_numpy(), [0, -1j], atol=1e-15)
+    for q in (0, 3, 11, 12, 17):
+        g, _ = both(18, lambda c: c.add_pauli_x_gate(q, False))
+        p = g.measure_numpy()
+        assert p[1 << q] == 1.0 and p.sum() == 1.0
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 11])
+def test_small_states_simple_kernel(n):
+    g, o = both(n, lambda c: circuits.random_circuit(c, n, 60, seed=n))
+    assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
+
+
+@pytest.mark.parametrize("n", [12, 14])
+def test_every_target_every_control(n):
+    worst = 0.0
+    for t in range(n):
+        for ctl in [None] + [q for q in range(n) if q != t]:
+            def build(c):
+                for q in range(n):
+                    c.add_rotation_y_gate(q, 0.3 + 0.11 * q); c.add_rotation_z_gate(q, 0.2 + 0.07 * q)
+                if ctl is None:
+                    c.add_rotation_x_gate(t, 1.234)
+                else:
+                    c.add_cnot_gate(ctl, t)
+                c.add_rotation_z_gate((t + 1) % n, 0.5)
+            g, o = both(n, build)
+            e = rel_err(g.state_numpy(), o.amplitudes())
+            worst = max(worst, e)
+            assert e < TOL, (t, ctl, e)
+            g.close()
+    print("worst rel err", worst)
+
+
+@pytest.mark.parametrize("n,gates,seed", [(12, 300, 1), (13, 400, 2), (16, 500, 3), (20, 400, 4), (22, 300, 5), (24, 200, 6)])
+def test_random_circuits(n, gates, seed):
+    g, o = both(n, lambda c: circuits.random_circuit(c, n, gates, seed))
+    assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
+    assert abs(g.norm() - 1.0) < 1e-12
+    st = g.stats()
+    assert st["gates_applied"] == gates and st["tile_passes"] < gates and st["kernel_launches"] > 0
+
+
+def test_fused_equals_unfused():
+    n = 16
+    rec = Recorder(); circuits.random_circuit(rec, n, 300, 11)
+    a = rec.replay(gpu_circuit(n)); b = rec.replay(gpu_circuit(n)); b.set_unfused(True)
+    a.forward(); b.forward()
+    assert rel_err(a.state_numpy(), b.state_numpy()) < TOL
+    assert b.stats()["simple_passes"] == 300 and a.stats()["simple_passes"] == 0
+
+
+def test_cfg1_layered20_full_pipeline():
+    # BASELINE configs[0]: forward, measure, sample 1000, extract_expectation_values
+    n = 20
+    rec = Recorder(); circuits.layered(rec, n, 10)
+    g = rec.replay(gpu_circuit(n)); o = rec.replay(OracleCircuit(n))
+    g.forward(); o.forward()
+    assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
+    pg, po = g.measure_numpy(), o.measure_np()
+    assert np.abs(pg - po).max() <= TOL * po.max()
+    u = np.random.default_rng(1235).random(1000)
+    sg = g.sample(1000, uniforms=u)
+    assert sg == o.sample(1000, uniforms=u, mode="tree")          # the specified summation order
+    assert sg == o.sample(1000, uniforms=u, mode="sequential")    # and the reference's sequential order
+    assert g.extract_expectation_values(sg) == o.extract_expectation_values(sg)
+
+
+def test_shapes_qft_and_hea():
+    g, o = both(18, lambda c: circuits.qft_like(c, 18))
+    assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
+    g, o = both(18, lambda c: circuits.hea(c, 18, 8))
+    assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
+
+
+@pytest.mark.parametrize("n", [3, 9, 10, 13, 21])
+def test_sampler_bit_exact(n):
+    g, o = both(n, lambda c: circuits.layered(c, n, 2, seed=n))
+    u = np.random.default_rng(99).random(20000)
+    u[0] = 0.0
+    u[1] = np.nextafter(1.0, 0.0)
+    sg = g.sample_numpy(u.size, u)
+    p = o.measure_np()
+    assert (sg == oracle.sample_tree(p, u)).all()
+    assert (sg == oracle.sample_sequential(p, u)).all()
+
+
+def test_sampler_on_exact_probabilities():
+    # the sampler's own |amp|^2 must be the reference's norm_sqr bit for bit
+    n = 15
+    g, o = both(n, lambda c: circuits.random_circuit(c, n, 200, 21))
+    ps = g.state_numpy()
+    mine = ps.real * ps.real + ps.imag * ps.imag
+    assert (g.measure_numpy() == mine).all()
+
+
+def test_measure_and_sample_defaults():
+    g, o = both(6, lambda c: [c.add_hadamard_gate(q) for q in range(6)])
+    assert len(g.measure()) == 64 and abs(sum(g.measure()) - 1) < 1e-14
+    s = g.sample()
+    assert len(s) == 1000 and all(0 <= x < 64 for x in s)        # default 1000 shots (circuit.rs:439-443)
+    assert g.sample(0) == []
+
+
+def test_observables_forward_twice_reset_set_parameters():
+    n = 12
+    g = gpu_circuit(n); o = OracleCircuit(n)
+    for c in (g, o):
+        c.add_rotation_x_gate(0, 0.1); c.add_hadamard_gate(5); c.add_rotation_z_gate(5, 0.2)
+        c.add_pauli_z_gate(0, True); c.add_cnot_gate(5, 11); c.add_pauli_x_gate(3, True)
+        c.set_parameters([1.0, 2.0])
+        c.forward(); c.forward()
+    assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
+    assert g.extract_expectation_values([0, 1, 8, 9]) == o.extract_expectation_values([0, 1, 8, 9])
+    g.reset_amplitudes()
+    assert g.state_numpy()[0] == 1.0 and np.abs(g.state_numpy()[1:]).max() == 0.0
+    g.reset()
+    assert g.gates == [] and g.observables == [3, 5]
+    assert g.extract_expectation_values([]) == []
+
+
+def test_expectation_z_exact():
+    n = 14
+    g, o = both(n, lambda c: circuits.hea(c, n, 4))
+    p = o.measure_np()
+    idx = np.arange(p.size)
+    want = np.array([(p * (1 - 2.0 * ((idx >> q) & 1))).sum() for q in range(n)])
+    assert np.abs(g.expectation_z() - want).max() < 1e-12
+
+
+def test_fidelity():
+    n = 12
+    g = gpu_circuit(n); o = OracleCircuit(n)
+    for c in (g, o):
+        for q in range(n):
+            c.add_rotation_y_gate(q, 0.1)
+        c.add_cnot_gate(0, 1)
+    p1 = [0.1 * i for i in range(n)]; p2 = [0.1 * i + 0.05 for i in range(n)]
+    assert abs(g.get_fidelity_between_two_states_with_parameters(p1, p2)
+               - o.get_fidelity_between_two_states_with_parameters(p1, p2)) < 1e-12
+
+
+def test_load_state_round_trip():
+    from damavand_b200 import _lib
+    import ctypes
+    n = 13
+    g = gpu_circuit(n)
+    rng = np.random.default_rng(3)
+    z = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    z /= np.linalg.norm(z)
+    re, im = np.ascontiguousarray(z.real), np.ascontiguousarray(z.imag)
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    _lib.check(g._lib.dvd_load_state(g._handle, dp(re), dp(im), 0, 1 << n), "load")
+    assert (g.state_numpy() == z).all()
+    o = OracleCircuit(n); o.state = np.ascontiguousarray(z).view(np.float64).copy()
+    for c in (g, o):
+        c.add_hadamard_gate(12); c.add_cnot_gate(12, 0); c.forward()
+    assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
+
+
+def test_error_paths():
+    from damavand_b200 import DamavandError
+    g = gpu_circuit(4)
+    with pytest.raises(ValueError):
+        g.add_hadamard_gate(4)
+    with pytest.raises(ValueError):
+        g.add_cnot_gate(1, 1)
+    with pytest.raises(ValueError):
+        g.sample(10, uniforms=[0.5])
+    import ctypes
+    re = (ctypes.c_double * 4)(1, 0, 0, 0); im = (ctypes.c_double * 4)()
+    assert g._lib.dvd_apply_gate(g._handle, re, im, -1, 9) != 0
+    assert b"target" in g._lib.dvd_last_error()
+    with pytest.raises(DamavandError):
+        from damavand_b200 import Circuit
+        Circuit(41, "gpu")
+
+
+def test_reference_export_names_drive_the_engine():
+    """The reference's own FFI names (rust_communication.cu) on top of the engine."""
+    import ctypes
+    from damavand_b200 import _lib, gates as pg
+    L = _lib.load()
+    n = 13
+    L.init_quantum_state.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.apply_one_qubit_gate_gpu_local.argtypes = [dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.retrieve_amplitudes_on_host.argtypes = [ctypes.c_int, dp, dp]
+    L.measure_on_gpu.argtypes = [ctypes.c_int, dp]
+    assert L.get_number_of_available_gpus() == 1
+    L.init_quantum_state(1 << n, 1, 1)
+    o = OracleCircuit(n)
+    for (name, t, c, p) in [("Hadamard", 12, None, None), ("CNOT", 3, 12, None), ("RotationY", 3, None, 0.4)]:
+        m = pg.matrix(name, p)
+        re = (ctypes.c_double * 4)(*m[0::2]); im = (ctypes.c_double * 4)(*m[1::2])
+        L.apply_one_qubit_gate_gpu_local(re, im, n, 1 << n, -1 if c is None else c, t)
+    o.add_hadamard_gate(12); o.add_cnot_gate(12, 3); o.add_rotation_y_gate(3, 0.4); o.forward()
+    re = np.empty(1 << n); im = np.empty(1 << n); pr = np.empty(1 << n)
+    L.retrieve_amplitudes_on_host(1 << n, re.ctypes.data_as(dp), im.ctypes.data_as(dp))
+    L.measure_on_gpu(1 << n, pr.ctypes.data_as(dp))
+    assert rel_err(re + 1j * im, o.amplitudes()) < TOL
+    assert np.abs(pr - o.measure_np()).max() < 1e-15
+
+
+@pytest.mark.parametrize("name,n", [("hea", 28), ("qft", 26)])
+def test_large_state_properties(name, n):
+    """Full-size style checks through size-independent properties: unitarity, <Z> consistency,
+    fused == unfused on a subsample of amplitudes."""
+    rec = Recorder()
+    if name == "hea":
+        circuits.hea(rec, n, 3)
+    else:
+        circuits.qft_like(rec, n)
+    a = rec.replay(gpu_circuit(n)); a.forward()
+    assert abs(a.norm() - 1.0) < 1e-11
+    ez = a.expectation_z()
+    assert np.all(np.abs(ez) <= 1 + 1e-12)
+    b = rec.replay(gpu_circuit(n)); b.set_unfused(True); b.forward()
+    import ctypes
+    cnt = 1 << 16
+    dp = lambda x: x.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    for first in (0, (1 << n) // 3, (1 << n) - cnt):
+        ra, ia, rb, ib = (np.empty(cnt) for _ in range(4))
+        a._lib.dvd_read_state(a._handle, dp(ra), dp(ia), first, cnt)
+        b._lib.dvd_read_state(b._handle, dp(rb), dp(ib), first, cnt)
+        scale = 2.0 ** (-n / 2)
+        assert np.abs((ra - rb) + 1j * (ia - ib)).max() < 1e-12 * max(scale, np.abs(ra + 1j * ia).max())
+    assert np.abs(ez - b.expectation_z()).max() < 1e-11
