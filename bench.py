@@ -103,7 +103,16 @@ class ClockSampler:
 
 def build_workload(circ, name):
     from damavand_b200 import circuits
-    return circuits.WORKLOADS[name](circ)
+    return circuits.workload(name)[1](circ)
+
+
+def workload_qubits(name):
+    from damavand_b200 import circuits
+    return circuits.workload(name)[0]
+
+
+def workload_desc(name):
+    return WORKLOAD_DESC.get(name, name)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -134,16 +143,15 @@ def run_cpu(name: str, steps: int, warmup: int, gates_per_step: int):
     Returns (gates_per_sec, seconds_per_step, description, cores)."""
     from oracle.oracle import OracleCircuit
     from damavand_b200 import circuits
-    n = WORKLOAD_QUBITS[name]
+    n = workload_qubits(name)
     n_cpu = cpu_sample_gates(name, n, host_mem_gib())
     o = OracleCircuit(n_cpu)
     if n_cpu == n:
-        circuits.WORKLOADS[name](o)
+        circuits.workload(name)[1](o)
     else:   # same generator, fewer qubits (host RAM cannot hold state + clone)
-        gen = {"qft30": lambda c: circuits.qft_like(c, n_cpu), "hea28": lambda c: circuits.hea(c, n_cpu, 50),
-               "random32": lambda c: circuits.random_circuit(c, n_cpu, 640), "hea34": lambda c: circuits.hea(c, n_cpu, 10),
-               "layered20": lambda c: circuits.layered(c, n_cpu, 10)}[name]
-        gen(o)
+        import re
+        kind = re.match(r"[a-z]+", name).group(0)
+        circuits.workload(f"{kind}{n_cpu}")[1](o)
     all_gates = [g for i, g in enumerate(o.gates) if i not in set(o.observables)]
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
@@ -173,14 +181,14 @@ def reference_arm(args):
     if rank != 0:
         return 0
     name = args.workload or ("qft30" if args.gpus == 1 else "random32")
-    n = WORKLOAD_QUBITS[name]
+    n = workload_qubits(name)
     gates_per_step = args.cpu_gates_per_step or (2 if n >= 30 else 4 if n >= 28 else 50)
     gps, sec_step, desc, cores, n_cpu = run_cpu(name, args.steps, args.warmup, gates_per_step)
     line = {
         "impl": "reference", "metric": "gates_per_sec", "value": gps, "unit": "gates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_step * 1e3, "higher_is_better": True,
         "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{name}: {WORKLOAD_DESC[name]}", "cpu_qubits": n_cpu, "gates_per_step": gates_per_step},
+        "config": {"workload": f"{name}: {workload_desc(name)}", "cpu_qubits": n_cpu, "gates_per_step": gates_per_step},
         "cpu_baseline": {"value": gps, "unit": "gates/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": gps, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -198,7 +206,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None, choices=sorted(WORKLOAD_DESC))
+    ap.add_argument("--workload", default=None)
     ap.add_argument("--cpu-gates-per-step", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -215,7 +223,7 @@ def main():
             return 2
     rank = int(os.environ.get("RANK", "0"))
     name = args.workload or ("qft30" if args.gpus == 1 else "random32")
-    n = WORKLOAD_QUBITS[name]
+    n = workload_qubits(name)
     method = "gpu" if args.gpus == 1 else "distributed_gpu"
     if args.gpus > 1:
         import torch
@@ -346,7 +354,7 @@ def main():
             "metric": "gates_per_sec", "value": value, "unit": "gates/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{name}: {WORKLOAD_DESC[name]}", "apply_method": method,
+            "config": {"workload": f"{name}: {workload_desc(name)}", "apply_method": method,
                        "step": "reset to |0..0> + forward of the whole circuit",
                        "l2": "state (>= 4 GiB per GPU) is far larger than the 126 MB L2; no flush needed",
                        "fused": not args.unfused, "wall_s_timed_region": t_wall},

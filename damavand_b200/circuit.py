@@ -259,6 +259,8 @@ class Circuit:
 
     def extract_expectation_values_numpy(self, samples) -> np.ndarray:
         s = np.ascontiguousarray(np.asarray(samples, dtype=np.uint64))
+        if s.shape[0] == 0:          # the reference's loop body never runs (circuit.rs:496)
+            return np.empty((0, len(self.observables)), dtype=np.float64)
         q = np.ascontiguousarray(np.array([self.gates[i][1] for i in self.observables], dtype=np.int32))
         out = np.empty((s.shape[0], q.shape[0]), dtype=np.float64)
         _lib.check(self._lib.dvd_extract_expectation_values(

@@ -95,6 +95,26 @@ def random_circuit(circ, n: int, gates: int = 640, seed: int = 1234) -> int:
     return gates
 
 
+def workload(name: str):
+    """Resolve a workload name: the five BASELINE configs, or `qft<n>`, `hea<n>[x<layers>]`,
+    `random<n>[x<gates>]`, `layered<n>[x<layers>]` for other sizes.  Returns (n_qubits, builder)."""
+    import re
+    m = re.fullmatch(r"(qft|hea|random|layered)(\d+)(?:x(\d+))?", name)
+    if not m:
+        raise KeyError(name)
+    kind, n, k = m.group(1), int(m.group(2)), m.group(3)
+    if kind == "qft":
+        return n, (lambda c: qft_like(c, n))
+    if kind == "hea":
+        layers = int(k) if k else (50 if n <= 28 else 10)
+        return n, (lambda c: hea(c, n, layers, observables=(n >= 34)))
+    if kind == "random":
+        g = int(k) if k else 640
+        return n, (lambda c: random_circuit(c, n, g))
+    layers = int(k) if k else 10
+    return n, (lambda c: layered(c, n, layers))
+
+
 WORKLOADS = {
     "layered20": lambda c: layered(c, 20, 10),
     "hea28": lambda c: hea(c, 28, 50),
