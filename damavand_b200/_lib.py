@@ -80,7 +80,7 @@ SIGNATURES = {
     "dvd_timer_begin": (ctypes.c_int, [_VP]),
     "dvd_timer_end": (ctypes.c_int, [_VP, _DP]),
     "dvd_set_unfused": (ctypes.c_int, [_VP, ctypes.c_int]),
-    "dvd_plan_debug": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(Gate), ctypes.c_int64, _I32P, ctypes.c_int64]),
+    "dvd_plan_debug": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(Gate), ctypes.c_int64, ctypes.c_int, _I32P, ctypes.c_int64]),
     "dvd_plan_distributed_debug": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(Gate), ctypes.c_int64, _I32P, ctypes.c_int, _I32P, ctypes.c_int64]),
 }
 

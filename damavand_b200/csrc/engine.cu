@@ -10,6 +10,7 @@
 #include <climits>
 #include <cstdio>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -214,9 +215,9 @@ int dvd_apply_gate(dvd_state* s, const double m_re[4], const double m_im[4], int
     if (!s || !m_re || !m_im) return fail(DVD_ERR_ARG, "null argument");
     if (target < 0 || target >= s->n_qubits) return fail(DVD_ERR_ARG, "target qubit out of range");
     if (control < -1 || control >= s->n_qubits || control == target) return fail(DVD_ERR_ARG, "control qubit out of range");
-    HostGate g;
-    g.target = target; g.control = control; g.gate_idx = (int)s->pending.size();
-    for (int k = 0; k < 4; ++k) { g.m[2 * k] = m_re[k]; g.m[2 * k + 1] = m_im[k]; }
+    double m[8];
+    for (int k = 0; k < 4; ++k) { m[2 * k] = m_re[k]; m[2 * k + 1] = m_im[k]; }
+    HostGate g = make_gate(target, control, m, (int)s->pending.size());
     s->pending.push_back(g);
     return DVD_OK;
 }
@@ -231,9 +232,7 @@ int dvd_apply_circuit(dvd_state* s, const dvd_gate* gates, int64_t n) {
     }
     s->pending.reserve(s->pending.size() + (size_t)n);
     for (int64_t i = 0; i < n; ++i) {
-        HostGate g;
-        g.target = gates[i].target; g.control = gates[i].control; g.gate_idx = (int)s->pending.size();
-        std::memcpy(g.m, gates[i].m, sizeof g.m);
+        HostGate g = make_gate(gates[i].target, gates[i].control, gates[i].m, (int)s->pending.size());
         s->pending.push_back(g);
     }
     return DVD_OK;
@@ -242,13 +241,11 @@ int dvd_apply_circuit(dvd_state* s, const dvd_gate* gates, int64_t n) {
 }  // extern "C"
 
 // ---- flush ---------------------------------------------------------------------------------------
-static DevOp simple_op(const HostGate& g) {
-    DevOp op;
-    std::memset(&op, 0, sizeof op);
+static SimpleOp simple_op(const HostGate& g) {
+    SimpleOp op;
     std::memcpy(op.m, g.m, sizeof op.m);
-    classify_gate(g.m, &op.kind, &op.d0_is_one);
-    op.group = -1; op.tpos = -1; op.cpos = -1;
-    op.tbit = (int8_t)g.target; op.cbit = (int8_t)g.control; op.gate_idx = g.gate_idx;
+    op.tbit = g.target();
+    op.cbit = g.control();
     return op;
 }
 
@@ -315,17 +312,24 @@ static int flush_impl(dvd_state* s) {
     if (s->pending.empty()) return DVD_OK;
     CU(cudaSetDevice(s->device));
     std::vector<DistStep> steps;
+    const bool tiled = !s->unfused && s->n_local >= TILE_BITS;
+    const double chunk_bytes = (double)s->n_amps * 16.0;
+    for (const HostGate& g : s->pending) {
+        s->stats.gates_applied++;
+        s->stats.gate_algorithmic_bytes += (g.cmask ? 1.0 : 2.0) * chunk_bytes;
+    }
     try {
+        // level 0 (fused mode only): CNOT-conjugated diagonal runs -> parity phases
+        const std::vector<HostGate> fused = tiled ? fuse_diagonal_runs(s->pending) : s->pending;
         if (s->world > 1) {
-            steps = plan_distributed(s->pending, s->n_qubits, s->n_local, s->perm, /*restore_identity=*/true);
+            steps = plan_distributed(fused, s->n_qubits, s->n_local, s->perm, /*restore_identity=*/true);
         } else {
-            DistStep st; st.kind = DistStep::LOCAL_GATES; st.gates = s->pending;
+            DistStep st; st.kind = DistStep::LOCAL_GATES; st.gates = fused;
             steps.push_back(std::move(st));
         }
     } catch (const std::exception& e) {
         return fail(DVD_ERR_INTERNAL, std::string("planner: ") + e.what());
     }
-    const bool tiled = !s->unfused && s->n_local >= TILE_BITS;
     // plan every local step up front so that all ops go to the device in one copy
     std::vector<std::vector<Pass>> plans(steps.size());
     size_t total_ops = 0;
@@ -357,15 +361,9 @@ static int flush_impl(dvd_state* s) {
         if (total_ops) CU(cudaMemcpyAsync(s->d_ops, s->h_ops, total_ops * sizeof(DevOp), cudaMemcpyHostToDevice, s->stream));
     }
     size_t at = 0;
-    const double chunk_bytes = (double)s->n_amps * 16.0;
     for (size_t i = 0; i < steps.size(); ++i) {
         DistStep& st = steps[i];
         if (st.kind == DistStep::GLOBAL_SWAP) { TRY(global_swap(s, st.gq, st.lq)); continue; }
-        for (const HostGate& g : st.gates) {
-            if (g.gate_idx < 0) continue;   // layout-restoring CNOTs are not user gates
-            s->stats.gates_applied++;
-            s->stats.gate_algorithmic_bytes += (g.control >= 0 ? 1.0 : 2.0) * chunk_bytes;
-        }
         if (tiled) {
             for (auto& p : plans[i]) {
                 PassDesc pd = p.desc;
@@ -380,7 +378,7 @@ static int flush_impl(dvd_state* s) {
             for (const HostGate& g : st.gates) {
                 CU(launch_simple_gate(s->amp, s->n_local, s->rank_bits, simple_op(g), s->stream));
                 s->stats.kernel_launches++; s->stats.simple_passes++;
-                s->stats.pass_bytes += (g.control >= 0 ? 1.0 : 2.0) * chunk_bytes;
+                s->stats.pass_bytes += (g.cmask ? 1.0 : 2.0) * chunk_bytes;
             }
         }
     }
@@ -627,18 +625,21 @@ int dvd_set_unfused(dvd_state* s, int unfused) {
 
 // ---- planner inspection ---------------------------------------------------------------------
 static std::vector<HostGate> to_host_gates(const dvd_gate* gates, int64_t n) {
-    std::vector<HostGate> v((size_t)n);
+    std::vector<HostGate> v;
+    v.reserve((size_t)n);
     for (int64_t i = 0; i < n; ++i) {
-        v[i].target = gates[i].target; v[i].control = gates[i].control; v[i].gate_idx = (int)i;
-        std::memcpy(v[i].m, gates[i].m, sizeof v[i].m);
+        if (gates[i].target < 0 || gates[i].target > 62 || gates[i].control < -1 || gates[i].control > 62 ||
+            gates[i].control == gates[i].target)
+            throw std::runtime_error("bad qubit index");
+        v.push_back(make_gate(gates[i].target, gates[i].control, gates[i].m, (int)i));
     }
     return v;
 }
 
-int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates, int32_t* out, int64_t cap) {
+int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates, int fuse, int32_t* out, int64_t cap) {
     try {
         PlanOptions opt;
-        std::vector<Pass> passes = plan_local(to_host_gates(gates, n_gates), n_local, n_total, opt);
+        std::vector<Pass> passes = plan_local(fuse ? fuse_diagonal_runs(to_host_gates(gates, n_gates)) : to_host_gates(gates, n_gates), n_local, n_total, opt);
         std::vector<int32_t> v;
         v.push_back((int32_t)passes.size());
         for (auto& p : passes) {
@@ -647,7 +648,7 @@ int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t 
             v.push_back((int32_t)p.ops.size());
             for (auto& op : p.ops) {
                 v.push_back(op.gate_idx); v.push_back(op.kind); v.push_back(op.group);
-                v.push_back(op.tpos); v.push_back(op.cpos);
+                v.push_back(op.treg); v.push_back(op.cregm);
             }
         }
         if ((int64_t)v.size() > cap) return -(int64_t)v.size();
@@ -672,7 +673,7 @@ int64_t dvd_plan_distributed_debug(int n_total, int n_local, const dvd_gate* gat
             v.push_back((int32_t)st.kind);
             v.push_back(st.gq); v.push_back(st.lq);
             v.push_back((int32_t)st.gates.size());
-            for (auto& g : st.gates) { v.push_back(g.gate_idx); v.push_back(g.target); v.push_back(g.control); }
+            for (auto& g : st.gates) { v.push_back(g.gate_idx); v.push_back(g.target()); v.push_back(g.control()); }
         }
         if ((int64_t)v.size() > cap) return -(int64_t)v.size();
         std::memcpy(out, v.data(), v.size() * sizeof(int32_t));

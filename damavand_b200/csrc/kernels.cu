@@ -38,7 +38,8 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
     // global <-> register layout = IO_GROUP stage: lanes run over tile positions 0..4, i.e. over
     // >= 128 contiguous bytes (tile positions 0..2 are always physical qubits 0..2)
     const int tb_io = stage_idx(IO_GROUP, tid, 0);
-    cplx* p0 = amp + base + tile_offset(pd, tb_io);
+    const uint64_t off_io = tile_offset(pd, tb_io);
+    cplx* p0 = amp + base + off_io;
     uint64_t hs[REG_BITS];
 #pragma unroll
     for (int k = 0; k < REG_BITS; ++k) hs[k] = 1ull << pd.tile_q[IO_GROUP * REG_BITS + k];
@@ -53,7 +54,10 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
     }
 
     int cur = IO_GROUP;
-    int tbase = tb_io;
+    ThreadCtx ctx;
+    ctx.pidx = gbase | off_io;
+    ctx.ph = cplx{1.0, 0.0};
+    ctx.ph_dirty = false;
     for (int c0 = 0; c0 < pd.n_ops; c0 += OPS_CHUNK) {
         const int n = min(OPS_CHUNK, pd.n_ops - c0);
         __syncthreads();  // previous chunk fully consumed
@@ -68,13 +72,15 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
             const DevOp& op = sops[k];
             const int g = op.group;
             if (g >= 0 && g != cur) {
+                flush_phase(a, ctx);
                 switch_stage(tile, a, tid, cur, g);
                 cur = g;
-                tbase = stage_idx(g, tid, 0);
+                ctx.pidx = gbase | tile_offset(pd, stage_idx(g, tid, 0));
             }
-            apply_op(a, op, cur, tbase, gbase);
+            apply_op(a, op, ctx);
         }
     }
+    flush_phase(a, ctx);
     if (cur != IO_GROUP) switch_stage(tile, a, tid, cur, IO_GROUP);
 
 #pragma unroll
@@ -90,7 +96,7 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
 // One gate per pass (small states, debug path)
 // =================================================================================================
 __global__ void __launch_bounds__(256)
-k_simple_gate(cplx* __restrict__ amp, int n_local, uint64_t rank_bits, const __grid_constant__ DevOp op) {
+k_simple_gate(cplx* __restrict__ amp, int n_local, uint64_t rank_bits, const __grid_constant__ SimpleOp op) {
     const uint64_t n = 1ull << n_local;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -380,7 +386,7 @@ cudaError_t launch_tile_pass(cplx* amp, const DevOp* ops, const PassDesc& pd, cu
     return cudaGetLastError();
 }
 
-cudaError_t launch_simple_gate(cplx* amp, int n_local, uint64_t rank_bits, const DevOp& op, cudaStream_t s) {
+cudaError_t launch_simple_gate(cplx* amp, int n_local, uint64_t rank_bits, const SimpleOp& op, cudaStream_t s) {
     const uint64_t items = op.tbit < n_local ? (1ull << n_local) / 2 : (1ull << n_local);
     k_simple_gate<<<grid_for(items, 256, STREAM_CAP), 256, 0, s>>>(amp, n_local, rank_bits, op);
     return cudaGetLastError();

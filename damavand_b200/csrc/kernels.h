@@ -15,7 +15,8 @@ cudaError_t kernels_init();   // one-time function attributes (dynamic shared me
 cudaError_t launch_tile_pass(cplx* amp, const DevOp* ops, const PassDesc& pd, cudaStream_t s);
 
 // One gate, one pass, any size (used when n_local < TILE_BITS, and as the un-fused debug path).
-cudaError_t launch_simple_gate(cplx* amp, int n_local, uint64_t rank_bits, const DevOp& op, cudaStream_t s);
+struct SimpleOp { double m[8]; int32_t tbit; int32_t cbit; };   // cbit < 0: no control
+cudaError_t launch_simple_gate(cplx* amp, int n_local, uint64_t rank_bits, const SimpleOp& op, cudaStream_t s);
 
 cudaError_t launch_set_basis_state(cplx* amp, uint64_t index, cudaStream_t s);
 

@@ -3,7 +3,9 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <stdexcept>
+#include <utility>
 
 namespace dvd {
 
@@ -26,26 +28,117 @@ void classify_gate(const double m[8], int32_t* kind, int8_t* d0_is_one) {
     }
 }
 
+HostGate make_gate(int target, int control, const double m[8], int gate_idx) {
+    HostGate g;
+    g.tmask = 1ull << target;
+    g.cmask = control >= 0 ? 1ull << control : 0;
+    std::memcpy(g.m, m, sizeof g.m);
+    g.gate_idx = gate_idx;
+    g.diag = is_diagonal(m);
+    return g;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Level 0: diagonal-run fusion.
+//
+// Inside a run made only of diagonal gates and CNOTs the state is |x> -> phase(x) |A x> with A a
+// GF(2)-linear map.  rows[q] tracks qubit q's current value as a parity of the run's input bits, so
+// a diagonal gate met in the middle of the run is a phase on parity(x & rows[target]) (controlled by
+// parity(x & rows[control])).  Whenever A is back to the identity the run so far equals the product
+// of the collected parity phases -- all diagonal, all commuting, no amplitude moves.
+// ---------------------------------------------------------------------------------------------------
+std::vector<HostGate> fuse_diagonal_runs(const std::vector<HostGate>& gates) {
+    std::vector<HostGate> out;
+    out.reserve(gates.size());
+    uint64_t rows[64];
+    for (int q = 0; q < 64; ++q) rows[q] = 1ull << q;
+    int nonid = 0;
+    std::vector<HostGate> items, terms;
+    size_t ck_items = 0, ck_terms = 0;
+    bool ck_has_cnot = false, has_cnot = false;
+
+    auto xor_rows = [&](uint64_t mask) {
+        uint64_t r = 0;
+        while (mask) { const int q = __builtin_ctzll(mask); mask &= mask - 1; r ^= rows[q]; }
+        return r;
+    };
+    auto end_run = [&]() {
+        if (items.empty()) return;
+        if (ck_items > 0 && ck_has_cnot) {
+            // fused prefix: merge terms with identical masks
+            std::map<std::pair<uint64_t, uint64_t>, size_t> where;
+            const size_t first = out.size();
+            for (size_t i = 0; i < ck_terms; ++i) {
+                const HostGate& t = terms[i];
+                auto key = std::make_pair(t.tmask, t.cmask);
+                auto it = where.find(key);
+                if (it == where.end()) {
+                    where[key] = out.size();
+                    HostGate g = t;
+                    g.gate_idx = -1;
+                    out.push_back(g);
+                } else {
+                    HostGate& g = out[it->second];
+                    const double a0 = g.m[0], b0 = g.m[1], a1 = g.m[6], b1 = g.m[7];
+                    g.m[0] = a0 * t.m[0] - b0 * t.m[1]; g.m[1] = a0 * t.m[1] + b0 * t.m[0];
+                    g.m[6] = a1 * t.m[6] - b1 * t.m[7]; g.m[7] = a1 * t.m[7] + b1 * t.m[6];
+                }
+            }
+            (void)first;
+            for (size_t i = ck_items; i < items.size(); ++i) out.push_back(items[i]);
+        } else {
+            for (const HostGate& g : items) out.push_back(g);
+        }
+        items.clear(); terms.clear();
+        ck_items = ck_terms = 0; ck_has_cnot = has_cnot = false;
+        if (nonid) { for (int q = 0; q < 64; ++q) rows[q] = 1ull << q; nonid = 0; }
+    };
+
+    for (const HostGate& g : gates) {
+        int32_t kind; int8_t d0;
+        classify_gate(g.m, &kind, &d0);
+        const bool is_cnot = !g.diag && kind == K_SWAP && g.cmask != 0 && (g.cmask & (g.cmask - 1)) == 0;
+        if (g.diag) {
+            HostGate t = g;
+            t.tmask = xor_rows(g.tmask);
+            t.cmask = g.cmask ? xor_rows(g.cmask) : 0;
+            terms.push_back(t);
+            items.push_back(g);
+        } else if (is_cnot) {
+            const int t = g.target(), c = g.control();
+            const bool was = rows[t] != (1ull << t);
+            rows[t] ^= rows[c];
+            const bool is = rows[t] != (1ull << t);
+            nonid += (int)is - (int)was;
+            items.push_back(g);
+            has_cnot = true;
+        } else {
+            end_run();
+            out.push_back(g);
+            continue;
+        }
+        if (nonid == 0) { ck_items = items.size(); ck_terms = terms.size(); ck_has_cnot = has_cnot; }
+    }
+    end_run();
+    return out;
+}
+
 namespace {
 
 // Commutation bookkeeping for "pull a gate in front of the gates that were skipped".
-// A qubit is used diagonally by a gate when it is a control or the target of a diagonal gate, and
-// non-diagonally when it is the target of a non-diagonal gate.  Two gates commute if on every
-// shared qubit both uses are diagonal.
+// A qubit is used diagonally by a gate when it is in a control mask or in the mask of a diagonal
+// gate, and non-diagonally when it is the target of a non-diagonal gate.  Two gates commute if on
+// every shared qubit both uses are diagonal.
 struct Blocked {
     uint64_t x = 0;  // qubits with a skipped non-diagonal use
     uint64_t z = 0;  // qubits with a skipped diagonal use
-    bool can_pass(const HostGate& g, bool diag) const {
-        const uint64_t tb = 1ull << g.target;
-        if (diag) { if (x & tb) return false; }
-        else if ((x | z) & tb) return false;
-        if (g.control >= 0 && (x & (1ull << g.control))) return false;
-        return true;
+    bool can_pass(const HostGate& g) const {
+        if (g.diag) return !(x & (g.tmask | g.cmask));
+        return !((x | z) & g.tmask) && !(x & g.cmask);
     }
-    void skip(const HostGate& g, bool diag) {
-        const uint64_t tb = 1ull << g.target;
-        if (diag) z |= tb; else x |= tb;
-        if (g.control >= 0) z |= 1ull << g.control;
+    void skip(const HostGate& g) {
+        if (g.diag) z |= g.tmask | g.cmask;
+        else { x |= g.tmask; z |= g.cmask; }
     }
 };
 
@@ -57,14 +150,16 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
     if (n_total > 62) throw std::runtime_error("plan_local: too many qubits");
     std::vector<Pass> passes;
     const int G = (int)gates.size();
-    std::vector<char> diag(G);
+    const uint64_t all = n_total >= 64 ? ~0ull : ((1ull << n_total) - 1);
     for (int i = 0; i < G; ++i) {
-        diag[i] = is_diagonal(gates[i].m);
-        if (!diag[i] && gates[i].target >= n_local)
-            throw std::runtime_error("plan_local: non-diagonal gate on a rank-index qubit");
-        if (gates[i].target < 0 || gates[i].target >= n_total || gates[i].control >= n_total ||
-            gates[i].control == gates[i].target)
-            throw std::runtime_error("plan_local: bad qubit index");
+        const HostGate& g = gates[i];
+        if ((g.tmask | g.cmask) & ~all) throw std::runtime_error("plan_local: bad qubit index");
+        if (!g.diag) {
+            if (g.tmask == 0 || (g.tmask & (g.tmask - 1))) throw std::runtime_error("plan_local: bad target");
+            if (g.cmask & (g.cmask - 1)) throw std::runtime_error("plan_local: multi-qubit control on a non-diagonal gate");
+            if (g.cmask & g.tmask) throw std::runtime_error("plan_local: control == target");
+            if (g.target() >= n_local) throw std::runtime_error("plan_local: non-diagonal gate on a rank-index qubit");
+        }
     }
     std::vector<int> pending(G);
     for (int i = 0; i < G; ++i) pending[i] = i;
@@ -80,13 +175,13 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
         for (int k = 0; k < (int)pending.size(); ++k) {
             const int gi = pending[k];
             const HostGate& g = gates[gi];
-            bool ok = k < limit && (int)taken.size() < opt.max_ops_per_pass && blk.can_pass(g, diag[gi]);
-            if (ok && !diag[gi] && !((tile >> g.target) & 1)) {
-                if (tile_n < TILE_BITS) { tile |= 1ull << g.target; ++tile_n; }
+            bool ok = k < limit && (int)taken.size() < opt.max_ops_per_pass && blk.can_pass(g);
+            if (ok && !g.diag && !(tile & g.tmask)) {
+                if (tile_n < TILE_BITS) { tile |= g.tmask; ++tile_n; }
                 else ok = false;
             }
             if (ok) taken.push_back(gi);
-            else { blk.skip(g, diag[gi]); rest.push_back(gi); }
+            else { blk.skip(g); rest.push_back(gi); }
         }
         if (taken.empty()) throw std::runtime_error("plan_local: no progress");
         // pad the tile with the lowest unused local qubits (keeps segments long)
@@ -100,8 +195,8 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
         std::vector<int> order;  // qubits by first non-diagonal target use
         uint64_t seen = (1ull << min_low) - 1;
         for (int gi : taken) {
-            const int t = gates[gi].target;
-            if (!diag[gi] && !((seen >> t) & 1)) { seen |= 1ull << t; order.push_back(t); }
+            const HostGate& g = gates[gi];
+            if (!g.diag && !(seen & g.tmask)) { seen |= g.tmask; order.push_back(g.target()); }
         }
         for (int q = 0; q < n_local; ++q)
             if (((tile >> q) & 1) && !((seen >> q) & 1)) { seen |= 1ull << q; order.push_back(q); }
@@ -115,7 +210,7 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
             for (int g = NGROUPS - 1; g >= 0; --g)
                 for (int p = g * REG_BITS; p < (g + 1) * REG_BITS; ++p)
                     if (p >= min_low) free_pos.push_back(p);
-            if ((int)order.size() != (int)free_pos.size()) throw std::runtime_error("plan_local: tile size");
+            if (order.size() != free_pos.size()) throw std::runtime_error("plan_local: tile size");
             for (size_t i = 0; i < order.size(); ++i) {
                 pass.desc.tile_q[free_pos[i]] = order[i];
                 pos_of[order[i]] = free_pos[i];
@@ -127,40 +222,49 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
         // ---- stage level: sweep per register group ---------------------------------------------------
         std::vector<int> remaining = taken;
         int cur = IO_GROUP;
-        bool first = true;
         while (!remaining.empty()) {
-            // choose the group: keep `cur` if the first remaining op can run there, else move to it
+            // keep `cur` if the first remaining op can run there, else move to its group
             {
-                const int gi0 = remaining[0];
-                if (!diag[gi0]) {
-                    const int g0 = pos_of[gates[gi0].target] / REG_BITS;
-                    if (g0 != cur) { cur = g0; if (!first || g0 != IO_GROUP) ++pass.n_switches; }
+                const HostGate& g0 = gates[remaining[0]];
+                if (!g0.diag) {
+                    const int grp = pos_of[g0.target()] / REG_BITS;
+                    if (grp != cur) { cur = grp; ++pass.n_switches; }
                 }
             }
-            first = false;
+            uint64_t regphys = 0;          // physical qubits living in registers in this stage
+            int regq[REG_BITS];
+            for (int k = 0; k < REG_BITS; ++k) { regq[k] = pass.desc.tile_q[cur * REG_BITS + k]; regphys |= 1ull << regq[k]; }
+            auto reg_mask = [&](uint64_t mask) {
+                uint8_t r = 0;
+                for (int k = 0; k < REG_BITS; ++k) if ((mask >> regq[k]) & 1) r |= (uint8_t)(1 << k);
+                return r;
+            };
             Blocked b2;
             std::vector<int> rem2;
             for (int gi : remaining) {
                 const HostGate& g = gates[gi];
-                bool ok = b2.can_pass(g, diag[gi]) &&
-                          (diag[gi] || pos_of[g.target] / REG_BITS == cur);
-                if (ok) {
-                    DevOp op;
-                    std::memset(&op, 0, sizeof(op));
-                    std::memcpy(op.m, g.m, sizeof(op.m));
-                    classify_gate(g.m, &op.kind, &op.d0_is_one);
-                    op.tbit = (int8_t)g.target;
-                    op.tpos = (int8_t)pos_of[g.target];
-                    op.group = diag[gi] ? (int8_t)-1 : (int8_t)(op.tpos / REG_BITS);
-                    op.cbit = (int8_t)g.control;
-                    op.cpos = g.control >= 0 ? (int8_t)pos_of[g.control] : (int8_t)-1;
-                    op.gate_idx = g.gate_idx;
-                    if (g.control >= 0) ++pass.n_controlled;
-                    pass.ops.push_back(op);
+                const bool ok = b2.can_pass(g) && (g.diag || pos_of[g.target()] / REG_BITS == cur);
+                if (!ok) { b2.skip(g); rem2.push_back(gi); continue; }
+                DevOp op;
+                std::memset(&op, 0, sizeof(op));
+                std::memcpy(op.m, g.m, sizeof(op.m));
+                classify_gate(g.m, &op.kind, &op.d0_is_one);
+                op.gate_idx = g.gate_idx;
+                op.has_ctrl = g.cmask != 0;
+                op.cregm = reg_mask(g.cmask);
+                op.cmask = g.cmask & ~regphys;
+                if (g.diag) {
+                    op.group = -1;
+                    op.treg = -1;
+                    op.tregm = reg_mask(g.tmask);
+                    op.tmask = g.tmask & ~regphys;
                 } else {
-                    b2.skip(g, diag[gi]);
-                    rem2.push_back(gi);
+                    op.group = (int8_t)cur;
+                    op.treg = (int8_t)(pos_of[g.target()] % REG_BITS);
+                    op.tregm = 0;
+                    op.tmask = 0;
                 }
+                pass.ops.push_back(op);
             }
             remaining.swap(rem2);
         }
@@ -193,31 +297,33 @@ std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n
         perm[a] = lq; perm[b] = gq; inv[gq] = b; inv[lq] = a;
     };
     auto emit_local_cnot = [&](int pc, int pt) {
-        HostGate g; g.target = pt; g.control = pc; g.gate_idx = -1;
         const double x[8] = {0, 0, 1, 0, 1, 0, 0, 0};
-        std::memcpy(g.m, x, sizeof(x));
-        local_step().gates.push_back(g);
+        local_step().gates.push_back(make_gate(pt, pc, x, -1));
+    };
+    auto map_mask = [&](uint64_t mask) {
+        uint64_t r = 0;
+        while (mask) { const int q = __builtin_ctzll(mask); mask &= mask - 1; r |= 1ull << perm[q]; }
+        return r;
     };
 
     for (int i = 0; i < G; ++i) {
         const HostGate& g = gates[i];
-        const bool d = is_diagonal(g.m);
-        if (!d && perm[g.target] >= n_local) {
+        if (!g.diag && perm[g.target()] >= n_local) {
             // evict the local qubit whose next non-diagonal use is farthest away (Belady)
             std::vector<int> next_use(n_total, G + 1);
             for (int k = G - 1; k > i; --k)
-                if (!is_diagonal(gates[k].m)) next_use[gates[k].target] = k;
+                if (!gates[k].diag) next_use[gates[k].target()] = k;
             int victim = -1, best = -1;
             for (int p = n_local - 1; p >= 0; --p) {   // ties: prefer high local positions
                 const int lq = inv[p];
-                if (lq == g.control) continue;          // keeping the control local is not required, but cheap
+                if (lq == g.control()) continue;        // keep this gate's control local
                 if (next_use[lq] > best) { best = next_use[lq]; victim = p; }
             }
-            emit_swap(perm[g.target], victim);
+            emit_swap(perm[g.target()], victim);
         }
         HostGate pg = g;
-        pg.target = perm[g.target];
-        pg.control = g.control >= 0 ? perm[g.control] : -1;
+        pg.tmask = map_mask(g.tmask);
+        pg.cmask = map_mask(g.cmask);
         local_step().gates.push_back(pg);
     }
 
@@ -227,8 +333,7 @@ std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n
             if (perm[gp] == gp) continue;
             int x = perm[gp];                 // where logical gp lives now
             if (x >= n_local) {               // on another rank-index position: bounce through a local one
-                // pick a local position holding a qubit that belongs to a local position
-                int l = n_local - 1;
+                const int l = n_local - 1;
                 emit_swap(x, l);
                 x = l;
             }

@@ -2,7 +2,10 @@
 //
 // Takes the reference's per-gate stream (one FFI call per gate in
 // /root/reference/src/qubit_backend/circuit.rs:346-368) and turns it into a short list of passes
-// over HBM.  Three levels:
+// over HBM.  Four levels:
+//   0. fuse_diagonal_runs: runs of diagonal gates and CNOTs whose CNOTs cancel (e.g. the
+//      RZ-CNOT-RZ-CNOT controlled-phase decomposition) become parity-phase ops: no data movement,
+//      mutually commuting, foldable into one lazy scalar per thread;
 //   1. distributed level (plan_distributed): logical->physical qubit map, global<->local qubit
 //      swaps replacing the reference's per-gate full-chunk exchange
 //      (src/qubit_backend/circuit_distributed_gpu.rs:40-147);
@@ -17,18 +20,24 @@
 
 namespace dvd {
 
+// A gate on qubit masks.  Non-diagonal: tmask is one-hot (the target), cmask one-hot or 0.
+// Diagonal: multiply by (parity(x & tmask) ? m11 : m00) where cmask == 0 or parity(x & cmask) == 1.
 struct HostGate {
-    int target;     // qubit index (logical on input to plan_distributed, physical for plan_local)
-    int control;    // -1 = none
-    double m[8];    // row-major complex 2x2
-    int gate_idx;   // caller's index
+    uint64_t tmask = 0;
+    uint64_t cmask = 0;
+    double m[8];
+    int gate_idx = -1;   // caller's index, -1 for fused / layout-restoring ops
+    bool diag = false;
+    int target() const { return __builtin_ctzll(tmask); }
+    int control() const { return cmask ? __builtin_ctzll(cmask) : -1; }
 };
+
+HostGate make_gate(int target, int control, const double m[8], int gate_idx);
 
 struct Pass {
     PassDesc desc;
     std::vector<DevOp> ops;
     int n_switches = 0;        // stage switches inside the pass (shared-memory transposes)
-    int n_controlled = 0;
 };
 
 struct PlanOptions {
@@ -41,8 +50,11 @@ struct PlanOptions {
 void classify_gate(const double m[8], int32_t* kind, int8_t* d0_is_one);
 inline bool is_diagonal(const double m[8]) { return m[2] == 0.0 && m[3] == 0.0 && m[4] == 0.0 && m[5] == 0.0; }
 
+// Level 0.  Exact algebra on the gate list (no reordering across non-diagonal gates).
+std::vector<HostGate> fuse_diagonal_runs(const std::vector<HostGate>& gates);
+
 // Plan gates that are all executable locally: every non-diagonal gate has target < n_local.
-// Qubits >= n_local (rank-index qubits) may appear as controls or as targets of diagonal gates.
+// Qubits >= n_local (rank-index qubits) may appear in control masks and in diagonal gates.
 // Requires n_local >= TILE_BITS.
 std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, int n_total,
                              const PlanOptions& opt);

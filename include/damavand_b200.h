@@ -134,11 +134,11 @@ int dvd_timer_end(dvd_state* s, double* elapsed_ms);
 int dvd_set_unfused(dvd_state* s, int unfused);
 
 /* ---- planner inspection (host only, no GPU needed) ----------------------------------------- */
-/* Runs the pass planner on a gate list for a state of n_total qubits with n_local local qubits and
- * writes a flat int32 description:
- *   [n_passes, then per pass: tile_q[12], n_switches, n_ops, then per op: gate_idx, kind, group, tpos, cpos]
+/* Runs the pass planner on a gate list for a state of n_total qubits with n_local local qubits
+ * (fuse != 0: after the diagonal-run fusion pre-pass) and writes a flat int32 description:
+ *   [n_passes, then per pass: tile_q[12], n_switches, n_ops, then per op: gate_idx, kind, group, treg, cregm]
  * Returns the number of int32 written, or -(needed) if cap is too small, or INT64_MIN on error. */
-int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates,
+int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates, int fuse,
                        int32_t* out, int64_t cap);
 /* Runs the distributed planner: perm_io[logical] = physical (in/out).  Output:
  *   [n_steps, then per step: kind (0 local gates, 1 swap), a, b, n_gates, then per gate: gate_idx, target, control]

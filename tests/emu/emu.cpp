@@ -22,11 +22,16 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
     const uint64_t ctas = 1ull << (pd.n_local - TILE_BITS);
     std::vector<cplx> tile(TILE_AMPS);
     static cplx regs[NTHREADS][NREG];
+    static ThreadCtx ctx[NTHREADS];
     for (uint64_t cta = 0; cta < ctas; ++cta) {
         const uint64_t base = cta_base(pd, cta);
         const uint64_t gbase = base | pd.rank_bits;
-        for (int tid = 0; tid < NTHREADS; ++tid)
+        for (int tid = 0; tid < NTHREADS; ++tid) {
             for (int j = 0; j < NREG; ++j) regs[tid][j] = amp[base + tile_offset(pd, stage_idx(IO_GROUP, tid, j))];
+            ctx[tid].pidx = gbase | tile_offset(pd, stage_idx(IO_GROUP, tid, 0));
+            ctx[tid].ph = cplx{1.0, 0.0};
+            ctx[tid].ph_dirty = false;
+        }
         int cur = IO_GROUP;
         auto do_switch = [&](int to) {
             for (int tid = 0; tid < NTHREADS; ++tid)
@@ -36,10 +41,15 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
             cur = to;
         };
         for (const DevOp& op : pass.ops) {
-            if (op.group >= 0 && op.group != cur) do_switch(op.group);
-            if (op.kind != K_DIAG && (op.tpos < 0 || (op.tpos >> 2) != cur)) throw std::runtime_error("emu: op not in its register group");
-            for (int tid = 0; tid < NTHREADS; ++tid) apply_op(regs[tid], op, cur, stage_idx(cur, tid, 0), gbase);
+            if (op.group >= 0 && op.group != cur) {
+                for (int tid = 0; tid < NTHREADS; ++tid) flush_phase(regs[tid], ctx[tid]);
+                do_switch(op.group);
+                for (int tid = 0; tid < NTHREADS; ++tid) ctx[tid].pidx = gbase | tile_offset(pd, stage_idx(cur, tid, 0));
+            }
+            if (op.kind != K_DIAG && (op.group != cur || op.treg < 0 || op.treg >= REG_BITS)) throw std::runtime_error("emu: op not in its register group");
+            for (int tid = 0; tid < NTHREADS; ++tid) apply_op(regs[tid], op, ctx[tid]);
         }
+        for (int tid = 0; tid < NTHREADS; ++tid) flush_phase(regs[tid], ctx[tid]);
         if (cur != IO_GROUP) do_switch(IO_GROUP);
         for (int tid = 0; tid < NTHREADS; ++tid)
             for (int j = 0; j < NREG; ++j) amp[base + tile_offset(pd, stage_idx(IO_GROUP, tid, j))] = regs[tid][j];
@@ -48,7 +58,7 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
 
 static void run_simple(cplx* amp, int n_local, uint64_t rank_bits, const HostGate& g) {
     const uint64_t n = 1ull << n_local;
-    const int t = g.target, c = g.control;
+    const int t = g.target(), c = g.control();
     if (t < n_local) {
         for (uint64_t k = 0; k < n / 2; ++k) {
             const uint64_t i0 = ((k >> t) << (t + 1)) | (k & ((1ull << t) - 1)), i1 = i0 | (1ull << t);
@@ -67,11 +77,8 @@ static void run_simple(cplx* amp, int n_local, uint64_t rank_bits, const HostGat
 }
 
 static std::vector<HostGate> conv(const dvd_gate* gates, int64_t n) {
-    std::vector<HostGate> v((size_t)n);
-    for (int64_t i = 0; i < n; ++i) {
-        v[i].target = gates[i].target; v[i].control = gates[i].control; v[i].gate_idx = (int)i;
-        std::memcpy(v[i].m, gates[i].m, sizeof v[i].m);
-    }
+    std::vector<HostGate> v;
+    for (int64_t i = 0; i < n; ++i) v.push_back(make_gate(gates[i].target, gates[i].control, gates[i].m, (int)i));
     return v;
 }
 
@@ -82,7 +89,7 @@ extern "C" {
 static std::string g_err;
 const char* emu_error() { return g_err.c_str(); }
 
-int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, double* state, int64_t* stats /*[4]*/) {
+int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int fuse, double* state, int64_t* stats /*[4]*/) {
     try {
         int g = 0; while ((1 << g) < world) ++g;
         const int n_local = n_qubits - g;
@@ -92,6 +99,7 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, dou
         for (int q = 0; q < n_qubits; ++q) perm[q] = q;
         std::vector<DistStep> steps;
         std::vector<HostGate> hg = conv(gates, n_gates);
+        if (fuse && n_local >= TILE_BITS) hg = fuse_diagonal_runs(hg);
         if (world > 1) steps = plan_distributed(hg, n_qubits, n_local, perm, true);
         else { DistStep st; st.kind = DistStep::LOCAL_GATES; st.gates = hg; steps.push_back(st); }
         for (int q = 0; q < n_qubits; ++q) if (perm[q] != q) throw std::runtime_error("emu: layout not restored");

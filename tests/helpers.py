@@ -53,7 +53,7 @@ def emu():
         if not os.path.exists(EMU_LIB) or any(os.path.getmtime(d) > os.path.getmtime(EMU_LIB) for d in deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", EMU_LIB, src])
         L = ctypes.CDLL(EMU_LIB)
-        L.emu_run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(_lib.Gate), ctypes.c_int64,
+        L.emu_run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(_lib.Gate), ctypes.c_int64, ctypes.c_int,
                               ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
         L.emu_run.restype = ctypes.c_int
         L.emu_error.restype = ctypes.c_char_p
@@ -62,7 +62,7 @@ def emu():
     return _emu
 
 
-def emu_run(oracle_circ: OracleCircuit, world: int = 1, state=None):
+def emu_run(oracle_circ: OracleCircuit, world: int = 1, state=None, fuse: bool = True):
     """Run the recorded gates of `oracle_circ` through the CPU replay of the CUDA path."""
     n = oracle_circ.num_qubits
     arr, ng = gate_array(oracle_circ)
@@ -70,7 +70,7 @@ def emu_run(oracle_circ: OracleCircuit, world: int = 1, state=None):
         state = np.zeros(2 << n, dtype=np.float64)
         state[0] = 1.0
     stats = (ctypes.c_int64 * 4)()
-    rc = emu().emu_run(n, world, arr, ng, state.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stats)
+    rc = emu().emu_run(n, world, arr, ng, int(fuse), state.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stats)
     if rc != 0:
         raise RuntimeError(emu().emu_error().decode())
     return state.view(np.complex128), dict(passes=stats[0], swaps=stats[1], switches=stats[2], ops=stats[3])

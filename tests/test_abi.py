@@ -78,7 +78,7 @@ def test_planner_debug_entry_points():
     gates[1].target, gates[1].control = 13, 2; gates[1].m[:] = pg.pauli_x()
     gates[2].target, gates[2].control = 5, -1; gates[2].m[:] = pg.rotation_z(0.3)
     out = (ctypes.c_int32 * 256)()
-    k = L.dvd_plan_debug(n, n, gates, 3, out, 256)
+    k = L.dvd_plan_debug(n, n, gates, 3, 0, out, 256)
     assert k > 0 and out[0] == 1              # one pass
     tile = list(out[1:13])
     assert 13 in tile and tile[:3] == [0, 1, 2]
@@ -90,7 +90,7 @@ def test_planner_debug_entry_points():
     steps = out[0]
     assert steps >= 3
     # too-small buffer reports the needed size
-    assert L.dvd_plan_debug(n, n, gates, 3, out, 2) < 0
+    assert L.dvd_plan_debug(n, n, gates, 3, 0, out, 2) < 0
     # bad input is an error, not a crash
     gates[0].target = 99
-    assert L.dvd_plan_debug(n, n, gates, 3, out, 256) < -10**9
+    assert L.dvd_plan_debug(n, n, gates, 3, 1, out, 256) < -10**9
