@@ -56,6 +56,7 @@ struct dvd_state {
     std::vector<int> perm;      // logical -> physical (identity between flushes)
     DevOp* d_ops = nullptr; size_t d_ops_cap = 0;
     DevOp* h_ops = nullptr; size_t h_ops_cap = 0;
+    cplx* d_tabs = nullptr; cplx* h_tabs = nullptr; size_t tabs_cap = 0;   // phase tables of the queued passes
     double* d_tree = nullptr; bool tree_valid = false;
     double* d_scratch = nullptr; size_t scratch_doubles = 0;
     ncclComm_t comm = nullptr;
@@ -191,6 +192,8 @@ int dvd_destroy(dvd_state* s) {
     if (s->d_scratch) cudaFree(s->d_scratch);
     if (s->d_ops) cudaFree(s->d_ops);
     if (s->h_ops) cudaFreeHost(s->h_ops);
+    if (s->d_tabs) cudaFree(s->d_tabs);
+    if (s->h_tabs) cudaFreeHost(s->h_tabs);
     for (auto& b : s->swap_buf) if (b) cudaFree(b);
     for (int i = 0; i < 2; ++i) {
         if (s->ev_pack[i]) cudaEventDestroy(s->ev_pack[i]);
@@ -332,19 +335,19 @@ static int flush_impl(dvd_state* s) {
     }
     // plan every local step up front so that all ops go to the device in one copy
     std::vector<std::vector<Pass>> plans(steps.size());
-    size_t total_ops = 0;
+    size_t total_ops = 0, total_tabs = 0;
     if (tiled) {
         try {
             for (size_t i = 0; i < steps.size(); ++i)
                 if (steps[i].kind == DistStep::LOCAL_GATES) {
                     plans[i] = plan_local(steps[i].gates, s->n_local, s->n_qubits, s->opt);
-                    for (auto& p : plans[i]) total_ops += p.ops.size();
+                    for (auto& p : plans[i]) { total_ops += p.ops.size(); total_tabs += p.tables.size(); }
                 }
         } catch (const std::exception& e) {
             return fail(DVD_ERR_INTERNAL, std::string("planner: ") + e.what());
         }
+        CU(cudaStreamSynchronize(s->stream));   // the pinned staging buffers may still be in flight
         if (total_ops > s->h_ops_cap) {
-            CU(cudaStreamSynchronize(s->stream));
             if (s->h_ops) CU(cudaFreeHost(s->h_ops));
             if (s->d_ops) CU(cudaFree(s->d_ops));
             s->h_ops = nullptr; s->d_ops = nullptr; s->h_ops_cap = s->d_ops_cap = 0;
@@ -352,15 +355,27 @@ static int flush_impl(dvd_state* s) {
             CU(cudaMallocHost(&s->h_ops, cap * sizeof(DevOp)));
             CU(cudaMalloc(&s->d_ops, cap * sizeof(DevOp)));
             s->h_ops_cap = s->d_ops_cap = cap;
-        } else {
-            CU(cudaStreamSynchronize(s->stream));   // the pinned staging buffer may still be in flight
         }
-        size_t at = 0;
+        if (total_tabs > s->tabs_cap) {
+            if (s->h_tabs) CU(cudaFreeHost(s->h_tabs));
+            if (s->d_tabs) CU(cudaFree(s->d_tabs));
+            s->h_tabs = nullptr; s->d_tabs = nullptr; s->tabs_cap = 0;
+            const size_t cap = std::max<size_t>(total_tabs * 2, 64 * TABLE_ENTRIES);
+            CU(cudaMallocHost(&s->h_tabs, cap * sizeof(cplx)));
+            CU(cudaMalloc(&s->d_tabs, cap * sizeof(cplx)));
+            s->tabs_cap = cap;
+        }
+        size_t at = 0, tat = 0;
         for (auto& pl : plans)
-            for (auto& p : pl) { std::memcpy(s->h_ops + at, p.ops.data(), p.ops.size() * sizeof(DevOp)); at += p.ops.size(); }
+            for (auto& p : pl) {
+                std::memcpy(s->h_ops + at, p.ops.data(), p.ops.size() * sizeof(DevOp)); at += p.ops.size();
+                if (!p.tables.empty()) std::memcpy(s->h_tabs + tat, p.tables.data(), p.tables.size() * sizeof(cplx));
+                tat += p.tables.size();
+            }
         if (total_ops) CU(cudaMemcpyAsync(s->d_ops, s->h_ops, total_ops * sizeof(DevOp), cudaMemcpyHostToDevice, s->stream));
+        if (total_tabs) CU(cudaMemcpyAsync(s->d_tabs, s->h_tabs, total_tabs * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
     }
-    size_t at = 0;
+    size_t at = 0, tat = 0;
     for (size_t i = 0; i < steps.size(); ++i) {
         DistStep& st = steps[i];
         if (st.kind == DistStep::GLOBAL_SWAP) { TRY(global_swap(s, st.gq, st.lq)); continue; }
@@ -368,8 +383,9 @@ static int flush_impl(dvd_state* s) {
             for (auto& p : plans[i]) {
                 PassDesc pd = p.desc;
                 pd.rank_bits = s->rank_bits;
+                pd.tables = s->d_tabs + tat;
                 CU(launch_tile_pass(s->amp, s->d_ops + at, pd, s->stream));
-                at += p.ops.size();
+                at += p.ops.size(); tat += p.tables.size();
                 s->stats.kernel_launches++; s->stats.tile_passes++;
                 s->stats.stage_switches += p.n_switches;
                 s->stats.pass_bytes += 2.0 * chunk_bytes;
@@ -647,8 +663,8 @@ int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t 
             v.push_back(p.n_switches);
             v.push_back((int32_t)p.ops.size());
             for (auto& op : p.ops) {
-                v.push_back(op.gate_idx); v.push_back(op.kind); v.push_back(op.group);
-                v.push_back(op.treg); v.push_back(op.cregm);
+                v.push_back(op.gate_idx); v.push_back(op.code); v.push_back(op.group);
+                v.push_back(op.tab); v.push_back(op.regm);
             }
         }
         if ((int64_t)v.size() > cap) return -(int64_t)v.size();

@@ -25,6 +25,22 @@ __device__ __forceinline__ void switch_stage(cplx* tile, cplx (&a)[NREG], int ti
     for (int j = 0; j < NREG; ++j) a[j] = tile[swz(stage_idx(to, tid, j))];
 }
 
+// Global <-> register layout = IO_GROUP stage: lanes run over tile positions 0..4, i.e. over
+// >= 128 contiguous bytes (tile positions 0..2 are always physical qubits 0..2).  The addressing is
+// recomputed for the write-back (opaque re-read of %tid / %ctaid) so that it does not occupy
+// registers while the gates run.
+struct IoAddr { cplx* p0; uint64_t hs[REG_BITS]; };
+__device__ __forceinline__ IoAddr io_addr(cplx* amp, const PassDesc& pd) {
+    unsigned tid, cta;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(cta));
+    IoAddr io;
+    io.p0 = amp + cta_base(pd, (uint64_t)cta) + tile_offset(pd, stage_idx(IO_GROUP, (int)tid, 0));
+#pragma unroll
+    for (int k = 0; k < REG_BITS; ++k) io.hs[k] = 1ull << pd.tile_q[IO_GROUP * REG_BITS + k];
+    return io;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 2)
 k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_constant__ PassDesc pd) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -32,32 +48,25 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
     __shared__ DevOp sops[OPS_CHUNK];
 
     const int tid = threadIdx.x;
-    const uint64_t base = cta_base(pd, (uint64_t)blockIdx.x);
-    const uint64_t gbase = base | pd.rank_bits;
-
-    // global <-> register layout = IO_GROUP stage: lanes run over tile positions 0..4, i.e. over
-    // >= 128 contiguous bytes (tile positions 0..2 are always physical qubits 0..2)
-    const int tb_io = stage_idx(IO_GROUP, tid, 0);
-    const uint64_t off_io = tile_offset(pd, tb_io);
-    cplx* p0 = amp + base + off_io;
-    uint64_t hs[REG_BITS];
-#pragma unroll
-    for (int k = 0; k < REG_BITS; ++k) hs[k] = 1ull << pd.tile_q[IO_GROUP * REG_BITS + k];
-
     cplx a[NREG];
+    {
+        const IoAddr io = io_addr(amp, pd);
 #pragma unroll
-    for (int j = 0; j < NREG; ++j) {
-        uint64_t off = 0;
+        for (int j = 0; j < NREG; ++j) {
+            uint64_t off = 0;
 #pragma unroll
-        for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += hs[k];
-        a[j] = p0[off];
+            for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += io.hs[k];
+            a[j] = io.p0[off];
+        }
     }
 
+    const uint64_t gbase = cta_base(pd, (uint64_t)blockIdx.x) | pd.rank_bits;
     int cur = IO_GROUP;
     ThreadCtx ctx;
-    ctx.pidx = gbase | off_io;
+    ctx.pidx = gbase | tile_offset(pd, stage_idx(IO_GROUP, tid, 0));
     ctx.ph = cplx{1.0, 0.0};
     ctx.ph_dirty = false;
+    ctx.tables = pd.tables;
     for (int c0 = 0; c0 < pd.n_ops; c0 += OPS_CHUNK) {
         const int n = min(OPS_CHUNK, pd.n_ops - c0);
         __syncthreads();  // previous chunk fully consumed
@@ -71,11 +80,11 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
         for (int k = 0; k < n; ++k) {
             const DevOp& op = sops[k];
             const int g = op.group;
-            if (g >= 0 && g != cur) {
+            if (g != cur) {
                 flush_phase(a, ctx);
                 switch_stage(tile, a, tid, cur, g);
                 cur = g;
-                ctx.pidx = gbase | tile_offset(pd, stage_idx(g, tid, 0));
+                ctx.pidx = (cta_base(pd, (uint64_t)blockIdx.x) | pd.rank_bits) | tile_offset(pd, stage_idx(g, tid, 0));
             }
             apply_op(a, op, ctx);
         }
@@ -83,12 +92,15 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
     flush_phase(a, ctx);
     if (cur != IO_GROUP) switch_stage(tile, a, tid, cur, IO_GROUP);
 
+    {
+        const IoAddr io = io_addr(amp, pd);
 #pragma unroll
-    for (int j = 0; j < NREG; ++j) {
-        uint64_t off = 0;
+        for (int j = 0; j < NREG; ++j) {
+            uint64_t off = 0;
 #pragma unroll
-        for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += hs[k];
-        p0[off] = a[j];
+            for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += io.hs[k];
+            io.p0[off] = a[j];
+        }
     }
 }
 

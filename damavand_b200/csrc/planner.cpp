@@ -2,6 +2,8 @@
 #include "planner.h"
 
 #include <algorithm>
+#include <cmath>
+#include <complex>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -144,6 +146,263 @@ struct Blocked {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------
+// Phase polynomial of the diagonal gates of a pass.
+//
+// Every 1- and 2-qubit diagonal term is rewritten as monomials over the index bits,
+//     K * prod_q a_q^{x_q} * prod_{q<q'} b_qq'^{x_q x_q'},
+// accumulated in extended precision and emitted as late as commutation allows: a term on qubits
+// {q,q'} commutes with every gate that does not TARGET q or q' non-diagonally.  While a qubit is
+// thread-level its terms cost a table lookup per thread; the terms of a register qubit are forced out
+// only when a non-diagonal gate is about to hit that qubit (or at the end of the pass).
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+using cl = std::complex<long double>;
+
+bool is_one(const cl& v) { return std::abs(v - cl(1, 0)) < 1e-17L; }
+
+struct DiagAcc {
+    cl K{1, 0};
+    std::map<int, cl> a;
+    std::map<std::pair<int, int>, cl> b;
+
+    void mul_a(int q, const cl& f) { auto it = a.find(q); if (it == a.end()) a[q] = f; else it->second *= f; }
+    void mul_b(int q, int p, const cl& f) {
+        auto key = std::make_pair(std::min(q, p), std::max(q, p));
+        auto it = b.find(key); if (it == b.end()) b[key] = f; else it->second *= f;
+    }
+    // false: not a simple 1-/2-qubit phase (caller emits the generic op)
+    bool add(const HostGate& g) {
+        const cl d0((long double)g.m[0], (long double)g.m[1]), d1((long double)g.m[6], (long double)g.m[7]);
+        const long double n0 = std::norm(d0), n1 = std::norm(d1);
+        if (!(n0 > 1e-30L) || !(n1 > 1e-30L) || !std::isfinite((double)n0) || !std::isfinite((double)n1)) return false;
+        const int nt = __builtin_popcountll(g.tmask), nc = __builtin_popcountll(g.cmask);
+        if (g.tmask & g.cmask) return false;
+        if (nc == 0 && nt == 0) { K *= d0; return true; }
+        if (nc == 0 && nt == 1) { K *= d0; mul_a(__builtin_ctzll(g.tmask), d1 / d0); return true; }
+        if (nc == 0 && nt == 2) {
+            const int q = __builtin_ctzll(g.tmask), p = 63 - __builtin_clzll(g.tmask);
+            const cl r = d1 / d0;
+            K *= d0; mul_a(q, r); mul_a(p, r); mul_b(q, p, cl(1, 0) / (r * r));
+            return true;
+        }
+        if (nc == 1 && nt == 1) {
+            const int c = __builtin_ctzll(g.cmask), t = __builtin_ctzll(g.tmask);
+            mul_a(c, d0); mul_b(c, t, d1 / d0);
+            return true;
+        }
+        return false;
+    }
+};
+
+cplx to_cplx(const cl& v) { return cplx{(double)v.real(), (double)v.imag()}; }
+
+struct StageEmitter {
+    Pass& pass;
+    DiagAcc& acc;
+    int n_total;
+    int group = IO_GROUP;
+    int regq[REG_BITS];
+    uint64_t regphys = 0;
+
+    void set_stage(int g) {
+        group = g; regphys = 0;
+        for (int k = 0; k < REG_BITS; ++k) { regq[k] = pass.desc.tile_q[g * REG_BITS + k]; regphys |= 1ull << regq[k]; }
+    }
+    int reg_of(int q) const { for (int k = 0; k < REG_BITS; ++k) if (regq[k] == q) return k; return -1; }
+    uint8_t reg_mask(uint64_t mask) const {
+        uint8_t r = 0;
+        for (int k = 0; k < REG_BITS; ++k) if ((mask >> regq[k]) & 1) r |= (uint8_t)(1 << k);
+        return r;
+    }
+    DevOp blank(int gate_idx) const {
+        DevOp op; std::memset(&op, 0, sizeof(op));
+        op.group = (int8_t)group; op.gate_idx = gate_idx; op.creg = -1;
+        return op;
+    }
+    // Sub-tables for prod_c f_c^{x_c} * scale over thread-level partners; returns (tab, bytemask).
+    void build_tables(const std::vector<std::pair<int, cl>>& partners, const cl& scale, int32_t* tab, uint8_t* bytes) {
+        uint8_t mask = 0;
+        for (auto& pr : partners) mask |= (uint8_t)(1u << (pr.first / 8));
+        if (mask == 0) mask = 1;      // constant only: one sub-table
+        *tab = (int32_t)(pass.tables.size() / TABLE_ENTRIES);
+        *bytes = mask;
+        bool first = true;
+        for (int by = 0; by < MAX_INDEX_BYTES; ++by) {
+            if (!((mask >> by) & 1)) continue;
+            std::vector<cl> e(TABLE_ENTRIES, first ? scale : cl(1, 0));
+            first = false;
+            for (auto& pr : partners) {
+                if (pr.first / 8 != by) continue;
+                const int bit = 1 << (pr.first % 8);
+                for (int v = 0; v < TABLE_ENTRIES; ++v) if (v & bit) e[v] *= pr.second;
+            }
+            for (int v = 0; v < TABLE_ENTRIES; ++v) pass.tables.push_back(to_cplx(e[v]));
+        }
+    }
+    // Emit every accumulated term that involves register qubit q (register bit r of this stage).
+    void flush_qubit(int q, cl* fold_K = nullptr) {
+        const int r = reg_of(q);
+        if (r < 0) throw std::runtime_error("plan_local: flush of a non-register qubit");
+        cl A(1, 0);
+        { auto it = acc.a.find(q); if (it != acc.a.end()) { A = it->second; acc.a.erase(it); } }
+        std::vector<std::pair<int, cl>> partners;
+        for (auto it = acc.b.begin(); it != acc.b.end();) {
+            if (it->first.first != q && it->first.second != q) { ++it; continue; }
+            const int c = it->first.first == q ? it->first.second : it->first.first;
+            const int rc = reg_of(c);
+            if (!is_one(it->second)) {
+                if (rc >= 0) {
+                    DevOp op = blank(-1);
+                    op.code = OC_PAIR + pair_id(std::min(r, rc), std::max(r, rc));
+                    const cplx f = to_cplx(it->second);
+                    op.m[0] = f.x; op.m[1] = f.y;
+                    pass.ops.push_back(op);
+                } else {
+                    partners.push_back({c, it->second});
+                }
+            }
+            it = acc.b.erase(it);
+        }
+        if (!partners.empty()) {
+            DevOp op = blank(-1);
+            op.code = OC_TABLE_REG + r;
+            build_tables(partners, A, &op.tab, &op.regm);
+            pass.ops.push_back(op);
+        } else if (!is_one(A)) {
+            DevOp op = blank(-1);
+            op.code = OC_DIAG1 + r;
+            cl d0(1, 0);
+            if (fold_K && !is_one(*fold_K)) { d0 = *fold_K; *fold_K = cl(1, 0); }   // the pass constant rides along
+            else op.flags = F_D0_ONE;
+            const cplx f0 = to_cplx(d0), f1 = to_cplx(d0 * A);
+            op.m[0] = f0.x; op.m[1] = f0.y; op.m[6] = f1.x; op.m[7] = f1.y;
+            pass.ops.push_back(op);
+        }
+    }
+    // End of the pass: everything that is left.
+    void flush_all() {
+        // if nothing thread-level is left, the constant K can ride on a register-bit op for free
+        bool thread_terms = false;
+        for (auto& kv : acc.a) if (reg_of(kv.first) < 0 && !is_one(kv.second)) thread_terms = true;
+        for (auto& kv : acc.b)
+            if (reg_of(kv.first.first) < 0 && reg_of(kv.first.second) < 0 && !is_one(kv.second)) thread_terms = true;
+        for (int k = 0; k < REG_BITS; ++k) flush_qubit(regq[k], thread_terms ? nullptr : &acc.K);
+        // only thread-level qubits remain
+        std::vector<std::pair<int, cl>> ones;
+        for (auto& kv : acc.a) if (!is_one(kv.second)) ones.push_back({kv.first, kv.second});
+        std::vector<std::pair<std::pair<int, int>, cl>> same, cross;
+        for (auto& kv : acc.b) {
+            if (is_one(kv.second)) continue;
+            (kv.first.first / 8 == kv.first.second / 8 ? same : cross).push_back({kv.first, kv.second});
+        }
+        if (same.empty() && ones.size() <= 2) {
+            bool k_done = is_one(acc.K);
+            for (auto& pr : ones) {
+                DevOp op = blank(-1);
+                op.code = OC_PHASE;
+                op.tmask = 1ull << pr.first;
+                const cl d0 = k_done ? cl(1, 0) : acc.K;
+                if (k_done) op.flags = F_D0_ONE;
+                k_done = true;
+                const cplx c0 = to_cplx(d0), c1 = to_cplx(d0 * pr.second);
+                op.m[0] = c0.x; op.m[1] = c0.y; op.m[6] = c1.x; op.m[7] = c1.y;
+                pass.ops.push_back(op);
+            }
+            if (!k_done) {
+                DevOp op = blank(-1);
+                op.code = OC_PHASE;
+                const cplx c0 = to_cplx(acc.K);
+                op.m[0] = c0.x; op.m[1] = c0.y; op.m[6] = c0.x; op.m[7] = c0.y;
+                pass.ops.push_back(op);
+            }
+        } else {
+            // one table op: K, the 1-body factors and the pairs that live inside one byte
+            DevOp op = blank(-1);
+            op.code = OC_TABLE;
+            uint8_t mask = 0;
+            for (auto& pr : ones) mask |= (uint8_t)(1u << (pr.first / 8));
+            for (auto& pr : same) mask |= (uint8_t)(1u << (pr.first.first / 8));
+            if (mask == 0) mask = 1;
+            op.tab = (int32_t)(pass.tables.size() / TABLE_ENTRIES);
+            op.regm = mask;
+            bool first = true;
+            for (int by = 0; by < MAX_INDEX_BYTES; ++by) {
+                if (!((mask >> by) & 1)) continue;
+                for (int v = 0; v < TABLE_ENTRIES; ++v) {
+                    cl e = first ? acc.K : cl(1, 0);
+                    for (auto& pr : ones)
+                        if (pr.first / 8 == by && ((v >> (pr.first % 8)) & 1)) e *= pr.second;
+                    for (auto& pr : same)
+                        if (pr.first.first / 8 == by && ((v >> (pr.first.first % 8)) & 1) && ((v >> (pr.first.second % 8)) & 1))
+                            e *= pr.second;
+                    pass.tables.push_back(to_cplx(e));
+                }
+                first = false;
+            }
+            pass.ops.push_back(op);
+        }
+        // pairs that straddle two bytes: pivot tables, greedy on the pair graph
+        while (!cross.empty()) {
+            std::map<int, int> deg;
+            for (auto& pr : cross) { deg[pr.first.first]++; deg[pr.first.second]++; }
+            int pivot = -1, best = 0;
+            for (auto& kv : deg) if (kv.second > best) { best = kv.second; pivot = kv.first; }
+            std::vector<std::pair<int, cl>> partners;
+            std::vector<std::pair<std::pair<int, int>, cl>> rest;
+            for (auto& pr : cross) {
+                if (pr.first.first == pivot) partners.push_back({pr.first.second, pr.second});
+                else if (pr.first.second == pivot) partners.push_back({pr.first.first, pr.second});
+                else rest.push_back(pr);
+            }
+            DevOp op = blank(-1);
+            op.code = OC_TABLE;
+            op.tmask = 1ull << pivot;
+            build_tables(partners, cl(1, 0), &op.tab, &op.regm);
+            pass.ops.push_back(op);
+            cross.swap(rest);
+        }
+        acc = DiagAcc();
+    }
+    void emit_gate(const HostGate& g) {
+        if (g.diag) {
+            if (acc.add(g)) return;
+            DevOp op = blank(g.gate_idx);
+            std::memcpy(op.m, g.m, sizeof(op.m));
+            const uint8_t tregm = reg_mask(g.tmask), cregm = reg_mask(g.cmask);
+            op.tmask = g.tmask & ~regphys;
+            op.cmask = g.cmask & ~regphys;
+            if (g.m[0] == 1.0 && g.m[1] == 0.0) op.flags |= F_D0_ONE;
+            if (g.cmask) op.flags |= F_HAS_CTRL;
+            if (tregm == 0 && cregm == 0) op.code = OC_PHASE;
+            else { op.code = OC_DIAGGEN; op.regm = (uint8_t)(tregm | (cregm << 4)); }
+            pass.ops.push_back(op);
+            return;
+        }
+        const int t = g.target();
+        const int treg = reg_of(t);
+        if (treg < 0) throw std::runtime_error("plan_local: gate outside its register group");
+        flush_qubit(t);
+        DevOp op = blank(g.gate_idx);
+        std::memcpy(op.m, g.m, sizeof(op.m));
+        int32_t kind; int8_t d0;
+        classify_gate(g.m, &kind, &d0);
+        if (kind == K_SWAP) kind = K_ANTIDIAG;   // interim: X / CNOT as arithmetic, never as register moves
+        const int c = g.control();
+        const int creg = c >= 0 ? reg_of(c) : -1;
+        if (creg >= 0) {
+            op.code = OC_CGEN + treg; op.creg = (int8_t)creg;
+        } else {
+            op.cmask = g.cmask;
+            op.code = OC_GATE + kind * 4 + treg;
+        }
+        pass.ops.push_back(op);
+    }
+};
+
+}  // namespace
+
 std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, int n_total,
                              const PlanOptions& opt) {
     if (n_local < TILE_BITS) throw std::runtime_error("plan_local: n_local < TILE_BITS");
@@ -221,53 +480,30 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
 
         // ---- stage level: sweep per register group ---------------------------------------------------
         std::vector<int> remaining = taken;
+        DiagAcc acc;
+        StageEmitter em{pass, acc, n_total};
         int cur = IO_GROUP;
+        em.set_stage(cur);
         while (!remaining.empty()) {
             // keep `cur` if the first remaining op can run there, else move to its group
             {
                 const HostGate& g0 = gates[remaining[0]];
                 if (!g0.diag) {
                     const int grp = pos_of[g0.target()] / REG_BITS;
-                    if (grp != cur) { cur = grp; ++pass.n_switches; }
+                    if (grp != cur) { cur = grp; ++pass.n_switches; em.set_stage(cur); }
                 }
             }
-            uint64_t regphys = 0;          // physical qubits living in registers in this stage
-            int regq[REG_BITS];
-            for (int k = 0; k < REG_BITS; ++k) { regq[k] = pass.desc.tile_q[cur * REG_BITS + k]; regphys |= 1ull << regq[k]; }
-            auto reg_mask = [&](uint64_t mask) {
-                uint8_t r = 0;
-                for (int k = 0; k < REG_BITS; ++k) if ((mask >> regq[k]) & 1) r |= (uint8_t)(1 << k);
-                return r;
-            };
             Blocked b2;
             std::vector<int> rem2;
             for (int gi : remaining) {
                 const HostGate& g = gates[gi];
                 const bool ok = b2.can_pass(g) && (g.diag || pos_of[g.target()] / REG_BITS == cur);
                 if (!ok) { b2.skip(g); rem2.push_back(gi); continue; }
-                DevOp op;
-                std::memset(&op, 0, sizeof(op));
-                std::memcpy(op.m, g.m, sizeof(op.m));
-                classify_gate(g.m, &op.kind, &op.d0_is_one);
-                op.gate_idx = g.gate_idx;
-                op.has_ctrl = g.cmask != 0;
-                op.cregm = reg_mask(g.cmask);
-                op.cmask = g.cmask & ~regphys;
-                if (g.diag) {
-                    op.group = -1;
-                    op.treg = -1;
-                    op.tregm = reg_mask(g.tmask);
-                    op.tmask = g.tmask & ~regphys;
-                } else {
-                    op.group = (int8_t)cur;
-                    op.treg = (int8_t)(pos_of[g.target()] % REG_BITS);
-                    op.tregm = 0;
-                    op.tmask = 0;
-                }
-                pass.ops.push_back(op);
+                em.emit_gate(g);
             }
             remaining.swap(rem2);
         }
+        em.flush_all();
         if (cur != IO_GROUP) ++pass.n_switches;
         pass.desc.n_ops = (int)pass.ops.size();
         passes.push_back(std::move(pass));

@@ -11,7 +11,8 @@
 //      (src/qubit_backend/circuit_distributed_gpu.rs:40-147);
 //   2. pass level (plan_local): choose TILE_BITS physical qubits per pass and pull every gate that
 //      commutes its way to the front and fits the tile;
-//   3. stage level: order the gates of a pass so that consecutive gates share a register group.
+//   3. stage level: order the gates of a pass so that consecutive gates share a register group, and
+//      compile its diagonal gates into a phase polynomial emitted as table / register-bit / pair ops.
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -37,6 +38,7 @@ HostGate make_gate(int target, int control, const double m[8], int gate_idx);
 struct Pass {
     PassDesc desc;
     std::vector<DevOp> ops;
+    std::vector<cplx> tables;  // phase sub-tables (TABLE_ENTRIES each) referenced by ops[].tab
     int n_switches = 0;        // stage switches inside the pass (shared-memory transposes)
 };
 

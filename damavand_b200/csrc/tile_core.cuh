@@ -9,6 +9,13 @@
 // qubits ("tile positions"), every thread owns 2^REG_BITS amplitudes in registers, and a whole
 // run of gates is applied per pass.  One thread owns both amplitudes of every pair it updates,
 // so there is no read/write race by construction.
+//
+// The op stream is a small instruction set (OpCode) decoded once per op with ONE dense switch;
+// every case is straight-line code over compile-time register indices.  Diagonal gates never
+// run as gates: the planner folds them into a phase polynomial per pass
+//     K * prod_q a_q^{x_q} * prod_{q<q'} b_qq'^{x_q x_q'}
+// and emits it as byte-indexed phase tables (thread-level bits), per-register-bit factors and
+// register-pair factors, at the latest point the commutation rules allow.
 #pragma once
 #include <stdint.h>
 
@@ -30,39 +37,52 @@ constexpr int NTHREADS = 1 << THREAD_BITS; // 256
 constexpr int NGROUPS = TILE_BITS / REG_BITS;  // 3 register groups: tile positions [4g, 4g+4)
 constexpr int IO_GROUP = NGROUPS - 1;      // global loads/stores use the group-2 layout (coalesced)
 constexpr int TILE_AMPS = 1 << TILE_BITS;
+constexpr int TABLE_ENTRIES = 256;         // one phase sub-table per byte of the physical index
+constexpr int MAX_INDEX_BYTES = 8;
 static_assert(REG_BITS == 4, "register masks are 4 bits wide");
 
+// Matrix classes the planner distinguishes (exact zero / one tests on the entries).
 enum OpKind : int32_t {
     K_GENERAL = 0,   // arbitrary complex 2x2
     K_REAL = 1,      // all four entries real (H, RY)
     K_RXLIKE = 2,    // real diagonal, purely imaginary off-diagonal (RX)
-    K_DIAG = 3,      // m01 = m10 = 0 (RZ, Z, S, T, and fused parity phases)
-    K_ANTIDIAG = 4,  // m00 = m11 = 0 (Y)
-    K_SWAP = 5,      // m01 = m10 = 1, m00 = m11 = 0 (X, CNOT): pure exchange
+    K_ANTIDIAG = 3,  // m00 = m11 = 0 (Y)
+    K_SWAP = 4,      // m01 = m10 = 1, m00 = m11 = 0 (X, CNOT): pure exchange
+    K_DIAG = 5,      // m01 = m10 = 0 (RZ, Z, S, T, fused parity phases)
 };
 
+// Device instruction set.
+enum OpCode : int32_t {
+    OC_GATE = 0,        // + kind*4 + treg (kind 0..3): 2x2 on register bit treg; control none / thread-level
+    OC_SWAP = 16,       // + treg: exchange along register bit treg (X; CNOT with thread-level control)
+    OC_CSWAP = 20,      // + treg*4 + creg: CNOT with both qubits in registers
+    OC_CGEN = 36,       // + treg: general 2x2 on treg, control = register bit op.creg (rare)
+    OC_DIAG1 = 40,      // + r: registers with bit r set *= d1, the others *= d0 (unless d0 == 1)
+    OC_PHASE = 44,      // thread-level parity phase -> lazy per-thread scalar
+    OC_DIAGGEN = 45,    // generic parity phase with register bits in its masks (fallback)
+    OC_TABLE = 46,      // product of phase-table lookups -> lazy scalar (optional thread-level pivot)
+    OC_TABLE_REG = 47,  // + r: product of phase-table lookups -> registers with bit r set
+    OC_PAIR = 51,       // + pair id: registers with both bits set *= (m[0], m[1])
+    OC_COUNT = 57,
+};
+DVD_HD int pair_id(int r0, int r1) {   // r0 < r1
+    return r0 == 0 ? r1 - 1 : r0 == 1 ? r1 + 1 : 5;
+}
+
+enum OpFlags : uint8_t { F_D0_ONE = 1, F_HAS_CTRL = 2 };
+
 // One operation as the device sees it, fully decoded by the planner for the stage it runs in.
-//
-// Diagonal ops are "parity phases": the amplitude with physical index x is multiplied by
-// (parity(x & T) ? m11 : m00) when the op is uncontrolled or parity(x & C) == 1.  T and C are
-// given split into the bits that live in the executing thread's registers (tregm / cregm, 4-bit
-// masks over the current register group) and all other physical bits (tmask / cmask).  A plain
-// RZ / controlled-phase has one-hot masks; wider masks come from fusing CNOT-conjugated runs.
-// Non-diagonal ops always target one register bit (treg); their control is one physical qubit,
-// either another register bit (cregm one-hot) or a thread-level bit (cmask one-hot).
 struct alignas(16) DevOp {
     double m[8];       // m00.re m00.im m01.re m01.im m10.re m10.im m11.re m11.im
-    uint64_t tmask;    // diagonal: thread-level part of the target parity mask
+    uint64_t tmask;    // thread-level part of the target parity mask (diagonal ops, table pivot)
     uint64_t cmask;    // thread-level part of the control parity mask (0 = none)
-    int32_t kind;
-    int8_t group;      // register group the op must run in (non-diagonal), -1 = any
-    int8_t treg;       // non-diagonal: target register bit 0..3
-    uint8_t tregm;     // diagonal: register-level part of the target parity mask
-    uint8_t cregm;     // register-level part of the control parity mask
-    int8_t has_ctrl;
-    int8_t d0_is_one;  // diagonal with m00 == 1 exactly
-    int8_t pad[2];
+    int32_t code;      // OpCode (+ operands)
+    int32_t tab;       // table ops: first sub-table (units of TABLE_ENTRIES entries)
     int32_t gate_idx;  // caller's gate index (-1 for fused / layout ops)
+    int8_t group;      // register group the op runs in
+    int8_t creg;       // OC_CGEN: control register bit
+    uint8_t regm;      // OC_DIAGGEN: tregm | cregm << 4;  table ops: bytes of the index that have a sub-table
+    uint8_t flags;     // OpFlags
 };
 static_assert(sizeof(DevOp) == 96, "DevOp layout");
 
@@ -73,6 +93,7 @@ struct PassDesc {
     int32_t tile_q[TILE_BITS];    // physical qubit of each tile position
     int32_t sorted_q[TILE_BITS];  // the same qubits in ascending order
     uint64_t rank_bits;           // this rank's value of the global (rank-index) qubits, in place
+    const cplx* tables;           // phase tables of this pass (device pointer; host pointer in the replay)
 };
 
 // ---- index helpers ---------------------------------------------------------------------------
@@ -121,12 +142,14 @@ DVD_HD int parity4(int v) { return (0x6996 >> (v & 15)) & 1; }
 
 // ---- arithmetic --------------------------------------------------------------------------------
 DVD_HD cplx cmul(cplx a, double mr, double mi) { return cplx{a.x * mr - a.y * mi, a.x * mi + a.y * mr}; }
+DVD_HD cplx cmul(cplx a, cplx b) { return cmul(a, b.x, b.y); }
 
 // Per-thread context of the current stage.
 struct ThreadCtx {
     uint64_t pidx;   // physical index of register 0 (register bits zero), rank bits included
     cplx ph;         // lazily accumulated scalar phase common to all 16 registers
     bool ph_dirty;
+    const cplx* tables;   // phase tables of the pass
 };
 
 DVD_HD void flush_phase(cplx (&a)[NREG], ThreadCtx& ctx) {
@@ -157,92 +180,146 @@ DVD_HD void pair_update(cplx& a0, cplx& a1, const double (&m)[8]) {
     }
 }
 
-// All 8 pairs along register bit B; creg >= 0 restricts to the pairs whose register bit creg is 1.
+// All 8 pairs along register bit B.
 template <int B, int KIND>
-DVD_HD void apply_pairs(cplx (&a)[NREG], const double (&m)[8], int creg) {
+DVD_HD void gate_all(cplx (&a)[NREG], const double* mp) {
+    double m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = mp[k];
 #pragma unroll
     for (int k = 0; k < NREG / 2; ++k) {
         const int j0 = ((k >> B) << (B + 1)) | (k & ((1 << B) - 1));
-        const int j1 = j0 | (1 << B);
-        if (creg >= 0 && !((j0 >> creg) & 1)) continue;
-        pair_update<KIND>(a[j0], a[j1], m);
+        pair_update<KIND>(a[j0], a[j0 | (1 << B)], m);
     }
 }
-
+// The 4 pairs along B whose register bit C is set (C != B).
+template <int B, int C>
+DVD_HD void cswap(cplx (&a)[NREG]) {
+#pragma unroll
+    for (int k = 0; k < NREG / 2; ++k) {
+        const int j0 = ((k >> B) << (B + 1)) | (k & ((1 << B) - 1));
+        if (!((j0 >> C) & 1)) continue;
+        const cplx t = a[j0]; a[j0] = a[j0 | (1 << B)]; a[j0 | (1 << B)] = t;
+    }
+}
 template <int B>
-DVD_HD void apply_kind(cplx (&a)[NREG], int kind, const double (&m)[8], int creg) {
-    switch (kind) {
-        case K_GENERAL: apply_pairs<B, K_GENERAL>(a, m, creg); break;
-        case K_REAL: apply_pairs<B, K_REAL>(a, m, creg); break;
-        case K_RXLIKE: apply_pairs<B, K_RXLIKE>(a, m, creg); break;
-        case K_ANTIDIAG: apply_pairs<B, K_ANTIDIAG>(a, m, creg); break;
-        default: apply_pairs<B, K_SWAP>(a, m, creg); break;
+DVD_HD void cswap_b(cplx (&a)[NREG], int c) {
+    switch (c) {
+        case 0: if (B != 0) cswap<B, B == 0 ? 1 : 0>(a); break;
+        case 1: if (B != 1) cswap<B, B == 1 ? 0 : 1>(a); break;
+        case 2: if (B != 2) cswap<B, B == 2 ? 0 : 2>(a); break;
+        default: if (B != 3) cswap<B, B == 3 ? 0 : 3>(a); break;
+    }
+}
+// General 2x2 along B on the pairs whose register bit creg (runtime) is set.
+template <int B>
+DVD_HD void cgen(cplx (&a)[NREG], const double* mp, int creg) {
+    double m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = mp[k];
+#pragma unroll
+    for (int k = 0; k < NREG / 2; ++k) {
+        const int j0 = ((k >> B) << (B + 1)) | (k & ((1 << B) - 1));
+        if ((j0 >> creg) & 1) pair_update<K_GENERAL>(a[j0], a[j0 | (1 << B)], m);
     }
 }
 
 // Multiply register j by (bit_j ? d1 : d0) where bit_j = compile-time bit B of j.
 template <int B>
-DVD_HD void diag_regbit(cplx (&a)[NREG], const double (&m)[8], bool flip, bool skip0) {
+DVD_HD void diag_regbit(cplx (&a)[NREG], const double* m, bool flip, bool d0one) {
     // flip: the thread-level parity is odd, so register bit 0 <-> 1 trade factors
     const double r0 = flip ? m[6] : m[0], i0 = flip ? m[7] : m[1];
     const double r1 = flip ? m[0] : m[6], i1 = flip ? m[1] : m[7];
+    const bool skip0 = d0one && !flip, skip1 = d0one && flip;
 #pragma unroll
     for (int j = 0; j < NREG; ++j) {
-        if ((j >> B) & 1) a[j] = cmul(a[j], r1, i1);
+        if ((j >> B) & 1) { if (!skip1) a[j] = cmul(a[j], r1, i1); }
         else if (!skip0) a[j] = cmul(a[j], r0, i0);
     }
 }
+template <int B>
+DVD_HD void scale_regbit(cplx (&a)[NREG], cplx w) {
+#pragma unroll
+    for (int j = 0; j < NREG; ++j) if ((j >> B) & 1) a[j] = cmul(a[j], w.x, w.y);
+}
+template <int B0, int B1>
+DVD_HD void scale_pair(cplx (&a)[NREG], double wr, double wi) {
+#pragma unroll
+    for (int j = 0; j < NREG; ++j) if (((j >> B0) & 1) && ((j >> B1) & 1)) a[j] = cmul(a[j], wr, wi);
+}
+
+// Product of the phase sub-tables selected by the bytes of the thread's physical index.
+DVD_HD cplx table_lookup(const cplx* __restrict__ tables, int tab, unsigned bytes, uint64_t pidx) {
+    cplx w{1.0, 0.0};
+    bool first = true;
+    const cplx* t = tables + (size_t)tab * TABLE_ENTRIES;
+#pragma unroll
+    for (int b = 0; b < MAX_INDEX_BYTES; ++b) {
+        if ((bytes >> b) & 1u) {
+            const cplx e = t[(pidx >> (8 * b)) & 255u];
+            w = first ? e : cmul(w, e.x, e.y);
+            first = false;
+            t += TABLE_ENTRIES;
+        }
+    }
+    return w;
+}
+
+#define DVD_CASE4(base, STMT)        \
+    case (base) + 0: { constexpr int B = 0; STMT; } break; \
+    case (base) + 1: { constexpr int B = 1; STMT; } break; \
+    case (base) + 2: { constexpr int B = 2; STMT; } break; \
+    case (base) + 3: { constexpr int B = 3; STMT; } break;
 
 // Apply one op to the 16 register-resident amplitudes of a thread (stage already matches op.group).
 DVD_HD void apply_op(cplx (&a)[NREG], const DevOp& op, ThreadCtx& ctx) {
-    double m[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) m[k] = op.m[k];
-    const int kind = op.kind;
-    const int cregm = op.cregm;
-    const bool cthread = op.has_ctrl ? (parity64(ctx.pidx & op.cmask) != 0) : true;   // thread-level control parity
-    if (kind == K_DIAG) {
-        const int tregm = op.tregm;
-        const bool tpar = parity64(ctx.pidx & op.tmask) != 0;
-        if (tregm == 0 && cregm == 0) {
-            // the whole thread sees one factor: fold it into the lazy scalar phase (4 DFMA instead of 64)
-            if (cthread && !(op.d0_is_one && !tpar)) {
+    const int code = op.code;
+    const uint64_t cm = op.cmask;
+    const bool cthread = cm == 0 || parity64(ctx.pidx & cm) != 0;   // thread-level control parity
+    if (!cthread && code != OC_DIAGGEN) return;
+    const double* m = op.m;
+    switch (code) {
+        DVD_CASE4(OC_GATE + 4 * K_GENERAL, (gate_all<B, K_GENERAL>(a, m)))
+        DVD_CASE4(OC_GATE + 4 * K_REAL, (gate_all<B, K_REAL>(a, m)))
+        DVD_CASE4(OC_GATE + 4 * K_RXLIKE, (gate_all<B, K_RXLIKE>(a, m)))
+        DVD_CASE4(OC_GATE + 4 * K_ANTIDIAG, (gate_all<B, K_ANTIDIAG>(a, m)))
+        DVD_CASE4(OC_CGEN, (cgen<B>(a, m, op.creg)))
+        DVD_CASE4(OC_DIAG1, (diag_regbit<B>(a, m, parity64(ctx.pidx & op.tmask) != 0, (op.flags & F_D0_ONE) != 0)))
+        case OC_PHASE: {
+            const bool tpar = parity64(ctx.pidx & op.tmask) != 0;
+            if (!((op.flags & F_D0_ONE) && !tpar)) {
                 ctx.ph = cmul(ctx.ph, tpar ? m[6] : m[0], tpar ? m[7] : m[1]);
                 ctx.ph_dirty = true;
             }
-            return;
-        }
-        if (cregm == 0 && (tregm & (tregm - 1)) == 0) {
-            // one register bit in the target parity, control (if any) thread-level: RZ on a register qubit
-            if (!cthread) return;
-            // with d0 == 1 the untouched half is the one whose overall parity is even
-            const bool d0one = op.d0_is_one != 0;
-            switch (tregm) {
-                case 1: diag_regbit<0>(a, m, tpar, d0one && !tpar); break;
-                case 2: diag_regbit<1>(a, m, tpar, d0one && !tpar); break;
-                case 4: diag_regbit<2>(a, m, tpar, d0one && !tpar); break;
-                default: diag_regbit<3>(a, m, tpar, d0one && !tpar); break;
-            }
-            return;
-        }
-        // general parity phase with register bits in target and/or control masks
+        } break;
+        case OC_DIAGGEN: {
+            const int tregm = op.regm & 15, cregm = op.regm >> 4;
+            const bool has_ctrl = (op.flags & F_HAS_CTRL) != 0;
+            const bool cpar = cm != 0 && parity64(ctx.pidx & cm) != 0;
+            const bool tpar = parity64(ctx.pidx & op.tmask) != 0;
+            const bool d0one = (op.flags & F_D0_ONE) != 0;
 #pragma unroll
-        for (int j = 0; j < NREG; ++j) {
-            const bool on = op.has_ctrl ? (cthread != (parity4(j & cregm) != 0)) : true;
-            const bool bit = tpar != (parity4(j & tregm) != 0);
-            if (on && !(op.d0_is_one && !bit)) a[j] = cmul(a[j], bit ? m[6] : m[0], bit ? m[7] : m[1]);
-        }
-        return;
-    }
-    // non-diagonal: one target register bit; control none / thread-level / one register bit
-    int creg = -1;
-    if (cregm) creg = cregm == 1 ? 0 : cregm == 2 ? 1 : cregm == 4 ? 2 : 3;
-    else if (!cthread) return;
-    switch (op.treg) {
-        case 0: apply_kind<0>(a, kind, m, creg); break;
-        case 1: apply_kind<1>(a, kind, m, creg); break;
-        case 2: apply_kind<2>(a, kind, m, creg); break;
-        default: apply_kind<3>(a, kind, m, creg); break;
+            for (int j = 0; j < NREG; ++j) {
+                const bool on = has_ctrl ? (cpar != (parity4(j & cregm) != 0)) : true;
+                const bool bit = tpar != (parity4(j & tregm) != 0);
+                if (on && !(d0one && !bit)) a[j] = cmul(a[j], bit ? m[6] : m[0], bit ? m[7] : m[1]);
+            }
+        } break;
+        case OC_TABLE: {
+            if (op.tmask == 0 || parity64(ctx.pidx & op.tmask)) {
+                const cplx w = table_lookup(ctx.tables, op.tab, op.regm, ctx.pidx);
+                ctx.ph = cmul(ctx.ph, w.x, w.y);
+                ctx.ph_dirty = true;
+            }
+        } break;
+        DVD_CASE4(OC_TABLE_REG, (scale_regbit<B>(a, table_lookup(ctx.tables, op.tab, op.regm, ctx.pidx))))
+        case OC_PAIR + 0: scale_pair<0, 1>(a, m[0], m[1]); break;
+        case OC_PAIR + 1: scale_pair<0, 2>(a, m[0], m[1]); break;
+        case OC_PAIR + 2: scale_pair<0, 3>(a, m[0], m[1]); break;
+        case OC_PAIR + 3: scale_pair<1, 2>(a, m[0], m[1]); break;
+        case OC_PAIR + 4: scale_pair<1, 3>(a, m[0], m[1]); break;
+        case OC_PAIR + 5: scale_pair<2, 3>(a, m[0], m[1]); break;
+        default: break;
     }
 }
 

@@ -136,7 +136,7 @@ int dvd_set_unfused(dvd_state* s, int unfused);
 /* ---- planner inspection (host only, no GPU needed) ----------------------------------------- */
 /* Runs the pass planner on a gate list for a state of n_total qubits with n_local local qubits
  * (fuse != 0: after the diagonal-run fusion pre-pass) and writes a flat int32 description:
- *   [n_passes, then per pass: tile_q[12], n_switches, n_ops, then per op: gate_idx, kind, group, treg, cregm]
+ *   [n_passes, then per pass: tile_q[12], n_switches, n_ops, then per op: gate_idx, opcode, group, table, regmask]
  * Returns the number of int32 written, or -(needed) if cap is too small, or INT64_MIN on error. */
 int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates, int fuse,
                        int32_t* out, int64_t cap);

@@ -19,6 +19,7 @@ using namespace dvd;
 static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
     PassDesc pd = pass.desc;
     pd.rank_bits = rank_bits;
+    pd.tables = pass.tables.data();
     const uint64_t ctas = 1ull << (pd.n_local - TILE_BITS);
     std::vector<cplx> tile(TILE_AMPS);
     static cplx regs[NTHREADS][NREG];
@@ -31,6 +32,7 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
             ctx[tid].pidx = gbase | tile_offset(pd, stage_idx(IO_GROUP, tid, 0));
             ctx[tid].ph = cplx{1.0, 0.0};
             ctx[tid].ph_dirty = false;
+            ctx[tid].tables = pd.tables;
         }
         int cur = IO_GROUP;
         auto do_switch = [&](int to) {
@@ -41,12 +43,12 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
             cur = to;
         };
         for (const DevOp& op : pass.ops) {
-            if (op.group >= 0 && op.group != cur) {
+            if (op.group != cur) {
                 for (int tid = 0; tid < NTHREADS; ++tid) flush_phase(regs[tid], ctx[tid]);
                 do_switch(op.group);
                 for (int tid = 0; tid < NTHREADS; ++tid) ctx[tid].pidx = gbase | tile_offset(pd, stage_idx(cur, tid, 0));
             }
-            if (op.kind != K_DIAG && (op.group != cur || op.treg < 0 || op.treg >= REG_BITS)) throw std::runtime_error("emu: op not in its register group");
+            if (op.group != cur || op.code < 0 || op.code >= OC_COUNT) throw std::runtime_error("emu: op not in its register group");
             for (int tid = 0; tid < NTHREADS; ++tid) apply_op(regs[tid], op, ctx[tid]);
         }
         for (int tid = 0; tid < NTHREADS; ++tid) flush_phase(regs[tid], ctx[tid]);
