@@ -16,13 +16,33 @@ namespace dvd {
 // =================================================================================================
 constexpr int OPS_CHUNK = 32;
 
-__device__ __forceinline__ void switch_stage(cplx* tile, cplx (&a)[NREG], int tid, int from, int to) {
-    __syncthreads();  // everybody finished reading the tile in the previous switch
+// Register <-> shared-memory transposes.  Thanks to the additive padding (smem_slot) every
+// register's slot is a compile-time offset from one per-thread base.
+template <int G>
+__device__ __forceinline__ void stage_store(cplx* tile, const cplx (&a)[NREG], int tid) {
+    cplx* p = tile + smem_slot(stage_idx(G, tid, 0));
 #pragma unroll
-    for (int j = 0; j < NREG; ++j) tile[swz(stage_idx(from, tid, j))] = a[j];
-    __syncthreads();
+    for (int j = 0; j < NREG; ++j) p[smem_slot(j << (REG_BITS * G))] = a[j];
+}
+template <int G>
+__device__ __forceinline__ void stage_load(const cplx* tile, cplx (&a)[NREG], int tid) {
+    const cplx* p = tile + smem_slot(stage_idx(G, tid, 0));
 #pragma unroll
-    for (int j = 0; j < NREG; ++j) a[j] = tile[swz(stage_idx(to, tid, j))];
+    for (int j = 0; j < NREG; ++j) a[j] = p[smem_slot(j << (REG_BITS * G))];
+}
+// Store through a GF(2)-affine permutation of the tile index: every pending X / CNOT of the pass is
+// executed here, as addressing, instead of as data movement of its own.
+template <int G>
+__device__ __forceinline__ void stage_store_perm(cplx* tile, const cplx (&a)[NREG], int tid, const DevOp& op, uint64_t gbase) {
+    const PermPayload& pp = *reinterpret_cast<const PermPayload*>(op.m);
+    const unsigned pb = perm_index(op, perm_const(op, gbase), (unsigned)stage_idx(G, tid, 0));
+    const unsigned c0 = pp.col[REG_BITS * G + 0], c1 = pp.col[REG_BITS * G + 1];
+    const unsigned c2 = pp.col[REG_BITS * G + 2], c3 = pp.col[REG_BITS * G + 3];
+#pragma unroll
+    for (int j = 0; j < NREG; ++j) {
+        const unsigned x = pb ^ ((j & 1) ? c0 : 0u) ^ ((j & 2) ? c1 : 0u) ^ ((j & 4) ? c2 : 0u) ^ ((j & 8) ? c3 : 0u);
+        tile[smem_slot((int)x)] = a[j];
+    }
 }
 
 // Global <-> register layout = IO_GROUP stage: lanes run over tile positions 0..4, i.e. over
@@ -61,9 +81,8 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
     }
 
     const uint64_t gbase = cta_base(pd, (uint64_t)blockIdx.x) | pd.rank_bits;
-    int cur = IO_GROUP;
     ThreadCtx ctx;
-    ctx.pidx = gbase | tile_offset(pd, stage_idx(IO_GROUP, tid, 0));
+    ctx.pidx = thread_pidx(pd, gbase, IO_GROUP, tid);
     ctx.ph = cplx{1.0, 0.0};
     ctx.ph_dirty = false;
     ctx.tables = pd.tables;
@@ -79,18 +98,31 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
         __syncthreads();
         for (int k = 0; k < n; ++k) {
             const DevOp& op = sops[k];
-            const int g = op.group;
-            if (g != cur) {
+            const int code = op.code;
+            if (code >= OC_SWITCH) {
+                const int from = (code - OC_SWITCH) / NGROUPS, to = (code - OC_SWITCH) % NGROUPS;
                 flush_phase(a, ctx);
-                switch_stage(tile, a, tid, cur, g);
-                cur = g;
-                ctx.pidx = (cta_base(pd, (uint64_t)blockIdx.x) | pd.rank_bits) | tile_offset(pd, stage_idx(g, tid, 0));
+                __syncthreads();   // the previous transpose's loads are done everywhere
+                if (op.flags & F_PERM) {
+                    if (from == 0) stage_store_perm<0>(tile, a, tid, op, gbase);
+                    else if (from == 1) stage_store_perm<1>(tile, a, tid, op, gbase);
+                    else stage_store_perm<2>(tile, a, tid, op, gbase);
+                } else {
+                    if (from == 0) stage_store<0>(tile, a, tid);
+                    else if (from == 1) stage_store<1>(tile, a, tid);
+                    else stage_store<2>(tile, a, tid);
+                }
+                __syncthreads();
+                if (to == 0) stage_load<0>(tile, a, tid);
+                else if (to == 1) stage_load<1>(tile, a, tid);
+                else stage_load<2>(tile, a, tid);
+                ctx.pidx = thread_pidx(pd, gbase, to, tid);
+                continue;
             }
             apply_op(a, op, ctx);
         }
     }
-    flush_phase(a, ctx);
-    if (cur != IO_GROUP) switch_stage(tile, a, tid, cur, IO_GROUP);
+    flush_phase(a, ctx);   // the planner always ends a pass in the IO layout
 
     {
         const IoAddr io = io_addr(amp, pd);
@@ -386,7 +418,7 @@ constexpr unsigned STREAM_CAP = 148 * 32;  // grid-stride kernels: a multiple of
 
 cudaError_t kernels_init() {
     cudaError_t e = cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TILE_AMPS * (int)sizeof(cplx));
+                                         TILE_SLOTS * (int)sizeof(cplx));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 SAMPLE_WARPS * (2 << BLK_BITS) * (int)sizeof(double));
@@ -394,7 +426,7 @@ cudaError_t kernels_init() {
 
 cudaError_t launch_tile_pass(cplx* amp, const DevOp* ops, const PassDesc& pd, cudaStream_t s) {
     const uint64_t ctas = 1ull << (pd.n_local - TILE_BITS);
-    k_tile_pass<<<(unsigned)ctas, NTHREADS, TILE_AMPS * sizeof(cplx), s>>>(amp, ops, pd);
+    k_tile_pass<<<(unsigned)ctas, NTHREADS, TILE_SLOTS * sizeof(cplx), s>>>(amp, ops, pd);
     return cudaGetLastError();
 }
 

@@ -198,13 +198,40 @@ struct DiagAcc {
 
 cplx to_cplx(const cl& v) { return cplx{(double)v.real(), (double)v.imag()}; }
 
+// Pending X / CNOT gates of a stage as an affine map over the tile index (see PermPayload).
+struct PermAcc {
+    uint16_t col[TILE_BITS];
+    uint16_t v0 = 0;
+    std::vector<std::pair<uint64_t, uint16_t>> cond;   // (physical control mask outside the tile, flipped tile bits)
+    bool identity = true;
+    PermAcc() { for (int p = 0; p < TILE_BITS; ++p) col[p] = (uint16_t)(1u << p); }
+    void add_x(int t) { v0 ^= (uint16_t)(1u << t); identity = false; }
+    void add_cnot(int c, int t) {     // tile positions
+        for (int p = 0; p < TILE_BITS; ++p) if ((col[p] >> c) & 1) col[p] ^= (uint16_t)(1u << t);
+        if ((v0 >> c) & 1) v0 ^= (uint16_t)(1u << t);
+        for (auto& cd : cond) if ((cd.second >> c) & 1) cd.second ^= (uint16_t)(1u << t);
+        identity = false;
+    }
+    bool can_add_ext(uint64_t mask) const {
+        for (auto& cd : cond) if (cd.first == mask) return true;
+        return (int)cond.size() < PERM_MAX_COND;
+    }
+    void add_cnot_ext(uint64_t mask, int t) {   // control outside the tile: a per-CTA conditional flip
+        for (auto& cd : cond) if (cd.first == mask) { cd.second ^= (uint16_t)(1u << t); identity = false; return; }
+        cond.push_back({mask, (uint16_t)(1u << t)});
+        identity = false;
+    }
+};
+
 struct StageEmitter {
     Pass& pass;
     DiagAcc& acc;
     int n_total;
+    const int* pos_of;           // physical qubit -> tile position (-1: outside the tile)
     int group = IO_GROUP;
     int regq[REG_BITS];
     uint64_t regphys = 0;
+    PermAcc perm;
 
     void set_stage(int g) {
         group = g; regphys = 0;
@@ -221,7 +248,33 @@ struct StageEmitter {
         op.group = (int8_t)group; op.gate_idx = gate_idx; op.creg = -1;
         return op;
     }
-    // Sub-tables for prod_c f_c^{x_c} * scale over thread-level partners; returns (tab, bytemask).
+    // Transpose to group `to`, executing every pending X / CNOT on the way.
+    void emit_switch(int to) {
+        DevOp op = blank(-1);
+        op.code = OC_SWITCH + group * NGROUPS + to;
+        op.group = (int8_t)to;
+        if (!perm.identity) {
+            op.flags |= F_PERM;
+            PermPayload pp; std::memset(&pp, 0, sizeof(pp));
+            for (int p = 0; p < TILE_BITS; ++p) pp.col[p] = perm.col[p];
+            pp.v0 = perm.v0;
+            pp.n_cond = (uint16_t)perm.cond.size();
+            for (size_t k = 0; k < perm.cond.size(); ++k) {
+                pp.cond_vec[k] = perm.cond[k].second;
+                if (k == 0) op.tmask = perm.cond[k].first;
+                else if (k == 1) op.cmask = perm.cond[k].first;
+                else pp.cond_mask23[k - 2] = perm.cond[k].first;
+            }
+            std::memcpy(op.m, &pp, sizeof(pp));
+        } else if (to == group) {
+            return;
+        }
+        pass.ops.push_back(op);
+        ++pass.n_switches;
+        perm = PermAcc();
+        set_stage(to);
+    }
+    // Sub-tables for scale * prod_c f_c^{x_c} over thread-level partners; returns (tab, bytemask).
     void build_tables(const std::vector<std::pair<int, cl>>& partners, const cl& scale, int32_t* tab, uint8_t* bytes) {
         uint8_t mask = 0;
         for (auto& pr : partners) mask |= (uint8_t)(1u << (pr.first / 8));
@@ -241,36 +294,51 @@ struct StageEmitter {
             for (int v = 0; v < TABLE_ENTRIES; ++v) pass.tables.push_back(to_cplx(e[v]));
         }
     }
-    // Emit every accumulated term that involves register qubit q (register bit r of this stage).
+    // Emit every accumulated term that involves qubit q, in the current stage's layout.
     void flush_qubit(int q, cl* fold_K = nullptr) {
         const int r = reg_of(q);
-        if (r < 0) throw std::runtime_error("plan_local: flush of a non-register qubit");
         cl A(1, 0);
         { auto it = acc.a.find(q); if (it != acc.a.end()) { A = it->second; acc.a.erase(it); } }
-        std::vector<std::pair<int, cl>> partners;
+        std::vector<std::pair<int, cl>> tpart;          // thread-level partners
+        std::vector<std::pair<int, cl>> rpart;          // register-level partners (register bit, factor)
         for (auto it = acc.b.begin(); it != acc.b.end();) {
             if (it->first.first != q && it->first.second != q) { ++it; continue; }
             const int c = it->first.first == q ? it->first.second : it->first.first;
-            const int rc = reg_of(c);
             if (!is_one(it->second)) {
-                if (rc >= 0) {
-                    DevOp op = blank(-1);
-                    op.code = OC_PAIR + pair_id(std::min(r, rc), std::max(r, rc));
-                    const cplx f = to_cplx(it->second);
-                    op.m[0] = f.x; op.m[1] = f.y;
-                    pass.ops.push_back(op);
-                } else {
-                    partners.push_back({c, it->second});
-                }
+                const int rc = reg_of(c);
+                if (rc >= 0) rpart.push_back({rc, it->second}); else tpart.push_back({c, it->second});
             }
             it = acc.b.erase(it);
         }
-        if (!partners.empty()) {
-            DevOp op = blank(-1);
-            op.code = OC_TABLE_REG + r;
-            build_tables(partners, A, &op.tab, &op.regm);
-            pass.ops.push_back(op);
-        } else if (!is_one(A)) {
+        if (r < 0) {
+            // q is thread-level: its own factor and its thread-level partners form a pivot table;
+            // each register-level partner rc gets a one-partner table applied to the registers with bit rc
+            if (!tpart.empty()) {
+                DevOp op = blank(-1);
+                op.code = OC_TABLE;
+                op.tmask = 1ull << q;
+                build_tables(tpart, A, &op.tab, &op.regm);
+                pass.ops.push_back(op);
+            } else if (!is_one(A)) {
+                DevOp op = blank(-1);
+                op.code = OC_PHASE;
+                op.tmask = 1ull << q;
+                op.flags = F_D0_ONE;
+                const cplx f = to_cplx(A);
+                op.m[0] = 1.0; op.m[6] = f.x; op.m[7] = f.y;
+                pass.ops.push_back(op);
+            }
+            for (auto& pr : rpart) {
+                DevOp op = blank(-1);
+                op.code = OC_TABLE_REG + pr.first;
+                std::vector<std::pair<int, cl>> one{{q, pr.second}};
+                build_tables(one, cl(1, 0), &op.tab, &op.regm);
+                pass.ops.push_back(op);
+            }
+            return;
+        }
+        if (tpart.empty() && rpart.empty()) {
+            if (is_one(A)) return;
             DevOp op = blank(-1);
             op.code = OC_DIAG1 + r;
             cl d0(1, 0);
@@ -279,7 +347,29 @@ struct StageEmitter {
             const cplx f0 = to_cplx(d0), f1 = to_cplx(d0 * A);
             op.m[0] = f0.x; op.m[1] = f0.y; op.m[6] = f1.x; op.m[7] = f1.y;
             pass.ops.push_back(op);
+            return;
         }
+        if (tpart.empty() && rpart.size() == 1 && is_one(A)) {
+            DevOp op = blank(-1);
+            const int rc = rpart[0].first;
+            op.code = OC_PAIR + pair_id(std::min(r, rc), std::max(r, rc));
+            const cplx f = to_cplx(rpart[0].second);
+            op.m[0] = f.x; op.m[1] = f.y;
+            pass.ops.push_back(op);
+            return;
+        }
+        // general: (tables | constant A) x register-partner factors on the registers with bit r
+        DevOp op = blank(-1);
+        op.code = OC_TABLE_REG + r;
+        if (!tpart.empty()) build_tables(tpart, A, &op.tab, &op.regm);
+        else { const cplx f = to_cplx(A); op.m[6] = f.x; op.m[7] = f.y; }
+        for (auto& pr : rpart) {
+            const int slot = pr.first < r ? pr.first : pr.first - 1;     // index among the other three bits, ascending
+            const cplx f = to_cplx(pr.second);
+            op.m[2 * slot] = f.x; op.m[2 * slot + 1] = f.y;
+            op.flags |= (uint8_t)(1u << (F_PM_SHIFT + slot));
+        }
+        pass.ops.push_back(op);
     }
     // End of the pass: everything that is left.
     void flush_all() {
@@ -365,6 +455,26 @@ struct StageEmitter {
         }
         acc = DiagAcc();
     }
+    static bool is_perm_gate(const HostGate& g) {
+        if (g.diag) return false;
+        int32_t kind; int8_t d0;
+        classify_gate(g.m, &kind, &d0);
+        return kind == K_SWAP;
+    }
+    bool perm_capacity(const HostGate& g) const {
+        const int c = g.control();
+        if (c < 0 || pos_of[c] >= 0) return true;
+        return perm.can_add_ext(g.cmask);
+    }
+    // X / CNOT: joins the pending permutation; executed by the next switch.
+    void emit_perm(const HostGate& g) {
+        const int t = g.target();
+        flush_qubit(t);              // phases on t do not commute with a flip of t
+        const int c = g.control();
+        if (c < 0) perm.add_x(pos_of[t]);
+        else if (pos_of[c] >= 0) perm.add_cnot(pos_of[c], pos_of[t]);
+        else perm.add_cnot_ext(g.cmask, pos_of[t]);
+    }
     void emit_gate(const HostGate& g) {
         if (g.diag) {
             if (acc.add(g)) return;
@@ -374,9 +484,13 @@ struct StageEmitter {
             op.tmask = g.tmask & ~regphys;
             op.cmask = g.cmask & ~regphys;
             if (g.m[0] == 1.0 && g.m[1] == 0.0) op.flags |= F_D0_ONE;
-            if (g.cmask) op.flags |= F_HAS_CTRL;
-            if (tregm == 0 && cregm == 0) op.code = OC_PHASE;
-            else { op.code = OC_DIAGGEN; op.regm = (uint8_t)(tregm | (cregm << 4)); }
+            if (tregm == 0 && cregm == 0) {
+                op.code = OC_PHASE;
+                if (g.cmask) op.flags |= F_TCTRL;
+            } else {
+                op.code = OC_DIAGGEN; op.regm = (uint8_t)(tregm | (cregm << 4));
+                if (g.cmask) op.flags |= F_HAS_CTRL;
+            }
             pass.ops.push_back(op);
             return;
         }
@@ -388,13 +502,13 @@ struct StageEmitter {
         std::memcpy(op.m, g.m, sizeof(op.m));
         int32_t kind; int8_t d0;
         classify_gate(g.m, &kind, &d0);
-        if (kind == K_SWAP) kind = K_ANTIDIAG;   // interim: X / CNOT as arithmetic, never as register moves
+        if (kind == K_SWAP) kind = K_ANTIDIAG;   // only reached by X-like gates that could not join a permutation
         const int c = g.control();
         const int creg = c >= 0 ? reg_of(c) : -1;
         if (creg >= 0) {
             op.code = OC_CGEN + treg; op.creg = (int8_t)creg;
         } else {
-            op.cmask = g.cmask;
+            if (g.cmask) { op.cmask = g.cmask; op.flags |= F_TCTRL; }
             op.code = OC_GATE + kind * 4 + treg;
         }
         pass.ops.push_back(op);
@@ -447,15 +561,15 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
         for (int q = 0; q < n_local && tile_n < TILE_BITS; ++q)
             if (!((tile >> q) & 1)) { tile |= 1ull << q; ++tile_n; }
 
-        // ---- tile positions: pinned low run, then by first non-diagonal use ----------------------
+        // ---- tile positions: pinned low run, then by first non-permutation target use -----------
         Pass pass;
         std::memset(&pass.desc, 0, sizeof(pass.desc));
         pass.desc.n_local = n_local;
-        std::vector<int> order;  // qubits by first non-diagonal target use
+        std::vector<int> order;  // qubits by first use as the target of a gate that needs registers
         uint64_t seen = (1ull << min_low) - 1;
         for (int gi : taken) {
             const HostGate& g = gates[gi];
-            if (!g.diag && !(seen & g.tmask)) { seen |= g.tmask; order.push_back(g.target()); }
+            if (!g.diag && !StageEmitter::is_perm_gate(g) && !(seen & g.tmask)) { seen |= g.tmask; order.push_back(g.target()); }
         }
         for (int q = 0; q < n_local; ++q)
             if (((tile >> q) & 1) && !((seen >> q) & 1)) { seen |= 1ull << q; order.push_back(q); }
@@ -479,32 +593,40 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
         std::sort(pass.desc.sorted_q, pass.desc.sorted_q + TILE_BITS);
 
         // ---- stage level: sweep per register group ---------------------------------------------------
+        // b2: gates skipped in this sweep; pp: X / CNOT gates accepted into the pending permutation.
+        // A later gate may run in this stage only if it commutes past both sets; permutation gates
+        // compose among themselves in program order, so they only need to pass b2.
         std::vector<int> remaining = taken;
         DiagAcc acc;
-        StageEmitter em{pass, acc, n_total};
-        int cur = IO_GROUP;
-        em.set_stage(cur);
+        StageEmitter em{pass, acc, n_total, pos_of};
+        em.set_stage(IO_GROUP);
         while (!remaining.empty()) {
-            // keep `cur` if the first remaining op can run there, else move to its group
             {
-                const HostGate& g0 = gates[remaining[0]];
-                if (!g0.diag) {
-                    const int grp = pos_of[g0.target()] / REG_BITS;
-                    if (grp != cur) { cur = grp; ++pass.n_switches; em.set_stage(cur); }
+                int want = em.group;
+                for (int gi : remaining) {
+                    const HostGate& g = gates[gi];
+                    if (!g.diag && !StageEmitter::is_perm_gate(g)) { want = pos_of[g.target()] / REG_BITS; break; }
                 }
+                em.emit_switch(want);    // no-op when nothing is pending and the group stays
             }
-            Blocked b2;
+            const int cur = em.group;
+            Blocked b2, pp;
             std::vector<int> rem2;
             for (int gi : remaining) {
                 const HostGate& g = gates[gi];
-                const bool ok = b2.can_pass(g) && (g.diag || pos_of[g.target()] / REG_BITS == cur);
+                bool ok;
+                const bool is_perm = StageEmitter::is_perm_gate(g);
+                if (is_perm) ok = b2.can_pass(g) && em.perm_capacity(g);
+                else ok = b2.can_pass(g) && pp.can_pass(g) && (g.diag || pos_of[g.target()] / REG_BITS == cur);
                 if (!ok) { b2.skip(g); rem2.push_back(gi); continue; }
-                em.emit_gate(g);
+                if (is_perm) { em.emit_perm(g); pp.skip(g); }
+                else em.emit_gate(g);
             }
+            if (rem2.size() == remaining.size()) throw std::runtime_error("plan_local: stage made no progress");
             remaining.swap(rem2);
         }
         em.flush_all();
-        if (cur != IO_GROUP) ++pass.n_switches;
+        em.emit_switch(IO_GROUP);
         pass.desc.n_ops = (int)pass.ops.size();
         passes.push_back(std::move(pass));
         pending.swap(rest);

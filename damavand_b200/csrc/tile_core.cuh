@@ -54,37 +54,59 @@ enum OpKind : int32_t {
 // Device instruction set.
 enum OpCode : int32_t {
     OC_GATE = 0,        // + kind*4 + treg (kind 0..3): 2x2 on register bit treg; control none / thread-level
-    OC_SWAP = 16,       // + treg: exchange along register bit treg (X; CNOT with thread-level control)
-    OC_CSWAP = 20,      // + treg*4 + creg: CNOT with both qubits in registers
-    OC_CGEN = 36,       // + treg: general 2x2 on treg, control = register bit op.creg (rare)
-    OC_DIAG1 = 40,      // + r: registers with bit r set *= d1, the others *= d0 (unless d0 == 1)
-    OC_PHASE = 44,      // thread-level parity phase -> lazy per-thread scalar
-    OC_DIAGGEN = 45,    // generic parity phase with register bits in its masks (fallback)
-    OC_TABLE = 46,      // product of phase-table lookups -> lazy scalar (optional thread-level pivot)
-    OC_TABLE_REG = 47,  // + r: product of phase-table lookups -> registers with bit r set
-    OC_PAIR = 51,       // + pair id: registers with both bits set *= (m[0], m[1])
-    OC_COUNT = 57,
+    OC_CGEN = 16,       // + treg: general 2x2 on treg, control = register bit op.creg (rare)
+    OC_DIAG1 = 20,      // + r: registers with bit r set *= d1, the others *= d0 (unless d0 == 1)
+    OC_PHASE = 24,      // thread-level parity phase -> lazy per-thread scalar
+    OC_DIAGGEN = 25,    // generic parity phase with register bits in its masks (fallback)
+    OC_TABLE = 26,      // product of phase-table lookups -> lazy scalar (optional thread-level pivot)
+    OC_TABLE_REG = 27,  // + r: (table lookups | constant) x factors of the other register bits -> registers with bit r
+    OC_PAIR = 31,       // + pair id: registers with both bits set *= (m[0], m[1])
+    OC_SWITCH = 37,     // + from*3 + to: transpose through shared memory, optionally with a GF(2)-affine
+                        //   permutation of the tile index (all pending X / CNOT gates)
+    OC_COUNT = 46,
 };
 DVD_HD int pair_id(int r0, int r1) {   // r0 < r1
     return r0 == 0 ? r1 - 1 : r0 == 1 ? r1 + 1 : 5;
 }
 
-enum OpFlags : uint8_t { F_D0_ONE = 1, F_HAS_CTRL = 2 };
+enum OpFlags : uint8_t {
+    F_D0_ONE = 1,     // diagonal op with d0 == 1
+    F_HAS_CTRL = 2,   // OC_DIAGGEN: controlled
+    F_TCTRL = 4,      // thread-level control parity mask in cmask must be odd
+    F_PERM = 8,       // OC_SWITCH: PermPayload in m[]
+    F_PM_SHIFT = 4,   // OC_TABLE_REG: bits 4..6 = which of the other three register bits carry a factor
+};
 
 // One operation as the device sees it, fully decoded by the planner for the stage it runs in.
 struct alignas(16) DevOp {
-    double m[8];       // m00.re m00.im m01.re m01.im m10.re m10.im m11.re m11.im
+    double m[8];       // m00.re m00.im m01.re m01.im m10.re m10.im m11.re m11.im  (or a PermPayload)
     uint64_t tmask;    // thread-level part of the target parity mask (diagonal ops, table pivot)
     uint64_t cmask;    // thread-level part of the control parity mask (0 = none)
     int32_t code;      // OpCode (+ operands)
     int32_t tab;       // table ops: first sub-table (units of TABLE_ENTRIES entries)
     int32_t gate_idx;  // caller's gate index (-1 for fused / layout ops)
-    int8_t group;      // register group the op runs in
+    int8_t group;      // register group the op runs in (OC_SWITCH: the group it switches to)
     int8_t creg;       // OC_CGEN: control register bit
     uint8_t regm;      // OC_DIAGGEN: tregm | cregm << 4;  table ops: bytes of the index that have a sub-table
     uint8_t flags;     // OpFlags
 };
 static_assert(sizeof(DevOp) == 96, "DevOp layout");
+
+// Payload of a permuting OC_SWITCH, stored over DevOp::m.  The amplitude at tile index i moves to
+//   i' = xor_{p : bit p of i} col[p]  ^  v0  ^  xor_k [parity(physical base & cond_mask_k)] cond_vec[k]
+// (X on a tile qubit flips a bit of v0; CNOT between tile qubits adds a row of the matrix to another;
+// CNOT controlled by a qubit outside the tile is a per-CTA conditional flip).  cond_mask 0 and 1
+// live in DevOp::tmask / DevOp::cmask, 2 and 3 in the payload.
+constexpr int PERM_MAX_COND = 4;
+struct PermPayload {
+    uint16_t col[TILE_BITS];
+    uint16_t v0;
+    uint16_t n_cond;
+    uint16_t cond_vec[PERM_MAX_COND];
+    uint32_t pad;
+    uint64_t cond_mask23[2];
+};
+static_assert(sizeof(PermPayload) <= 64, "PermPayload must fit in DevOp::m");
 
 // Per-launch description of a pass.
 struct PassDesc {
@@ -104,9 +126,12 @@ DVD_HD int stage_idx(int g, int tid, int j) {
     const int high = tid >> sh;
     return (high << (sh + REG_BITS)) | (j << sh) | low;
 }
-// Shared-memory swizzle (16-byte units): makes the group-0 layout (stride-16 lanes) conflict free
-// and keeps the other two layouts conflict free.
-DVD_HD int swz(int idx) { return idx ^ ((idx >> 4) & 7); }
+// Shared-memory slot (16-byte units) of tile index idx: one pad slot per 16 makes the group-0 layout
+// (lanes 16 slots apart) conflict free, keeps the other two conflict free, and -- unlike an XOR
+// swizzle -- stays additive: slot(base + (j << 4g)) = slot(base) + const(g, j), so every register's
+// address is an immediate offset from one per-thread base.
+constexpr int TILE_SLOTS = TILE_AMPS + TILE_AMPS / 16;
+DVD_HD int smem_slot(int idx) { return idx + (idx >> 4); }
 
 // Physical offset (in amplitudes) of tile index idx.
 DVD_HD uint64_t tile_offset(const PassDesc& pd, int idx) {
@@ -192,25 +217,6 @@ DVD_HD void gate_all(cplx (&a)[NREG], const double* mp) {
         pair_update<KIND>(a[j0], a[j0 | (1 << B)], m);
     }
 }
-// The 4 pairs along B whose register bit C is set (C != B).
-template <int B, int C>
-DVD_HD void cswap(cplx (&a)[NREG]) {
-#pragma unroll
-    for (int k = 0; k < NREG / 2; ++k) {
-        const int j0 = ((k >> B) << (B + 1)) | (k & ((1 << B) - 1));
-        if (!((j0 >> C) & 1)) continue;
-        const cplx t = a[j0]; a[j0] = a[j0 | (1 << B)]; a[j0 | (1 << B)] = t;
-    }
-}
-template <int B>
-DVD_HD void cswap_b(cplx (&a)[NREG], int c) {
-    switch (c) {
-        case 0: if (B != 0) cswap<B, B == 0 ? 1 : 0>(a); break;
-        case 1: if (B != 1) cswap<B, B == 1 ? 0 : 1>(a); break;
-        case 2: if (B != 2) cswap<B, B == 2 ? 0 : 2>(a); break;
-        default: if (B != 3) cswap<B, B == 3 ? 0 : 3>(a); break;
-    }
-}
 // General 2x2 along B on the pairs whose register bit creg (runtime) is set.
 template <int B>
 DVD_HD void cgen(cplx (&a)[NREG], const double* mp, int creg) {
@@ -224,23 +230,15 @@ DVD_HD void cgen(cplx (&a)[NREG], const double* mp, int creg) {
     }
 }
 
-// Multiply register j by (bit_j ? d1 : d0) where bit_j = compile-time bit B of j.
+// Multiply register j by (bit B of j ? d1 : d0); d0 == 1 is skipped.
 template <int B>
-DVD_HD void diag_regbit(cplx (&a)[NREG], const double* m, bool flip, bool d0one) {
-    // flip: the thread-level parity is odd, so register bit 0 <-> 1 trade factors
-    const double r0 = flip ? m[6] : m[0], i0 = flip ? m[7] : m[1];
-    const double r1 = flip ? m[0] : m[6], i1 = flip ? m[1] : m[7];
-    const bool skip0 = d0one && !flip, skip1 = d0one && flip;
+DVD_HD void diag_regbit(cplx (&a)[NREG], const double* m, bool d0one) {
+    const double r0 = m[0], i0 = m[1], r1 = m[6], i1 = m[7];
 #pragma unroll
     for (int j = 0; j < NREG; ++j) {
-        if ((j >> B) & 1) { if (!skip1) a[j] = cmul(a[j], r1, i1); }
-        else if (!skip0) a[j] = cmul(a[j], r0, i0);
+        if ((j >> B) & 1) a[j] = cmul(a[j], r1, i1);
+        else if (!d0one) a[j] = cmul(a[j], r0, i0);
     }
-}
-template <int B>
-DVD_HD void scale_regbit(cplx (&a)[NREG], cplx w) {
-#pragma unroll
-    for (int j = 0; j < NREG; ++j) if ((j >> B) & 1) a[j] = cmul(a[j], w.x, w.y);
 }
 template <int B0, int B1>
 DVD_HD void scale_pair(cplx (&a)[NREG], double wr, double wi) {
@@ -256,7 +254,7 @@ DVD_HD cplx table_lookup(const cplx* __restrict__ tables, int tab, unsigned byte
 #pragma unroll
     for (int b = 0; b < MAX_INDEX_BYTES; ++b) {
         if ((bytes >> b) & 1u) {
-            const cplx e = t[(pidx >> (8 * b)) & 255u];
+            const cplx e = t[(unsigned)(pidx >> (8 * b)) & 255u];
             w = first ? e : cmul(w, e.x, e.y);
             first = false;
             t += TABLE_ENTRIES;
@@ -265,18 +263,68 @@ DVD_HD cplx table_lookup(const cplx* __restrict__ tables, int tab, unsigned byte
     return w;
 }
 
+// Registers with bit B set *= W * prod_k f_k^{bit o_k of j}: W from the tables (or the constant
+// m[6..7] when the op has none), f_k = m[2k..2k+1] for the other three register bits o_0<o_1<o_2.
+template <int B>
+DVD_HD void table_reg(cplx (&a)[NREG], const DevOp& op, const ThreadCtx& ctx) {
+    constexpr int O0 = B == 0 ? 1 : 0, O1 = B <= 1 ? 2 : 1, O2 = B <= 2 ? 3 : 2;
+    const unsigned pm = (op.flags >> F_PM_SHIFT) & 7u;
+    const cplx w = op.regm ? table_lookup(ctx.tables, op.tab, op.regm, ctx.pidx) : cplx{op.m[6], op.m[7]};
+    cplx w4[4];
+    w4[0] = w;
+    w4[1] = (pm & 1u) ? cmul(w, op.m[0], op.m[1]) : w;
+    w4[2] = (pm & 2u) ? cmul(w4[0], op.m[2], op.m[3]) : w4[0];
+    w4[3] = (pm & 2u) ? cmul(w4[1], op.m[2], op.m[3]) : w4[1];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (h == 1 && (pm & 4u)) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) w4[s] = cmul(w4[s], op.m[4], op.m[5]);
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int j = (1 << B) | ((s & 1) << O0) | (((s >> 1) & 1) << O1) | (h << O2);
+            a[j] = cmul(a[j], w4[s].x, w4[s].y);
+        }
+    }
+}
+
+// ---- stage switch helpers (shared by the kernel and the CPU replay) ------------------------------
+// Physical index of register 0 of thread tid in group g's layout (register bits zero).
+DVD_HD uint64_t thread_pidx(const PassDesc& pd, uint64_t gbase, int g, int tid) {
+    return gbase | tile_offset(pd, stage_idx(g, tid, 0));
+}
+// Constant part of a permuting switch for one CTA: v0 ^ conditional flips.
+DVD_HD unsigned perm_const(const DevOp& op, uint64_t gbase) {
+    const PermPayload& pp = *reinterpret_cast<const PermPayload*>(op.m);
+    unsigned v = pp.v0;
+    const int nc = pp.n_cond;
+    if (nc > 0 && parity64(gbase & op.tmask)) v ^= pp.cond_vec[0];
+    if (nc > 1 && parity64(gbase & op.cmask)) v ^= pp.cond_vec[1];
+    if (nc > 2 && parity64(gbase & pp.cond_mask23[0])) v ^= pp.cond_vec[2];
+    if (nc > 3 && parity64(gbase & pp.cond_mask23[1])) v ^= pp.cond_vec[3];
+    return v;
+}
+// Image of tile index idx under the permutation (v = perm_const).
+DVD_HD unsigned perm_index(const DevOp& op, unsigned v, unsigned idx) {
+    const PermPayload& pp = *reinterpret_cast<const PermPayload*>(op.m);
+    unsigned r = v;
+#pragma unroll
+    for (int p = 0; p < TILE_BITS; ++p) if ((idx >> p) & 1u) r ^= pp.col[p];
+    return r;
+}
+
 #define DVD_CASE4(base, STMT)        \
     case (base) + 0: { constexpr int B = 0; STMT; } break; \
     case (base) + 1: { constexpr int B = 1; STMT; } break; \
     case (base) + 2: { constexpr int B = 2; STMT; } break; \
     case (base) + 3: { constexpr int B = 3; STMT; } break;
 
-// Apply one op to the 16 register-resident amplitudes of a thread (stage already matches op.group).
+// Apply one op (anything but OC_SWITCH) to the 16 register-resident amplitudes of a thread.
 DVD_HD void apply_op(cplx (&a)[NREG], const DevOp& op, ThreadCtx& ctx) {
     const int code = op.code;
-    const uint64_t cm = op.cmask;
-    const bool cthread = cm == 0 || parity64(ctx.pidx & cm) != 0;   // thread-level control parity
-    if (!cthread && code != OC_DIAGGEN) return;
+    const unsigned flags = op.flags;
+    if ((flags & F_TCTRL) && !parity64(ctx.pidx & op.cmask)) return;   // thread-level control
     const double* m = op.m;
     switch (code) {
         DVD_CASE4(OC_GATE + 4 * K_GENERAL, (gate_all<B, K_GENERAL>(a, m)))
@@ -284,20 +332,20 @@ DVD_HD void apply_op(cplx (&a)[NREG], const DevOp& op, ThreadCtx& ctx) {
         DVD_CASE4(OC_GATE + 4 * K_RXLIKE, (gate_all<B, K_RXLIKE>(a, m)))
         DVD_CASE4(OC_GATE + 4 * K_ANTIDIAG, (gate_all<B, K_ANTIDIAG>(a, m)))
         DVD_CASE4(OC_CGEN, (cgen<B>(a, m, op.creg)))
-        DVD_CASE4(OC_DIAG1, (diag_regbit<B>(a, m, parity64(ctx.pidx & op.tmask) != 0, (op.flags & F_D0_ONE) != 0)))
+        DVD_CASE4(OC_DIAG1, (diag_regbit<B>(a, m, (flags & F_D0_ONE) != 0)))
         case OC_PHASE: {
             const bool tpar = parity64(ctx.pidx & op.tmask) != 0;
-            if (!((op.flags & F_D0_ONE) && !tpar)) {
+            if (!((flags & F_D0_ONE) && !tpar)) {
                 ctx.ph = cmul(ctx.ph, tpar ? m[6] : m[0], tpar ? m[7] : m[1]);
                 ctx.ph_dirty = true;
             }
         } break;
-        case OC_DIAGGEN: {
+        case OC_DIAGGEN: {   // control handled here: thread-level and register-level parts combine
             const int tregm = op.regm & 15, cregm = op.regm >> 4;
-            const bool has_ctrl = (op.flags & F_HAS_CTRL) != 0;
-            const bool cpar = cm != 0 && parity64(ctx.pidx & cm) != 0;
+            const bool has_ctrl = (flags & F_HAS_CTRL) != 0;
+            const bool cpar = op.cmask != 0 && parity64(ctx.pidx & op.cmask) != 0;
             const bool tpar = parity64(ctx.pidx & op.tmask) != 0;
-            const bool d0one = (op.flags & F_D0_ONE) != 0;
+            const bool d0one = (flags & F_D0_ONE) != 0;
 #pragma unroll
             for (int j = 0; j < NREG; ++j) {
                 const bool on = has_ctrl ? (cpar != (parity4(j & cregm) != 0)) : true;
@@ -312,7 +360,7 @@ DVD_HD void apply_op(cplx (&a)[NREG], const DevOp& op, ThreadCtx& ctx) {
                 ctx.ph_dirty = true;
             }
         } break;
-        DVD_CASE4(OC_TABLE_REG, (scale_regbit<B>(a, table_lookup(ctx.tables, op.tab, op.regm, ctx.pidx))))
+        DVD_CASE4(OC_TABLE_REG, (table_reg<B>(a, op, ctx)))
         case OC_PAIR + 0: scale_pair<0, 1>(a, m[0], m[1]); break;
         case OC_PAIR + 1: scale_pair<0, 2>(a, m[0], m[1]); break;
         case OC_PAIR + 2: scale_pair<0, 3>(a, m[0], m[1]); break;

@@ -25,8 +25,15 @@ def stats(name, fuse=1, n_local=None):
         passes.append((tile, sw, nops, kinds))
     tot = sum(p[2] for p in passes)
     print(f"{name} fuse={fuse}: gates {ng} -> ops {tot}, passes {len(passes)}, switches {sum(p[1] for p in passes)}")
+    names = [(0, "gate"), (16, "cgen"), (20, "diag1"), (24, "phase"), (25, "diaggen"), (26, "table"), (27, "table_reg"), (31, "pair"), (37, "switch"), (46, "?")]
+    def nm(c):
+        for (lo, n), (hi, _) in zip(names, names[1:]):
+            if lo <= c < hi: return n
+        return "?"
     for t, sw, nops, kinds in passes[:6]:
-        print("   tile", t, "switches", sw, "ops", nops, "kinds", kinds)
+        agg = {}
+        for c, k in kinds.items(): agg[nm(c)] = agg.get(nm(c), 0) + k
+        print("   tile", t, "switches", sw, "ops", nops, agg)
     return passes
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
     pd.rank_bits = rank_bits;
     pd.tables = pass.tables.data();
     const uint64_t ctas = 1ull << (pd.n_local - TILE_BITS);
-    std::vector<cplx> tile(TILE_AMPS);
+    std::vector<cplx> tile(TILE_SLOTS);
     static cplx regs[NTHREADS][NREG];
     static ThreadCtx ctx[NTHREADS];
     for (uint64_t cta = 0; cta < ctas; ++cta) {
@@ -35,24 +35,35 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
             ctx[tid].tables = pd.tables;
         }
         int cur = IO_GROUP;
-        auto do_switch = [&](int to) {
-            for (int tid = 0; tid < NTHREADS; ++tid)
-                for (int j = 0; j < NREG; ++j) tile[swz(stage_idx(cur, tid, j))] = regs[tid][j];
-            for (int tid = 0; tid < NTHREADS; ++tid)
-                for (int j = 0; j < NREG; ++j) regs[tid][j] = tile[swz(stage_idx(to, tid, j))];
-            cur = to;
-        };
         for (const DevOp& op : pass.ops) {
-            if (op.group != cur) {
+            if (op.code < 0 || op.code >= OC_COUNT) throw std::runtime_error("emu: bad opcode");
+            if (op.code >= OC_SWITCH) {
+                const int from = (op.code - OC_SWITCH) / NGROUPS, to = (op.code - OC_SWITCH) % NGROUPS;
+                if (from != cur || to != op.group) throw std::runtime_error("emu: switch does not start in the current group");
+                if (from == to && !(op.flags & F_PERM)) throw std::runtime_error("emu: useless switch");
                 for (int tid = 0; tid < NTHREADS; ++tid) flush_phase(regs[tid], ctx[tid]);
-                do_switch(op.group);
-                for (int tid = 0; tid < NTHREADS; ++tid) ctx[tid].pidx = gbase | tile_offset(pd, stage_idx(cur, tid, 0));
+                std::vector<int> hits(TILE_SLOTS, 0);
+                const unsigned v = (op.flags & F_PERM) ? perm_const(op, gbase) : 0;
+                for (int tid = 0; tid < NTHREADS; ++tid)
+                    for (int j = 0; j < NREG; ++j) {
+                        unsigned idx = (unsigned)stage_idx(from, tid, j);
+                        if (op.flags & F_PERM) idx = perm_index(op, v, idx);
+                        if (idx >= (unsigned)TILE_AMPS) throw std::runtime_error("emu: permutation leaves the tile");
+                        if (hits[smem_slot((int)idx)]++) throw std::runtime_error("emu: permutation is not a bijection");
+                        tile[smem_slot((int)idx)] = regs[tid][j];
+                    }
+                for (int tid = 0; tid < NTHREADS; ++tid) {
+                    for (int j = 0; j < NREG; ++j) regs[tid][j] = tile[smem_slot(stage_idx(to, tid, j))];
+                    ctx[tid].pidx = thread_pidx(pd, gbase, to, tid);
+                }
+                cur = to;
+                continue;
             }
-            if (op.group != cur || op.code < 0 || op.code >= OC_COUNT) throw std::runtime_error("emu: op not in its register group");
+            if (op.group != cur) throw std::runtime_error("emu: op not in its register group");
             for (int tid = 0; tid < NTHREADS; ++tid) apply_op(regs[tid], op, ctx[tid]);
         }
         for (int tid = 0; tid < NTHREADS; ++tid) flush_phase(regs[tid], ctx[tid]);
-        if (cur != IO_GROUP) do_switch(IO_GROUP);
+        if (cur != IO_GROUP) throw std::runtime_error("emu: pass does not end in the IO layout");
         for (int tid = 0; tid < NTHREADS; ++tid)
             for (int j = 0; j < NREG; ++j) amp[base + tile_offset(pd, stage_idx(IO_GROUP, tid, j))] = regs[tid][j];
     }
@@ -151,7 +162,7 @@ int emu_max_bank_conflict() {
         for (int j = 0; j < NREG; ++j)
             for (int q0 = 0; q0 < NTHREADS; q0 += 8) {
                 int cnt[8] = {0};
-                for (int l = 0; l < 8; ++l) cnt[swz(stage_idx(g, q0 + l, j)) & 7]++;
+                for (int l = 0; l < 8; ++l) cnt[smem_slot(stage_idx(g, q0 + l, j)) & 7]++;
                 for (int b = 0; b < 8; ++b) worst = cnt[b] > worst ? cnt[b] : worst;
             }
     return worst;
