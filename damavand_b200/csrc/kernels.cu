@@ -66,6 +66,8 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* tile = reinterpret_cast<cplx*>(smem_raw);
     __shared__ DevOp sops[OPS_CHUNK];
+    __shared__ cplx s_tl[OPS_CHUNK][TABLE_TILE_ENTRIES];   // thread-index phase factors of the chunk's table ops
+    __shared__ cplx s_wc[OPS_CHUNK];                       // their per-CTA constants
 
     const int tid = threadIdx.x;
     cplx a[NREG];
@@ -85,7 +87,7 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
     ctx.pidx = thread_pidx(pd, gbase, IO_GROUP, tid);
     ctx.ph = cplx{1.0, 0.0};
     ctx.ph_dirty = false;
-    ctx.tables = pd.tables;
+    ctx.tid = tid;
     for (int c0 = 0; c0 < pd.n_ops; c0 += OPS_CHUNK) {
         const int n = min(OPS_CHUNK, pd.n_ops - c0);
         __syncthreads();  // previous chunk fully consumed
@@ -96,14 +98,29 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
             for (int i = tid; i < n16; i += NTHREADS) dst[i] = src[i];
         }
         __syncthreads();
+        // stage the chunk's phase tables: the thread-index factors as they are, the byte tables
+        // reduced to one constant per CTA (they only see index bits outside the tile)
+        for (int e = tid; e < n * TABLE_TILE_ENTRIES; e += NTHREADS) {
+            const int k = e / TABLE_TILE_ENTRIES, j = e % TABLE_TILE_ENTRIES;
+            const OpHdr h = load_hdr(sops[k]);
+            if (is_table_op(h.code) && (h.flags() & F_TABLE)) s_tl[k][j] = pd.tables[(size_t)h.tab * TABLE_UNIT + j];
+        }
+        if (tid < n) {
+            const OpHdr h = load_hdr(sops[tid]);
+            if (is_table_op(h.code) && (h.flags() & F_TABLE)) s_wc[tid] = table_cta_const(pd.tables, h.tab, h.regm(), gbase);
+        }
+        __syncthreads();
+        OpHdr next = load_hdr(sops[0]);
         for (int k = 0; k < n; ++k) {
             const DevOp& op = sops[k];
-            const int code = op.code;
+            const OpHdr h = next;
+            if (k + 1 < n) next = load_hdr(sops[k + 1]);
+            const int code = h.code;
             if (code >= OC_SWITCH) {
                 const int from = (code - OC_SWITCH) / NGROUPS, to = (code - OC_SWITCH) % NGROUPS;
                 flush_phase(a, ctx);
                 __syncthreads();   // the previous transpose's loads are done everywhere
-                if (op.flags & F_PERM) {
+                if (h.flags() & F_PERM) {
                     if (from == 0) stage_store_perm<0>(tile, a, tid, op, gbase);
                     else if (from == 1) stage_store_perm<1>(tile, a, tid, op, gbase);
                     else stage_store_perm<2>(tile, a, tid, op, gbase);
@@ -119,7 +136,7 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
                 ctx.pidx = thread_pidx(pd, gbase, to, tid);
                 continue;
             }
-            apply_op(a, op, ctx);
+            apply_op(a, h, op, ctx, s_tl[k], &s_wc[k]);
         }
     }
     flush_phase(a, ctx);   // the planner always ends a pass in the IO layout

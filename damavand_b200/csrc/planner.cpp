@@ -274,20 +274,34 @@ struct StageEmitter {
         perm = PermAcc();
         set_stage(to);
     }
-    // Sub-tables for scale * prod_c f_c^{x_c} over thread-level partners; returns (tab, bytemask).
-    void build_tables(const std::vector<std::pair<int, cl>>& partners, const cl& scale, int32_t* tab, uint8_t* bytes) {
+    // Table block (see tile_core.cuh) for scale * prod_c f_c^{x_c} over thread-level partners of the
+    // current stage: tile qubits go to the two thread-index tables, the rest to per-byte tables of the
+    // CTA's base index.
+    void build_tables(const std::vector<std::pair<int, cl>>& partners, const cl& scale, DevOp* op) {
+        std::vector<cl> tile_tab(TABLE_TILE_ENTRIES, cl(1, 0));
+        for (int v = 0; v < 16; ++v) tile_tab[v] = scale;
         uint8_t mask = 0;
-        for (auto& pr : partners) mask |= (uint8_t)(1u << (pr.first / 8));
-        if (mask == 0) mask = 1;      // constant only: one sub-table
-        *tab = (int32_t)(pass.tables.size() / TABLE_ENTRIES);
-        *bytes = mask;
-        bool first = true;
+        const int sh = REG_BITS * group;
+        for (auto& pr : partners) {
+            const int p = pos_of[pr.first];
+            if (p >= 0) {
+                if (p >= sh && p < sh + REG_BITS) throw std::runtime_error("plan_local: register qubit in a thread table");
+                const int tb = p < sh ? p : p - REG_BITS;          // bit of the thread index
+                const int base = tb < 4 ? 0 : 16, bit = 1 << (tb & 3);
+                for (int v = 0; v < 16; ++v) if (v & bit) tile_tab[base + v] *= pr.second;
+            } else {
+                mask |= (uint8_t)(1u << (pr.first / 8));
+            }
+        }
+        op->tab = (int32_t)(pass.tables.size() / TABLE_UNIT);
+        op->regm = mask;
+        op->flags |= F_TABLE;
+        for (auto& e : tile_tab) pass.tables.push_back(to_cplx(e));
         for (int by = 0; by < MAX_INDEX_BYTES; ++by) {
             if (!((mask >> by) & 1)) continue;
-            std::vector<cl> e(TABLE_ENTRIES, first ? scale : cl(1, 0));
-            first = false;
+            std::vector<cl> e(TABLE_ENTRIES, cl(1, 0));
             for (auto& pr : partners) {
-                if (pr.first / 8 != by) continue;
+                if (pos_of[pr.first] >= 0 || pr.first / 8 != by) continue;
                 const int bit = 1 << (pr.first % 8);
                 for (int v = 0; v < TABLE_ENTRIES; ++v) if (v & bit) e[v] *= pr.second;
             }
@@ -317,7 +331,7 @@ struct StageEmitter {
                 DevOp op = blank(-1);
                 op.code = OC_TABLE;
                 op.tmask = 1ull << q;
-                build_tables(tpart, A, &op.tab, &op.regm);
+                build_tables(tpart, A, &op);
                 pass.ops.push_back(op);
             } else if (!is_one(A)) {
                 DevOp op = blank(-1);
@@ -332,7 +346,7 @@ struct StageEmitter {
                 DevOp op = blank(-1);
                 op.code = OC_TABLE_REG + pr.first;
                 std::vector<std::pair<int, cl>> one{{q, pr.second}};
-                build_tables(one, cl(1, 0), &op.tab, &op.regm);
+                build_tables(one, cl(1, 0), &op);
                 pass.ops.push_back(op);
             }
             return;
@@ -361,7 +375,7 @@ struct StageEmitter {
         // general: (tables | constant A) x register-partner factors on the registers with bit r
         DevOp op = blank(-1);
         op.code = OC_TABLE_REG + r;
-        if (!tpart.empty()) build_tables(tpart, A, &op.tab, &op.regm);
+        if (!tpart.empty()) build_tables(tpart, A, &op);
         else { const cplx f = to_cplx(A); op.m[6] = f.x; op.m[7] = f.y; }
         for (auto& pr : rpart) {
             const int slot = pr.first < r ? pr.first : pr.first - 1;     // index among the other three bits, ascending
@@ -382,12 +396,9 @@ struct StageEmitter {
         // only thread-level qubits remain
         std::vector<std::pair<int, cl>> ones;
         for (auto& kv : acc.a) if (!is_one(kv.second)) ones.push_back({kv.first, kv.second});
-        std::vector<std::pair<std::pair<int, int>, cl>> same, cross;
-        for (auto& kv : acc.b) {
-            if (is_one(kv.second)) continue;
-            (kv.first.first / 8 == kv.first.second / 8 ? same : cross).push_back({kv.first, kv.second});
-        }
-        if (same.empty() && ones.size() <= 2) {
+        std::vector<std::pair<std::pair<int, int>, cl>> cross;
+        for (auto& kv : acc.b) if (!is_one(kv.second)) cross.push_back({kv.first, kv.second});
+        if (ones.size() <= 2) {
             bool k_done = is_one(acc.K);
             for (auto& pr : ones) {
                 DevOp op = blank(-1);
@@ -408,32 +419,13 @@ struct StageEmitter {
                 pass.ops.push_back(op);
             }
         } else {
-            // one table op: K, the 1-body factors and the pairs that live inside one byte
+            // one table op: K and all the 1-body factors
             DevOp op = blank(-1);
             op.code = OC_TABLE;
-            uint8_t mask = 0;
-            for (auto& pr : ones) mask |= (uint8_t)(1u << (pr.first / 8));
-            for (auto& pr : same) mask |= (uint8_t)(1u << (pr.first.first / 8));
-            if (mask == 0) mask = 1;
-            op.tab = (int32_t)(pass.tables.size() / TABLE_ENTRIES);
-            op.regm = mask;
-            bool first = true;
-            for (int by = 0; by < MAX_INDEX_BYTES; ++by) {
-                if (!((mask >> by) & 1)) continue;
-                for (int v = 0; v < TABLE_ENTRIES; ++v) {
-                    cl e = first ? acc.K : cl(1, 0);
-                    for (auto& pr : ones)
-                        if (pr.first / 8 == by && ((v >> (pr.first % 8)) & 1)) e *= pr.second;
-                    for (auto& pr : same)
-                        if (pr.first.first / 8 == by && ((v >> (pr.first.first % 8)) & 1) && ((v >> (pr.first.second % 8)) & 1))
-                            e *= pr.second;
-                    pass.tables.push_back(to_cplx(e));
-                }
-                first = false;
-            }
+            build_tables(ones, acc.K, &op);
             pass.ops.push_back(op);
         }
-        // pairs that straddle two bytes: pivot tables, greedy on the pair graph
+        // thread-level pairs: pivot tables, greedy on the pair graph
         while (!cross.empty()) {
             std::map<int, int> deg;
             for (auto& pr : cross) { deg[pr.first.first]++; deg[pr.first.second]++; }
@@ -449,7 +441,7 @@ struct StageEmitter {
             DevOp op = blank(-1);
             op.code = OC_TABLE;
             op.tmask = 1ull << pivot;
-            build_tables(partners, cl(1, 0), &op.tab, &op.regm);
+            build_tables(partners, cl(1, 0), &op);
             pass.ops.push_back(op);
             cross.swap(rest);
         }

@@ -75,6 +75,7 @@ enum OpFlags : uint8_t {
     F_TCTRL = 4,      // thread-level control parity mask in cmask must be odd
     F_PERM = 8,       // OC_SWITCH: PermPayload in m[]
     F_PM_SHIFT = 4,   // OC_TABLE_REG: bits 4..6 = which of the other three register bits carry a factor
+    F_TABLE = 128,    // table ops: the op has a phase table (else OC_TABLE_REG uses the constant m[6..7])
 };
 
 // One operation as the device sees it, fully decoded by the planner for the stage it runs in.
@@ -83,14 +84,32 @@ struct alignas(16) DevOp {
     uint64_t tmask;    // thread-level part of the target parity mask (diagonal ops, table pivot)
     uint64_t cmask;    // thread-level part of the control parity mask (0 = none)
     int32_t code;      // OpCode (+ operands)
-    int32_t tab;       // table ops: first sub-table (units of TABLE_ENTRIES entries)
+    int32_t tab;       // table ops: start of the op's table block, in units of 16 entries (see TableBlock)
     int32_t gate_idx;  // caller's gate index (-1 for fused / layout ops)
     int8_t group;      // register group the op runs in (OC_SWITCH: the group it switches to)
     int8_t creg;       // OC_CGEN: control register bit
-    uint8_t regm;      // OC_DIAGGEN: tregm | cregm << 4;  table ops: bytes of the index that have a sub-table
+    uint8_t regm;      // OC_DIAGGEN: tregm | cregm << 4;  table ops: bytes of the CTA base index with a sub-table
     uint8_t flags;     // OpFlags
 };
 static_assert(sizeof(DevOp) == 96, "DevOp layout");
+
+// The 16 header bytes of a DevOp, fetched with one 128-bit shared-memory load.
+struct alignas(16) OpHdr {
+    int32_t code, tab, gate_idx;
+    uint32_t packed;   // group | creg << 8 | regm << 16 | flags << 24
+    DVD_HD unsigned flags() const { return packed >> 24; }
+    DVD_HD unsigned regm() const { return (packed >> 16) & 255u; }
+    DVD_HD int creg() const { return (int)(int8_t)((packed >> 8) & 255u); }
+};
+DVD_HD OpHdr load_hdr(const DevOp& op) { return *reinterpret_cast<const OpHdr*>(&op.code); }
+
+// Phase table block of one table op (all entries complex128):
+//   [16: factor by thread-index bits 0..3][16: by thread-index bits 4..7][256 per set bit of regm: by
+//   byte b of the CTA's physical base index].  The first two depend only on the thread's position in
+//   the tile and are staged in shared memory with the op; the byte tables are looked up ONCE per CTA
+//   (they only see bits outside the tile) and staged as a single constant.
+constexpr int TABLE_TILE_ENTRIES = 32;
+constexpr int TABLE_UNIT = 16;
 
 // Payload of a permuting OC_SWITCH, stored over DevOp::m.  The amplitude at tile index i moves to
 //   i' = xor_{p : bit p of i} col[p]  ^  v0  ^  xor_k [parity(physical base & cond_mask_k)] cond_vec[k]
@@ -174,7 +193,7 @@ struct ThreadCtx {
     uint64_t pidx;   // physical index of register 0 (register bits zero), rank bits included
     cplx ph;         // lazily accumulated scalar phase common to all 16 registers
     bool ph_dirty;
-    const cplx* tables;   // phase tables of the pass
+    int tid;         // thread index inside the CTA
 };
 
 DVD_HD void flush_phase(cplx (&a)[NREG], ThreadCtx& ctx) {
@@ -246,15 +265,15 @@ DVD_HD void scale_pair(cplx (&a)[NREG], double wr, double wi) {
     for (int j = 0; j < NREG; ++j) if (((j >> B0) & 1) && ((j >> B1) & 1)) a[j] = cmul(a[j], wr, wi);
 }
 
-// Product of the phase sub-tables selected by the bytes of the thread's physical index.
-DVD_HD cplx table_lookup(const cplx* __restrict__ tables, int tab, unsigned bytes, uint64_t pidx) {
+// CTA-constant part of a table op: product of the byte sub-tables at the CTA's physical base index.
+DVD_HD cplx table_cta_const(const cplx* __restrict__ tables, int tab, unsigned bytes, uint64_t gbase) {
     cplx w{1.0, 0.0};
     bool first = true;
-    const cplx* t = tables + (size_t)tab * TABLE_ENTRIES;
+    const cplx* t = tables + (size_t)tab * TABLE_UNIT + TABLE_TILE_ENTRIES;
 #pragma unroll
     for (int b = 0; b < MAX_INDEX_BYTES; ++b) {
         if ((bytes >> b) & 1u) {
-            const cplx e = t[(unsigned)(pidx >> (8 * b)) & 255u];
+            const cplx e = t[(unsigned)(gbase >> (8 * b)) & 255u];
             w = first ? e : cmul(w, e.x, e.y);
             first = false;
             t += TABLE_ENTRIES;
@@ -262,14 +281,19 @@ DVD_HD cplx table_lookup(const cplx* __restrict__ tables, int tab, unsigned byte
     }
     return w;
 }
+// Full table value of a thread: CTA constant x the two thread-index factors.
+DVD_HD cplx table_value(const cplx* tl, const cplx* wc, int tid) {
+    const cplx lo = tl[tid & 15], hi = tl[16 + (tid >> 4)];
+    return cmul(cmul(*wc, lo.x, lo.y), hi.x, hi.y);
+}
 
-// Registers with bit B set *= W * prod_k f_k^{bit o_k of j}: W from the tables (or the constant
+// Registers with bit B set *= W * prod_k f_k^{bit o_k of j}: W from the table (or the constant
 // m[6..7] when the op has none), f_k = m[2k..2k+1] for the other three register bits o_0<o_1<o_2.
 template <int B>
-DVD_HD void table_reg(cplx (&a)[NREG], const DevOp& op, const ThreadCtx& ctx) {
+DVD_HD void table_reg(cplx (&a)[NREG], const DevOp& op, unsigned flags, const ThreadCtx& ctx, const cplx* tl, const cplx* wc) {
     constexpr int O0 = B == 0 ? 1 : 0, O1 = B <= 1 ? 2 : 1, O2 = B <= 2 ? 3 : 2;
-    const unsigned pm = (op.flags >> F_PM_SHIFT) & 7u;
-    const cplx w = op.regm ? table_lookup(ctx.tables, op.tab, op.regm, ctx.pidx) : cplx{op.m[6], op.m[7]};
+    const unsigned pm = (flags >> F_PM_SHIFT) & 7u;
+    const cplx w = (flags & F_TABLE) ? table_value(tl, wc, ctx.tid) : cplx{op.m[6], op.m[7]};
     cplx w4[4];
     w4[0] = w;
     w4[1] = (pm & 1u) ? cmul(w, op.m[0], op.m[1]) : w;
@@ -321,9 +345,10 @@ DVD_HD unsigned perm_index(const DevOp& op, unsigned v, unsigned idx) {
     case (base) + 3: { constexpr int B = 3; STMT; } break;
 
 // Apply one op (anything but OC_SWITCH) to the 16 register-resident amplitudes of a thread.
-DVD_HD void apply_op(cplx (&a)[NREG], const DevOp& op, ThreadCtx& ctx) {
-    const int code = op.code;
-    const unsigned flags = op.flags;
+// h: the op's header (already fetched); tl / wc: the op's staged table entries and CTA constant.
+DVD_HD void apply_op(cplx (&a)[NREG], const OpHdr& h, const DevOp& op, ThreadCtx& ctx, const cplx* tl, const cplx* wc) {
+    const int code = h.code;
+    const unsigned flags = h.flags();
     if ((flags & F_TCTRL) && !parity64(ctx.pidx & op.cmask)) return;   // thread-level control
     const double* m = op.m;
     switch (code) {
@@ -331,7 +356,7 @@ DVD_HD void apply_op(cplx (&a)[NREG], const DevOp& op, ThreadCtx& ctx) {
         DVD_CASE4(OC_GATE + 4 * K_REAL, (gate_all<B, K_REAL>(a, m)))
         DVD_CASE4(OC_GATE + 4 * K_RXLIKE, (gate_all<B, K_RXLIKE>(a, m)))
         DVD_CASE4(OC_GATE + 4 * K_ANTIDIAG, (gate_all<B, K_ANTIDIAG>(a, m)))
-        DVD_CASE4(OC_CGEN, (cgen<B>(a, m, op.creg)))
+        DVD_CASE4(OC_CGEN, (cgen<B>(a, m, h.creg())))
         DVD_CASE4(OC_DIAG1, (diag_regbit<B>(a, m, (flags & F_D0_ONE) != 0)))
         case OC_PHASE: {
             const bool tpar = parity64(ctx.pidx & op.tmask) != 0;
@@ -341,7 +366,7 @@ DVD_HD void apply_op(cplx (&a)[NREG], const DevOp& op, ThreadCtx& ctx) {
             }
         } break;
         case OC_DIAGGEN: {   // control handled here: thread-level and register-level parts combine
-            const int tregm = op.regm & 15, cregm = op.regm >> 4;
+            const int tregm = h.regm() & 15, cregm = h.regm() >> 4;
             const bool has_ctrl = (flags & F_HAS_CTRL) != 0;
             const bool cpar = op.cmask != 0 && parity64(ctx.pidx & op.cmask) != 0;
             const bool tpar = parity64(ctx.pidx & op.tmask) != 0;
@@ -355,12 +380,12 @@ DVD_HD void apply_op(cplx (&a)[NREG], const DevOp& op, ThreadCtx& ctx) {
         } break;
         case OC_TABLE: {
             if (op.tmask == 0 || parity64(ctx.pidx & op.tmask)) {
-                const cplx w = table_lookup(ctx.tables, op.tab, op.regm, ctx.pidx);
+                const cplx w = table_value(tl, wc, ctx.tid);
                 ctx.ph = cmul(ctx.ph, w.x, w.y);
                 ctx.ph_dirty = true;
             }
         } break;
-        DVD_CASE4(OC_TABLE_REG, (table_reg<B>(a, op, ctx)))
+        DVD_CASE4(OC_TABLE_REG, (table_reg<B>(a, op, flags, ctx, tl, wc)))
         case OC_PAIR + 0: scale_pair<0, 1>(a, m[0], m[1]); break;
         case OC_PAIR + 1: scale_pair<0, 2>(a, m[0], m[1]); break;
         case OC_PAIR + 2: scale_pair<0, 3>(a, m[0], m[1]); break;
@@ -370,5 +395,6 @@ DVD_HD void apply_op(cplx (&a)[NREG], const DevOp& op, ThreadCtx& ctx) {
         default: break;
     }
 }
+DVD_HD bool is_table_op(int code) { return code >= OC_TABLE && code < OC_PAIR; }
 
 }  // namespace dvd

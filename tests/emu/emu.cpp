@@ -32,7 +32,7 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
             ctx[tid].pidx = gbase | tile_offset(pd, stage_idx(IO_GROUP, tid, 0));
             ctx[tid].ph = cplx{1.0, 0.0};
             ctx[tid].ph_dirty = false;
-            ctx[tid].tables = pd.tables;
+            ctx[tid].tid = tid;
         }
         int cur = IO_GROUP;
         for (const DevOp& op : pass.ops) {
@@ -60,7 +60,14 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
                 continue;
             }
             if (op.group != cur) throw std::runtime_error("emu: op not in its register group");
-            for (int tid = 0; tid < NTHREADS; ++tid) apply_op(regs[tid], op, ctx[tid]);
+            const OpHdr h = load_hdr(op);
+            cplx wc{1.0, 0.0};
+            const cplx* tl = nullptr;
+            if (is_table_op(h.code) && (h.flags() & F_TABLE)) {
+                tl = pd.tables + (size_t)h.tab * TABLE_UNIT;
+                wc = table_cta_const(pd.tables, h.tab, h.regm(), gbase);
+            }
+            for (int tid = 0; tid < NTHREADS; ++tid) apply_op(regs[tid], h, op, ctx[tid], tl, &wc);
         }
         for (int tid = 0; tid < NTHREADS; ++tid) flush_phase(regs[tid], ctx[tid]);
         if (cur != IO_GROUP) throw std::runtime_error("emu: pass does not end in the IO layout");
