@@ -290,23 +290,34 @@ def main():
     n_local = n - int(np.log2(args.gpus))
     pass_bytes = 32.0 * (1 << n_local)
     roofline = None
-    if launches_fwd > 0 and st1["global_swaps"] == 0:
-        achieved = st1["pass_bytes"] / (fwd_ms / 1e3) / 1e9
+    if launches_fwd > 0:
+        fwd_s = fwd_ms / 1e3
+        # a non-controlled gate = 32*2^n_local B, a controlled gate = 16*2^n_local B; a launch of the
+        # pass kernel processes (gates / launches) of them.  achieved = algorithmic bytes per launch / mean launch
+        # duration = total algorithmic bytes / forward time (CUDA events on the engine's stream).
+        achieved = st1["gate_algorithmic_bytes"] / fwd_s / 1e9
+        hbm_gbs = st1["pass_bytes"] / fwd_s / 1e9
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get(f"{name}_g{args.gpus}", {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": "k_tile_pass" if st1["tile_passes"] else "k_simple_gate",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": traffic, "peak_source": peak_src,
                     "launches_per_circuit": launches_fwd, "avg_launch_ms": fwd_ms / launches_fwd,
-                    "algorithmic_bytes_per_launch": st1["pass_bytes"] / launches_fwd,
-                    "effective_gate_gbs": st1["gate_algorithmic_bytes"] / (fwd_ms / 1e3) / 1e9,
-                    "note": "achieved = (launches x 32 B x 2^n_local) / CUDA-event time of one forward; "
-                            "effective_gate_gbs counts 32*2^n B per gate (16*2^n if controlled) and exceeds the "
-                            "HBM peak because several gates share one pass"}
-    elif launches_fwd > 0:
-        achieved = st1["pass_bytes"] / (fwd_ms / 1e3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_tile_pass + NVLink swaps", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "global_swaps": st1["global_swaps"], "swap_bytes_sent_per_rank": st1["swap_bytes_sent"],
-                    "note": "forward time includes the NVLink exchanges; HBM fraction of the whole forward"}
+                    "algorithmic_bytes_per_launch": st1["gate_algorithmic_bytes"] / launches_fwd,
+                    "hbm_bytes_per_launch": pass_bytes,
+                    "hbm_pass_gbs": hbm_gbs, "hbm_pass_frac": hbm_gbs / peak,
+                    "note": "achieved counts SURVEY 8(d) algorithmic bytes (32*2^n B per gate, 16*2^n if controlled); "
+                            "it exceeds the HBM peak because one launch applies many gates while moving 32*2^n B once. "
+                            "hbm_pass_gbs = bytes the passes really move / time (what ncu's dram__bytes shows); the fused "
+                            "passes are fp64-pipe / issue bound, not HBM bound (DESIGN.md section 3)"}
+        if st1["global_swaps"]:
+            roofline["kernel"] += " + NVLink half-chunk swaps"
+            roofline["global_swaps"] = st1["global_swaps"]
+            roofline["swap_bytes_sent_per_rank"] = st1["swap_bytes_sent"]
 
     # e2e through the public API with host buffers: gates in, samples + expectation values out
     e2e = None

@@ -14,7 +14,6 @@ namespace dvd {
 // =================================================================================================
 // Tiled multi-gate pass
 // =================================================================================================
-constexpr int OPS_CHUNK = 32;
 
 // Register <-> shared-memory transposes.  Thanks to the additive padding (smem_slot) every
 // register's slot is a compile-time offset from one per-thread base.
@@ -100,21 +99,21 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
         __syncthreads();
         // stage the chunk's phase tables: the thread-index factors as they are, the byte tables
         // reduced to one constant per CTA (they only see index bits outside the tile)
-        for (int e = tid; e < n * TABLE_TILE_ENTRIES; e += NTHREADS) {
-            const int k = e / TABLE_TILE_ENTRIES, j = e % TABLE_TILE_ENTRIES;
-            const OpHdr h = load_hdr(sops[k]);
-            if (is_table_op(h.code) && (h.flags() & F_TABLE)) s_tl[k][j] = pd.tables[(size_t)h.tab * TABLE_UNIT + j];
+        if ((pd.table_chunks >> (c0 / OPS_CHUNK)) & 1ull) {
+            for (int e = tid; e < n * TABLE_TILE_ENTRIES; e += NTHREADS) {
+                const int k = e / TABLE_TILE_ENTRIES, j = e % TABLE_TILE_ENTRIES;
+                const OpHdr h = load_hdr(sops[k]);
+                if (is_table_op(h.code) && (h.flags() & F_TABLE)) s_tl[k][j] = pd.tables[(size_t)h.tab * TABLE_UNIT + j];
+            }
+            if (tid < n) {
+                const OpHdr h = load_hdr(sops[tid]);
+                if (is_table_op(h.code) && (h.flags() & F_TABLE)) s_wc[tid] = table_cta_const(pd.tables, h.tab, h.regm(), gbase);
+            }
+            __syncthreads();
         }
-        if (tid < n) {
-            const OpHdr h = load_hdr(sops[tid]);
-            if (is_table_op(h.code) && (h.flags() & F_TABLE)) s_wc[tid] = table_cta_const(pd.tables, h.tab, h.regm(), gbase);
-        }
-        __syncthreads();
-        OpHdr next = load_hdr(sops[0]);
         for (int k = 0; k < n; ++k) {
             const DevOp& op = sops[k];
-            const OpHdr h = next;
-            if (k + 1 < n) next = load_hdr(sops[k + 1]);
+            const OpHdr h = load_hdr(op);
             const int code = h.code;
             if (code >= OC_SWITCH) {
                 const int from = (code - OC_SWITCH) / NGROUPS, to = (code - OC_SWITCH) % NGROUPS;

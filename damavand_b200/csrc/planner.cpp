@@ -398,7 +398,7 @@ struct StageEmitter {
         for (auto& kv : acc.a) if (!is_one(kv.second)) ones.push_back({kv.first, kv.second});
         std::vector<std::pair<std::pair<int, int>, cl>> cross;
         for (auto& kv : acc.b) if (!is_one(kv.second)) cross.push_back({kv.first, kv.second});
-        if (ones.size() <= 2) {
+        if (ones.size() <= 4) {
             bool k_done = is_one(acc.K);
             for (auto& pr : ones) {
                 DevOp op = blank(-1);
@@ -620,6 +620,9 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
         em.flush_all();
         em.emit_switch(IO_GROUP);
         pass.desc.n_ops = (int)pass.ops.size();
+        if (pass.desc.n_ops > MAX_OPS_PER_PASS) throw std::runtime_error("plan_local: too many ops in one pass");
+        for (size_t k = 0; k < pass.ops.size(); ++k)
+            if (is_table_op(pass.ops[k].code) && (pass.ops[k].flags & F_TABLE)) pass.desc.table_chunks |= 1ull << (k / OPS_CHUNK);
         passes.push_back(std::move(pass));
         pending.swap(rest);
     }

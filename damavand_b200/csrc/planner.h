@@ -45,7 +45,7 @@ struct Pass {
 struct PlanOptions {
     int min_low = 3;           // tile always contains physical qubits [0, min_low): 128 B segments
     int window = 16384;        // look-ahead (gates) when filling a pass
-    int max_ops_per_pass = 1 << 20;
+    int max_ops_per_pass = 1024;   // gates taken into one pass (the op stream is capped at MAX_OPS_PER_PASS)
 };
 
 // Classify a 2x2 by exact zero / one tests on its entries.

@@ -135,7 +135,10 @@ struct PassDesc {
     int32_t sorted_q[TILE_BITS];  // the same qubits in ascending order
     uint64_t rank_bits;           // this rank's value of the global (rank-index) qubits, in place
     const cplx* tables;           // phase tables of this pass (device pointer; host pointer in the replay)
+    uint64_t table_chunks;        // bit c: ops [32c, 32c+32) contain a table op (its tables get staged)
 };
+constexpr int OPS_CHUNK = 32;
+constexpr int MAX_OPS_PER_PASS = 64 * OPS_CHUNK;
 
 // ---- index helpers ---------------------------------------------------------------------------
 // Tile index of register j of thread tid when group g's tile positions live in registers.
