@@ -10,7 +10,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdamavand_b200.so")
+# DVD_LIB_PATH: development override used to A/B two builds of the same C ABI on one GPU box
+LIB_PATH = os.environ.get("DVD_LIB_PATH") or os.path.join(HERE, "libdamavand_b200.so")
 
 NCCL_ID_BYTES = 128
 

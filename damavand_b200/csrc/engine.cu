@@ -54,16 +54,20 @@ struct dvd_state {
     cudaEvent_t ev_pack[2] = {nullptr, nullptr}, ev_comm[2] = {nullptr, nullptr};
     std::vector<HostGate> pending;
     std::vector<int> perm;      // logical -> physical (identity between flushes)
-    DevOp* d_ops = nullptr; size_t d_ops_cap = 0;
-    DevOp* h_ops = nullptr; size_t h_ops_cap = 0;
+    PassParams pass_params;     // staging for the kernel parameter block (copied at launch)
     cplx* d_tabs = nullptr; cplx* h_tabs = nullptr; size_t tabs_cap = 0;   // phase tables of the queued passes
     double* d_tree = nullptr; bool tree_valid = false;
     double* d_scratch = nullptr; size_t scratch_doubles = 0;
     ncclComm_t comm = nullptr;
     cplx* swap_buf[4] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t swap_chunk = 0;
+    // direct peer path: partner states (rank ^ 2^j) mapped with CUDA IPC; d_bar backs the stream barriers
+    bool peer_swap = false;
+    cplx* peer_amp[16] = {nullptr};
+    double* d_bar = nullptr;
     dvd_stats stats;
     bool unfused = false;
+    double stagger_frac = 0.0;  // DVD_STAGGER: fraction of the estimated CTA lifetime the second CTA per SM is held back
     PlanOptions opt;
 };
 
@@ -86,6 +90,54 @@ static int set_zero_state(dvd_state* s) {
     return DVD_OK;
 }
 
+// Stream-ordered barrier over all ranks: a one-element allreduce completes on a rank only after every
+// rank's stream has reached it, i.e. after all earlier kernels on every rank's stream have finished.
+static int stream_barrier(dvd_state* s) {
+    NC(g_nccl.AllReduce(s->d_bar, s->d_bar + 1, 1, ncclDouble, ncclSum, s->comm, s->stream));
+    return DVD_OK;
+}
+
+// Map the partner ranks' state buffers into this process (CUDA IPC, one node) so that global<->local
+// qubit swaps can run as one kernel over NVLink peer memory.  Every rank must take the same path, so
+// the outcome is agreed on with an allreduce(min); DVD_SWAP=nccl forces the staged NCCL send/recv path
+// (the only one that works across nodes).
+static int map_peers(dvd_state* s) {
+    CU(cudaMalloc(&s->d_bar, 4 * sizeof(double)));
+    CU(cudaMemsetAsync(s->d_bar, 0, 4 * sizeof(double), s->stream));
+    int g = 0; while ((1 << g) < s->world) ++g;
+    const char* mode = getenv("DVD_SWAP");
+    double ok = (mode && std::string(mode) == "nccl") ? 0.0 : 1.0;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::vector<cudaIpcMemHandle_t> handles(s->world);
+    unsigned char* d_h = nullptr;
+    CU(cudaMalloc(&d_h, (size_t)s->world * 64));
+    cudaIpcMemHandle_t mine;
+    if (cudaIpcGetMemHandle(&mine, s->amp) != cudaSuccess) { cudaGetLastError(); ok = 0.0; std::memset(&mine, 0, sizeof mine); }
+    CU(cudaMemcpyAsync(d_h + (size_t)s->rank * 64, &mine, 64, cudaMemcpyHostToDevice, s->stream));
+    NC(g_nccl.AllGather(d_h + (size_t)s->rank * 64, d_h, 64, ncclChar, s->comm, s->stream));
+    CU(cudaMemcpyAsync(handles.data(), d_h, (size_t)s->world * 64, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaFree(d_h));
+    if (ok != 0.0) {
+        for (int j = 0; j < g; ++j) {
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, handles[s->rank ^ (1 << j)], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError(); ok = 0.0; break;
+            }
+            s->peer_amp[j] = static_cast<cplx*>(p);
+        }
+    }
+    double agreed = 0.0;
+    CU(cudaMemcpyAsync(s->d_bar + 2, &ok, sizeof ok, cudaMemcpyHostToDevice, s->stream));
+    NC(g_nccl.AllReduce(s->d_bar + 2, s->d_bar + 3, 1, ncclDouble, ncclMin, s->comm, s->stream));
+    CU(cudaMemcpyAsync(&agreed, s->d_bar + 3, sizeof agreed, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->peer_swap = agreed != 0.0;
+    if (!s->peer_swap)
+        for (auto& p : s->peer_amp) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+    return DVD_OK;
+}
+
 static int create_common(int n_qubits, int device, int rank, int world, const void* nccl_id, dvd_state** out) {
     if (!out) return fail(DVD_ERR_ARG, "out is null");
     *out = nullptr;
@@ -105,6 +157,8 @@ static int create_common(int n_qubits, int device, int rank, int world, const vo
     s->n_qubits = n_qubits; s->n_local = n_qubits - g; s->rank = rank; s->world = world; s->device = device;
     s->n_amps = 1ull << s->n_local;
     s->rank_bits = (uint64_t)rank << s->n_local;
+    if (const char* e = getenv("DVD_STAGGER")) s->stagger_frac = atof(e);
+    if (const char* e = getenv("DVD_PLAN_CANDIDATES")) s->opt.candidates = std::max(1, atoi(e));
     s->perm.resize(n_qubits);
     for (int q = 0; q < n_qubits; ++q) s->perm[q] = q;
     auto cleanup = [&](int code) { dvd_destroy(s); return code; };
@@ -136,6 +190,8 @@ static int create_common(int n_qubits, int device, int rank, int world, const vo
         std::memcpy(&id, nccl_id, sizeof id);
         ncclResult_t r = g_nccl.CommInitRank(&s->comm, world, id, rank);
         if (r != ncclSuccess) return cleanup(fail(DVD_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)));
+        int prc = map_peers(s);
+        if (prc != DVD_OK) return cleanup(prc);
     }
     int rc = set_zero_state(s);
     if (rc != DVD_OK) return cleanup(rc);
@@ -190,11 +246,11 @@ int dvd_destroy(dvd_state* s) {
     if (s->amp) cudaFree(s->amp);
     if (s->d_tree) cudaFree(s->d_tree);
     if (s->d_scratch) cudaFree(s->d_scratch);
-    if (s->d_ops) cudaFree(s->d_ops);
-    if (s->h_ops) cudaFreeHost(s->h_ops);
     if (s->d_tabs) cudaFree(s->d_tabs);
     if (s->h_tabs) cudaFreeHost(s->h_tabs);
     for (auto& b : s->swap_buf) if (b) cudaFree(b);
+    for (auto& p : s->peer_amp) if (p) cudaIpcCloseMemHandle(p);
+    if (s->d_bar) cudaFree(s->d_bar);
     for (int i = 0; i < 2; ++i) {
         if (s->ev_pack[i]) cudaEventDestroy(s->ev_pack[i]);
         if (s->ev_comm[i]) cudaEventDestroy(s->ev_comm[i]);
@@ -244,6 +300,23 @@ int dvd_apply_circuit(dvd_state* s, const dvd_gate* gates, int64_t n) {
 }  // extern "C"
 
 // ---- flush ---------------------------------------------------------------------------------------
+// Rough SM cycles one CTA pair spends on a pass (measured per-op costs on B200, 2 CTAs per SM).
+static double pass_cycle_estimate(const Pass& p) {
+    double c = 12000.0;   // tile load + store at the HBM rate
+    for (const DevOp& op : p.ops) {
+        const int code = op.code;
+        if (code >= OC_SWITCH) c += 2600.0;
+        else if (code < OC_GATE + 4 * K_REAL) c += 1150.0;
+        else if (code < OC_GATE + 4 * K_HADAMARD) c += 600.0;
+        else if (code < OC_CGEN) c += 300.0;
+        else if (code < OC_DIAG1) c += 800.0;
+        else if (code < OC_PHASE) c += 300.0;
+        else if (code >= OC_TABLE_REG && code < OC_PAIR) c += 650.0;
+        else c += 150.0;
+    }
+    return c;
+}
+
 static SimpleOp simple_op(const HostGate& g) {
     SimpleOp op;
     std::memcpy(op.m, g.m, sizeof op.m);
@@ -269,9 +342,21 @@ static int ensure_swap_buffers(dvd_state* s) {
 // (rust_communication.cu:106-141).  Chunked and double buffered: pack k+1 / unpack k-1 on the compute
 // stream overlap the ncclSend/ncclRecv of chunk k on the communication stream.
 static int global_swap(dvd_state* s, int gq, int lq) {
-    TRY(ensure_swap_buffers(s));
     const int j = gq - s->n_local;
     const int b = (s->rank >> j) & 1;
+    if (s->peer_swap) {
+        // one kernel over NVLink peer memory: this rank moves the pairs of its half of the element range,
+        // the partner the other half; barriers order it against the passes before and after on BOTH ranks
+        const uint64_t half = s->n_amps / 2, share = half / 2;
+        TRY(stream_barrier(s));
+        CU(launch_swap_peer(s->amp, s->peer_amp[j], lq, b, b ? share : 0, b ? half : share, s->stream));
+        TRY(stream_barrier(s));
+        s->stats.kernel_launches++;
+        s->stats.global_swaps++;
+        s->stats.swap_bytes_sent += (int64_t)(half * sizeof(cplx));
+        return DVD_OK;
+    }
+    TRY(ensure_swap_buffers(s));
     const int partner = s->rank ^ (1 << j);
     const int mybit = 1 - b;    // the half that leaves: local bit lq != my rank bit
     const uint64_t half = s->n_amps / 2, C = s->swap_chunk;
@@ -333,59 +418,54 @@ static int flush_impl(dvd_state* s) {
     } catch (const std::exception& e) {
         return fail(DVD_ERR_INTERNAL, std::string("planner: ") + e.what());
     }
-    // plan every local step up front so that all ops go to the device in one copy
+    // plan every local step up front so that all phase tables go to the device in one copy; the op
+    // lists travel as kernel parameters
     std::vector<std::vector<Pass>> plans(steps.size());
-    size_t total_ops = 0, total_tabs = 0;
+    size_t total_tabs = 0;
     if (tiled) {
         try {
             for (size_t i = 0; i < steps.size(); ++i)
                 if (steps[i].kind == DistStep::LOCAL_GATES) {
                     plans[i] = plan_local(steps[i].gates, s->n_local, s->n_qubits, s->opt);
-                    for (auto& p : plans[i]) { total_ops += p.ops.size(); total_tabs += p.tables.size(); }
+                    for (auto& p : plans[i]) total_tabs += p.tables.size();
                 }
         } catch (const std::exception& e) {
             return fail(DVD_ERR_INTERNAL, std::string("planner: ") + e.what());
         }
-        CU(cudaStreamSynchronize(s->stream));   // the pinned staging buffers may still be in flight
-        if (total_ops > s->h_ops_cap) {
-            if (s->h_ops) CU(cudaFreeHost(s->h_ops));
-            if (s->d_ops) CU(cudaFree(s->d_ops));
-            s->h_ops = nullptr; s->d_ops = nullptr; s->h_ops_cap = s->d_ops_cap = 0;
-            const size_t cap = std::max<size_t>(total_ops * 2, 4096);
-            CU(cudaMallocHost(&s->h_ops, cap * sizeof(DevOp)));
-            CU(cudaMalloc(&s->d_ops, cap * sizeof(DevOp)));
-            s->h_ops_cap = s->d_ops_cap = cap;
-        }
-        if (total_tabs > s->tabs_cap) {
-            if (s->h_tabs) CU(cudaFreeHost(s->h_tabs));
-            if (s->d_tabs) CU(cudaFree(s->d_tabs));
-            s->h_tabs = nullptr; s->d_tabs = nullptr; s->tabs_cap = 0;
-            const size_t cap = std::max<size_t>(total_tabs * 2, 64 * TABLE_ENTRIES);
-            CU(cudaMallocHost(&s->h_tabs, cap * sizeof(cplx)));
-            CU(cudaMalloc(&s->d_tabs, cap * sizeof(cplx)));
-            s->tabs_cap = cap;
-        }
-        size_t at = 0, tat = 0;
-        for (auto& pl : plans)
-            for (auto& p : pl) {
-                std::memcpy(s->h_ops + at, p.ops.data(), p.ops.size() * sizeof(DevOp)); at += p.ops.size();
-                if (!p.tables.empty()) std::memcpy(s->h_tabs + tat, p.tables.data(), p.tables.size() * sizeof(cplx));
-                tat += p.tables.size();
+        if (total_tabs) {
+            CU(cudaStreamSynchronize(s->stream));   // the pinned staging buffer may still be in flight
+            if (total_tabs > s->tabs_cap) {
+                if (s->h_tabs) CU(cudaFreeHost(s->h_tabs));
+                if (s->d_tabs) CU(cudaFree(s->d_tabs));
+                s->h_tabs = nullptr; s->d_tabs = nullptr; s->tabs_cap = 0;
+                const size_t cap = std::max<size_t>(total_tabs * 2, 64 * TABLE_ENTRIES);
+                CU(cudaMallocHost(&s->h_tabs, cap * sizeof(cplx)));
+                CU(cudaMalloc(&s->d_tabs, cap * sizeof(cplx)));
+                s->tabs_cap = cap;
             }
-        if (total_ops) CU(cudaMemcpyAsync(s->d_ops, s->h_ops, total_ops * sizeof(DevOp), cudaMemcpyHostToDevice, s->stream));
-        if (total_tabs) CU(cudaMemcpyAsync(s->d_tabs, s->h_tabs, total_tabs * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
+            size_t tat = 0;
+            for (auto& pl : plans)
+                for (auto& p : pl) {
+                    if (!p.tables.empty()) std::memcpy(s->h_tabs + tat, p.tables.data(), p.tables.size() * sizeof(cplx));
+                    tat += p.tables.size();
+                }
+            CU(cudaMemcpyAsync(s->d_tabs, s->h_tabs, total_tabs * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
+        }
     }
-    size_t at = 0, tat = 0;
+    size_t tat = 0;
     for (size_t i = 0; i < steps.size(); ++i) {
         DistStep& st = steps[i];
         if (st.kind == DistStep::GLOBAL_SWAP) { TRY(global_swap(s, st.gq, st.lq)); continue; }
         if (tiled) {
             for (auto& p : plans[i]) {
-                PassDesc pd = p.desc;
-                pd.rank_bits = s->rank_bits;
-                pd.tables = s->d_tabs + tat;
-                CU(launch_tile_pass(s->amp, s->d_ops + at, pd, s->stream));
-                at += p.ops.size(); tat += p.tables.size();
+                PassParams& pp = s->pass_params;
+                pp.pd = p.desc;
+                pp.pd.rank_bits = s->rank_bits;
+                pp.pd.tables = s->d_tabs + tat;
+                pp.pd.stagger = s->stagger_frac > 0.0 ? (int32_t)(s->stagger_frac * pass_cycle_estimate(p)) : 0;
+                std::memcpy(pp.ops, p.ops.data(), p.ops.size() * sizeof(DevOp));
+                CU(launch_tile_pass(s->amp, pp, s->stream));
+                tat += p.tables.size();
                 s->stats.kernel_launches++; s->stats.tile_passes++;
                 s->stats.stage_switches += p.n_switches;
                 s->stats.pass_bytes += 2.0 * chunk_bytes;

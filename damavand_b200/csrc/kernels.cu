@@ -49,6 +49,12 @@ __device__ __forceinline__ void stage_store_perm(cplx* tile, const cplx (&a)[NRE
 // recomputed for the write-back (opaque re-read of %tid / %ctaid) so that it does not occupy
 // registers while the gates run.
 struct IoAddr { cplx* p0; uint64_t hs[REG_BITS]; };
+// Every amplitude is touched exactly once per pass: stream it past L1 so that the phase tables stay there.
+__device__ __forceinline__ cplx ld_stream(const cplx* p) {
+    const double2 v = __ldcs(reinterpret_cast<const double2*>(p));
+    return cplx{v.x, v.y};
+}
+__device__ __forceinline__ void st_stream(cplx* p, cplx v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
 __device__ __forceinline__ IoAddr io_addr(cplx* amp, const PassDesc& pd) {
     unsigned tid, cta;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
@@ -60,15 +66,29 @@ __device__ __forceinline__ IoAddr io_addr(cplx* amp, const PassDesc& pd) {
     return io;
 }
 
+template <int FROM>
+__device__ __forceinline__ void switch_store(cplx* tile, const cplx (&a)[NREG], int tid, const DevOp& op, uint64_t gbase) {
+    if (op.flags & F_PERM) stage_store_perm<FROM>(tile, a, tid, op, gbase);
+    else stage_store<FROM>(tile, a, tid);
+}
+
+// One launch = one pass: every amplitude is read once and written once; pp.ops is applied in between.
+// The op list lives in the kernel's parameter space (constant bank): op fields are warp-uniform loads.
 __global__ void __launch_bounds__(NTHREADS, 2)
-k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_constant__ PassDesc pd) {
+k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* tile = reinterpret_cast<cplx*>(smem_raw);
-    __shared__ DevOp sops[OPS_CHUNK];
-    __shared__ cplx s_tl[OPS_CHUNK][TABLE_TILE_ENTRIES];   // thread-index phase factors of the chunk's table ops
-    __shared__ cplx s_wc[OPS_CHUNK];                       // their per-CTA constants
+    __shared__ cplx s_wc[MAX_TABLE_OPS];      // per-CTA constants of the pass's table ops
+    const PassDesc& pd = pp.pd;
 
     const int tid = threadIdx.x;
+    // Two CTAs share an SM and run the same op list: started together they sit in the same phase
+    // (HBM / fp64 / shared-memory transposes) all the time.  Holding back the second CTA of every SM
+    // by about half a CTA lifetime in the FIRST wave puts the pair in antiphase for the whole launch.
+    if (pd.stagger > 0 && blockIdx.x >= 148u && blockIdx.x < 296u) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)pd.stagger) __nanosleep(200);
+    }
     cplx a[NREG];
     {
         const IoAddr io = io_addr(amp, pd);
@@ -77,66 +97,41 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
             uint64_t off = 0;
 #pragma unroll
             for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += io.hs[k];
-            a[j] = io.p0[off];
+            a[j] = ld_stream(io.p0 + off);
         }
     }
 
     const uint64_t gbase = cta_base(pd, (uint64_t)blockIdx.x) | pd.rank_bits;
+    const cplx* __restrict__ tables = pd.tables;
+    const int n_tab = pd.n_tab;
+    if (n_tab > 0) {   // byte tables only see index bits outside the tile: one constant per CTA and table op
+        if (tid < n_tab) s_wc[tid] = table_cta_const(tables, tid, gbase);
+        __syncthreads();
+    }
     ThreadCtx ctx;
     ctx.pidx = thread_pidx(pd, gbase, IO_GROUP, tid);
     ctx.ph = cplx{1.0, 0.0};
     ctx.ph_dirty = false;
     ctx.tid = tid;
-    for (int c0 = 0; c0 < pd.n_ops; c0 += OPS_CHUNK) {
-        const int n = min(OPS_CHUNK, pd.n_ops - c0);
-        __syncthreads();  // previous chunk fully consumed
-        {
-            const uint4* src = reinterpret_cast<const uint4*>(ops + c0);
-            uint4* dst = reinterpret_cast<uint4*>(sops);
-            const int n16 = n * (int)(sizeof(DevOp) / 16);
-            for (int i = tid; i < n16; i += NTHREADS) dst[i] = src[i];
-        }
-        __syncthreads();
-        // stage the chunk's phase tables: the thread-index factors as they are, the byte tables
-        // reduced to one constant per CTA (they only see index bits outside the tile)
-        if ((pd.table_chunks >> (c0 / OPS_CHUNK)) & 1ull) {
-            for (int e = tid; e < n * TABLE_TILE_ENTRIES; e += NTHREADS) {
-                const int k = e / TABLE_TILE_ENTRIES, j = e % TABLE_TILE_ENTRIES;
-                const OpHdr h = load_hdr(sops[k]);
-                if (is_table_op(h.code) && (h.flags() & F_TABLE)) s_tl[k][j] = pd.tables[(size_t)h.tab * TABLE_UNIT + j];
-            }
-            if (tid < n) {
-                const OpHdr h = load_hdr(sops[tid]);
-                if (is_table_op(h.code) && (h.flags() & F_TABLE)) s_wc[tid] = table_cta_const(pd.tables, h.tab, h.regm(), gbase);
-            }
+    const int n_ops = pd.n_ops;
+    for (int k = 0; k < n_ops; ++k) {
+        const DevOp& op = pp.ops[k];
+        const int code = op.code;
+        if (code >= OC_SWITCH) {
+            const int from = (code - OC_SWITCH) / NGROUPS, to = (code - OC_SWITCH) % NGROUPS;
+            flush_phase(a, ctx);
+            __syncthreads();   // the previous transpose's loads are done everywhere
+            if (from == 0) switch_store<0>(tile, a, tid, op, gbase);
+            else if (from == 1) switch_store<1>(tile, a, tid, op, gbase);
+            else switch_store<2>(tile, a, tid, op, gbase);
             __syncthreads();
+            if (to == 0) stage_load<0>(tile, a, tid);
+            else if (to == 1) stage_load<1>(tile, a, tid);
+            else stage_load<2>(tile, a, tid);
+            ctx.pidx = thread_pidx(pd, gbase, to, tid);
+            continue;
         }
-        for (int k = 0; k < n; ++k) {
-            const DevOp& op = sops[k];
-            const OpHdr h = load_hdr(op);
-            const int code = h.code;
-            if (code >= OC_SWITCH) {
-                const int from = (code - OC_SWITCH) / NGROUPS, to = (code - OC_SWITCH) % NGROUPS;
-                flush_phase(a, ctx);
-                __syncthreads();   // the previous transpose's loads are done everywhere
-                if (h.flags() & F_PERM) {
-                    if (from == 0) stage_store_perm<0>(tile, a, tid, op, gbase);
-                    else if (from == 1) stage_store_perm<1>(tile, a, tid, op, gbase);
-                    else stage_store_perm<2>(tile, a, tid, op, gbase);
-                } else {
-                    if (from == 0) stage_store<0>(tile, a, tid);
-                    else if (from == 1) stage_store<1>(tile, a, tid);
-                    else stage_store<2>(tile, a, tid);
-                }
-                __syncthreads();
-                if (to == 0) stage_load<0>(tile, a, tid);
-                else if (to == 1) stage_load<1>(tile, a, tid);
-                else stage_load<2>(tile, a, tid);
-                ctx.pidx = thread_pidx(pd, gbase, to, tid);
-                continue;
-            }
-            apply_op(a, h, op, ctx, s_tl[k], &s_wc[k]);
-        }
+        apply_op(a, op, ctx, tables, n_tab, s_wc);
     }
     flush_phase(a, ctx);   // the planner always ends a pass in the IO layout
 
@@ -147,7 +142,7 @@ k_tile_pass(cplx* __restrict__ amp, const DevOp* __restrict__ ops, const __grid_
             uint64_t off = 0;
 #pragma unroll
             for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += io.hs[k];
-            io.p0[off] = a[j];
+            st_stream(io.p0 + off, a[j]);
         }
     }
 }
@@ -390,6 +385,40 @@ k_unpack_half(cplx* __restrict__ amp, int lq, int bitval, uint64_t first, uint64
         amp[half_index(first + e, lq, bitval)] = buf[e];
 }
 
+// Global<->local qubit swap straight over NVLink peer memory: ONE kernel reads this rank's leaving
+// half and the partner's leaving half (a peer pointer mapped with CUDA IPC) and writes each into the
+// other's place.  The same thread moves both elements of a pair, so nothing is staged and there is no
+// race; the two ranks of a pair each handle half of the elements, which loads both NVLink directions
+// equally (reads pull data towards this GPU, writes push it away).  Replaces
+// exchange_amplitudes_between_gpus (rust_communication.cu:106-141: four serial full-chunk copies).
+constexpr int SWAP_UNROLL = 4;
+__global__ void __launch_bounds__(256)
+k_swap_peer(cplx* __restrict__ mine, cplx* __restrict__ peer, int lq, int my_bit, uint64_t e_begin, uint64_t e_end) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t e = e_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // my leaving half: local bit lq == 1 - my_bit; the partner's leaving half: its bit lq == my_bit
+    for (; e + (SWAP_UNROLL - 1) * stride < e_end; e += SWAP_UNROLL * stride) {
+        double2 x[SWAP_UNROLL], y[SWAP_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SWAP_UNROLL; ++u) {
+            x[u] = *reinterpret_cast<const double2*>(mine + half_index(e + u * stride, lq, 1 - my_bit));
+            y[u] = *reinterpret_cast<const double2*>(peer + half_index(e + u * stride, lq, my_bit));
+        }
+#pragma unroll
+        for (int u = 0; u < SWAP_UNROLL; ++u) {
+            *reinterpret_cast<double2*>(mine + half_index(e + u * stride, lq, 1 - my_bit)) = y[u];
+            *reinterpret_cast<double2*>(peer + half_index(e + u * stride, lq, my_bit)) = x[u];
+        }
+    }
+    for (; e < e_end; e += stride) {
+        const uint64_t im = half_index(e, lq, 1 - my_bit), ip = half_index(e, lq, my_bit);
+        const double2 x = *reinterpret_cast<const double2*>(mine + im);
+        const double2 y = *reinterpret_cast<const double2*>(peer + ip);
+        *reinterpret_cast<double2*>(mine + im) = y;
+        *reinterpret_cast<double2*>(peer + ip) = x;
+    }
+}
+
 constexpr int DOT_CTAS = 148 * 4;
 __global__ void __launch_bounds__(256)
 k_dot_partial(const cplx* __restrict__ a, const cplx* __restrict__ b, uint64_t count, double* __restrict__ partial) {
@@ -440,9 +469,9 @@ cudaError_t kernels_init() {
                                 SAMPLE_WARPS * (2 << BLK_BITS) * (int)sizeof(double));
 }
 
-cudaError_t launch_tile_pass(cplx* amp, const DevOp* ops, const PassDesc& pd, cudaStream_t s) {
-    const uint64_t ctas = 1ull << (pd.n_local - TILE_BITS);
-    k_tile_pass<<<(unsigned)ctas, NTHREADS, TILE_SLOTS * sizeof(cplx), s>>>(amp, ops, pd);
+cudaError_t launch_tile_pass(cplx* amp, const PassParams& pp, cudaStream_t s) {
+    const uint64_t ctas = 1ull << (pp.pd.n_local - TILE_BITS);
+    k_tile_pass<<<(unsigned)ctas, NTHREADS, TILE_SLOTS * sizeof(cplx), s>>>(amp, pp);
     return cudaGetLastError();
 }
 
@@ -521,6 +550,12 @@ cudaError_t launch_pack_half(const cplx* amp, int lq, int bitval, uint64_t first
 cudaError_t launch_unpack_half(cplx* amp, int lq, int bitval, uint64_t first, uint64_t count, const cplx* buf, cudaStream_t s) {
     if (count == 0) return cudaSuccess;
     k_unpack_half<<<grid_for(count, 256, STREAM_CAP), 256, 0, s>>>(amp, lq, bitval, first, count, buf);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_swap_peer(cplx* mine, cplx* peer, int lq, int my_bit, uint64_t e_begin, uint64_t e_end, cudaStream_t s) {
+    if (e_end <= e_begin) return cudaSuccess;
+    k_swap_peer<<<grid_for(e_end - e_begin, 256 * SWAP_UNROLL, 148 * 16), 256, 0, s>>>(mine, peer, lq, my_bit, e_begin, e_end);
     return cudaGetLastError();
 }
 

@@ -11,8 +11,8 @@ constexpr int BLK_BITS = 10;  // sampler / reduction leaf block: 2^10 amplitudes
 
 cudaError_t kernels_init();   // one-time function attributes (dynamic shared memory opt-in)
 
-// Tiled multi-gate pass (n_local >= TILE_BITS).  ops is a device pointer to pd.n_ops DevOps.
-cudaError_t launch_tile_pass(cplx* amp, const DevOp* ops, const PassDesc& pd, cudaStream_t s);
+// Tiled multi-gate pass (n_local >= TILE_BITS).  pp (description + op list) travels as the kernel parameter.
+cudaError_t launch_tile_pass(cplx* amp, const PassParams& pp, cudaStream_t s);
 
 // One gate, one pass, any size (used when n_local < TILE_BITS, and as the un-fused debug path).
 struct SimpleOp { double m[8]; int32_t tbit; int32_t cbit; };   // cbit < 0: no control
@@ -49,6 +49,10 @@ cudaError_t launch_expectation_z(const cplx* amp, int n_local, int n_total, uint
 // `bitval`, elements [first, first+count) of that half, to / from a contiguous buffer.
 cudaError_t launch_pack_half(const cplx* amp, int lq, int bitval, uint64_t first, uint64_t count, cplx* buf, cudaStream_t s);
 cudaError_t launch_unpack_half(cplx* amp, int lq, int bitval, uint64_t first, uint64_t count, const cplx* buf, cudaStream_t s);
+
+// Direct NVLink swap: exchange elements [e_begin, e_end) of this rank's leaving half (bit lq == 1 - my_bit)
+// with the partner's leaving half (its bit lq == my_bit); `peer` is the partner's state mapped with CUDA IPC.
+cudaError_t launch_swap_peer(cplx* mine, cplx* peer, int lq, int my_bit, uint64_t e_begin, uint64_t e_end, cudaStream_t s);
 
 // <a|b> partial dot (conj(a).b), deterministic two-stage reduction; out[0]=re, out[1]=im
 cudaError_t launch_dot(const cplx* a, const cplx* b, uint64_t count, double* partial, double* out, cudaStream_t s);

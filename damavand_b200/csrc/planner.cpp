@@ -22,7 +22,7 @@ void classify_gate(const double m[8], int32_t* kind, int8_t* d0_is_one) {
     } else if (diag_zero) {
         *kind = (m[2] == 1.0 && m[3] == 0.0 && m[4] == 1.0 && m[5] == 0.0) ? K_SWAP : K_ANTIDIAG;
     } else if (all_real) {
-        *kind = K_REAL;
+        *kind = (m[0] == m[2] && m[0] == m[4] && m[0] == -m[6]) ? K_HADAMARD : K_REAL;
     } else if (m[1] == 0.0 && m[7] == 0.0 && m[2] == 0.0 && m[4] == 0.0) {
         *kind = K_RXLIKE;
     } else {
@@ -123,6 +123,20 @@ std::vector<HostGate> fuse_diagonal_runs(const std::vector<HostGate>& gates) {
     }
     end_run();
     return out;
+}
+
+void Pass::finish_tables() {
+    tables.clear();
+    if (tab_desc.empty()) return;
+    const size_t n_tab = tab_desc.size(), byte_base = n_tab + tab_tile.size();
+    tables.resize(byte_base + tab_bytes.size());
+    for (size_t i = 0; i < n_tab; ++i) {
+        TableDesc d = tab_desc[i];
+        d.byte_off += (uint32_t)byte_base;
+        std::memcpy(&tables[i], &d, sizeof d);
+    }
+    if (!tab_tile.empty()) std::memcpy(&tables[n_tab], tab_tile.data(), tab_tile.size() * sizeof(cplx));
+    if (!tab_bytes.empty()) std::memcpy(&tables[byte_base], tab_bytes.data(), tab_bytes.size() * sizeof(cplx));
 }
 
 namespace {
@@ -293,10 +307,13 @@ struct StageEmitter {
                 mask |= (uint8_t)(1u << (pr.first / 8));
             }
         }
-        op->tab = (int32_t)(pass.tables.size() / TABLE_UNIT);
-        op->regm = mask;
+        op->tab = (int32_t)pass.tab_desc.size();
         op->flags |= F_TABLE;
-        for (auto& e : tile_tab) pass.tables.push_back(to_cplx(e));
+        TableDesc d; std::memset(&d, 0, sizeof d);
+        d.byte_off = (uint32_t)pass.tab_bytes.size();    // relocated by finish_tables()
+        d.bytes = mask;
+        pass.tab_desc.push_back(d);
+        for (auto& e : tile_tab) pass.tab_tile.push_back(to_cplx(e));
         for (int by = 0; by < MAX_INDEX_BYTES; ++by) {
             if (!((mask >> by) & 1)) continue;
             std::vector<cl> e(TABLE_ENTRIES, cl(1, 0));
@@ -305,7 +322,7 @@ struct StageEmitter {
                 const int bit = 1 << (pr.first % 8);
                 for (int v = 0; v < TABLE_ENTRIES; ++v) if (v & bit) e[v] *= pr.second;
             }
-            for (int v = 0; v < TABLE_ENTRIES; ++v) pass.tables.push_back(to_cplx(e[v]));
+            for (int v = 0; v < TABLE_ENTRIES; ++v) pass.tab_bytes.push_back(to_cplx(e[v]));
         }
     }
     // Emit every accumulated term that involves qubit q, in the current stage's layout.
@@ -497,6 +514,10 @@ struct StageEmitter {
         if (kind == K_SWAP) kind = K_ANTIDIAG;   // only reached by X-like gates that could not join a permutation
         const int c = g.control();
         const int creg = c >= 0 ? reg_of(c) : -1;
+        if (kind == K_HADAMARD) {
+            if (c >= 0) kind = K_REAL;                   // the factor cannot leave a controlled gate
+            else acc.K *= cl((long double)g.m[0], 0);    // h [[1,1],[1,-1]]: the kernel adds / subtracts, h joins the pass constant
+        }
         if (creg >= 0) {
             op.code = OC_CGEN + treg; op.creg = (int8_t)creg;
         } else {
@@ -530,23 +551,49 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
     for (int i = 0; i < G; ++i) pending[i] = i;
     const int min_low = std::min(opt.min_low, TILE_BITS);
 
+    int gate_budget = opt.max_ops_per_pass;
     while (!pending.empty()) {
         // ---- pass level: grow the tile greedily, take everything that commutes to the front ----
-        uint64_t tile = (1ull << min_low) - 1;
-        int tile_n = min_low;
-        Blocked blk;
+        // Candidate c hands the free tile positions to the qubits in first-come order but refuses the
+        // first c newcomers: on layered circuits (entangler chains) that slides the window along the
+        // dependency front, and the candidate that takes the most gates wins.  c = 0 is plain first-come.
+        uint64_t tile = 0;
+        int tile_n = 0;
         std::vector<int> taken, rest;
         const int limit = std::min<int>((int)pending.size(), opt.window);
-        for (int k = 0; k < (int)pending.size(); ++k) {
-            const int gi = pending[k];
-            const HostGate& g = gates[gi];
-            bool ok = k < limit && (int)taken.size() < opt.max_ops_per_pass && blk.can_pass(g);
-            if (ok && !g.diag && !(tile & g.tmask)) {
-                if (tile_n < TILE_BITS) { tile |= g.tmask; ++tile_n; }
-                else ok = false;
+        auto select = [&](int refuse, uint64_t& tile_o, int& tile_n_o, std::vector<int>* taken_o, std::vector<int>* rest_o) {
+            uint64_t t = (1ull << min_low) - 1, refused = 0;
+            int tn = min_low, n_taken = 0, score = 0;
+            Blocked blk;
+            for (int k = 0; k < (int)pending.size(); ++k) {
+                const int gi = pending[k];
+                const HostGate& g = gates[gi];
+                bool ok = k < limit && n_taken < gate_budget && blk.can_pass(g);
+                if (ok && !g.diag && !(t & g.tmask)) {
+                    if (refused & g.tmask) ok = false;
+                    else if (refuse > 0) { refused |= g.tmask; --refuse; ok = false; }
+                    else if (tn < TILE_BITS) { t |= g.tmask; ++tn; }
+                    else ok = false;
+                }
+                if (ok) { ++n_taken; score += g.diag ? 1 : 2; if (taken_o) taken_o->push_back(gi); }
+                else {
+                    blk.skip(g);
+                    if (rest_o) rest_o->push_back(gi);
+                    else if (k >= limit || (tn == TILE_BITS && (blk.x & t) == t)) break;   // scoring only: nothing more can be taken
+                }
             }
-            if (ok) taken.push_back(gi);
-            else { blk.skip(g); rest.push_back(gi); }
+            tile_o = t; tile_n_o = tn;
+            return score;
+        };
+        {
+            int best = 0, best_score = -1;
+            for (int c = 0; c < std::max(1, opt.candidates); ++c) {
+                uint64_t t; int tn;
+                const int sc = select(c, t, tn, nullptr, nullptr);
+                if (sc > best_score) { best_score = sc; best = c; }
+                if (tn < TILE_BITS) break;      // the circuit ran out of new qubits: later candidates only refuse more
+            }
+            select(best, tile, tile_n, &taken, &rest);
         }
         if (taken.empty()) throw std::runtime_error("plan_local: no progress");
         // pad the tile with the lowest unused local qubits (keeps segments long)
@@ -620,9 +667,15 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
         em.flush_all();
         em.emit_switch(IO_GROUP);
         pass.desc.n_ops = (int)pass.ops.size();
-        if (pass.desc.n_ops > MAX_OPS_PER_PASS) throw std::runtime_error("plan_local: too many ops in one pass");
-        for (size_t k = 0; k < pass.ops.size(); ++k)
-            if (is_table_op(pass.ops[k].code) && (pass.ops[k].flags & F_TABLE)) pass.desc.table_chunks |= 1ull << (k / OPS_CHUNK);
+        pass.desc.n_tab = (int)pass.tab_desc.size();
+        if (pass.desc.n_ops > MAX_OPS_PER_PASS || pass.desc.n_tab > MAX_TABLE_OPS) {
+            // the op list is a kernel parameter of bounded size: take fewer gates and plan this pass again
+            if (taken.size() <= 1) throw std::runtime_error("plan_local: one gate does not fit a pass");
+            gate_budget = (int)taken.size() / 2;
+            continue;
+        }
+        gate_budget = opt.max_ops_per_pass;
+        pass.finish_tables();
         passes.push_back(std::move(pass));
         pending.swap(rest);
     }
@@ -659,25 +712,60 @@ std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n
         return r;
     };
 
-    for (int i = 0; i < G; ++i) {
-        const HostGate& g = gates[i];
-        if (!g.diag && perm[g.target()] >= n_local) {
-            // evict the local qubit whose next non-diagonal use is farthest away (Belady)
-            std::vector<int> next_use(n_total, G + 1);
-            for (int k = G - 1; k > i; --k)
-                if (!gates[k].diag) next_use[gates[k].target()] = k;
-            int victim = -1, best = -1;
-            for (int p = n_local - 1; p >= 0; --p) {   // ties: prefer high local positions
-                const int lq = inv[p];
-                if (lq == g.control()) continue;        // keep this gate's control local
-                if (next_use[lq] > best) { best = next_use[lq]; victim = p; }
+    // List scheduling over LOGICAL qubits: run everything that is executable with the current layout
+    // and commutes past what had to wait (same rule as the pass level), and only then pay for swaps.
+    // On layered circuits this executes a whole light cone per layout instead of one layer.
+    std::vector<int> pending(G);
+    for (int i = 0; i < G; ++i) pending[i] = i;
+    const int first_victim = n_local > 8 ? 5 : 0;    // keep swap segments >= 512 B when there is a choice
+    while (!pending.empty()) {
+        {
+            Blocked blk;
+            std::vector<int> rest;
+            for (int gi : pending) {
+                const HostGate& g = gates[gi];
+                const bool local = g.diag || perm[g.target()] < n_local;
+                if (local && blk.can_pass(g)) {
+                    HostGate pg = g;
+                    pg.tmask = map_mask(g.tmask);
+                    pg.cmask = map_mask(g.cmask);
+                    local_step().gates.push_back(pg);
+                } else {
+                    blk.skip(g);
+                    rest.push_back(gi);
+                }
             }
-            emit_swap(perm[g.target()], victim);
+            pending.swap(rest);
         }
-        HostGate pg = g;
-        pg.tmask = map_mask(g.tmask);
-        pg.cmask = map_mask(g.cmask);
-        local_step().gates.push_back(pg);
+        if (pending.empty()) break;
+        // the gates that wait for nothing but a rank-index target: bring those qubits in
+        std::vector<int> want;
+        {
+            Blocked blk;
+            for (int gi : pending) {
+                const HostGate& g = gates[gi];
+                if (!g.diag && perm[g.target()] >= n_local && blk.can_pass(g) &&
+                    std::find(want.begin(), want.end(), g.target()) == want.end() && (int)want.size() < n_total - n_local)
+                    want.push_back(g.target());
+                blk.skip(g);
+            }
+        }
+        if (want.empty()) throw std::runtime_error("plan_distributed: no progress");
+        // evict the local qubits whose next non-diagonal use is farthest away (Belady)
+        std::vector<int> next_use(n_total, G + 1);
+        for (int k = (int)pending.size() - 1; k >= 0; --k)
+            if (!gates[pending[k]].diag) next_use[gates[pending[k]].target()] = k;
+        for (int lqbit : want) {
+            int victim = -1, best = -1;
+            for (int pass = 0; pass < 2 && victim < 0; ++pass)
+                for (int p = n_local - 1; p >= (pass == 0 ? first_victim : 0); --p) {   // ties: prefer high local positions
+                    const int lq = inv[p];
+                    if (std::find(want.begin(), want.end(), lq) != want.end()) continue;
+                    if (next_use[lq] > best) { best = next_use[lq]; victim = p; }
+                }
+            emit_swap(perm[lqbit], victim);
+            next_use[lqbit] = -1;    // just swapped in: not a victim for the rest of this round
+        }
     }
 
     if (restore_identity) {

@@ -38,14 +38,19 @@ HostGate make_gate(int target, int control, const double m[8], int gate_idx);
 struct Pass {
     PassDesc desc;
     std::vector<DevOp> ops;
-    std::vector<cplx> tables;  // phase sub-tables (TABLE_ENTRIES each) referenced by ops[].tab
+    std::vector<cplx> tables;  // the pass's table buffer (layout in tile_core.cuh), built by finish_tables()
+    std::vector<TableDesc> tab_desc;   // one record per table op, in op order (ops[].tab indexes it)
+    std::vector<cplx> tab_tile;        // TABLE_TILE_ENTRIES thread-index factors per table op
+    std::vector<cplx> tab_bytes;       // byte sub-tables (TABLE_ENTRIES each)
+    void finish_tables();              // concatenate [desc][tile][bytes] into `tables`
     int n_switches = 0;        // stage switches inside the pass (shared-memory transposes)
 };
 
 struct PlanOptions {
     int min_low = 3;           // tile always contains physical qubits [0, min_low): 128 B segments
     int window = 16384;        // look-ahead (gates) when filling a pass
-    int max_ops_per_pass = 1024;   // gates taken into one pass (the op stream is capped at MAX_OPS_PER_PASS)
+    int candidates = 12;       // tile candidates scored per pass (1 = first-come only)
+    int max_ops_per_pass = 1024;   // gates taken into one pass (halved and retried while the op stream exceeds MAX_OPS_PER_PASS)
 };
 
 // Classify a 2x2 by exact zero / one tests on its entries.

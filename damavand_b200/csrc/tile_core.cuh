@@ -47,23 +47,24 @@ enum OpKind : int32_t {
     K_REAL = 1,      // all four entries real (H, RY)
     K_RXLIKE = 2,    // real diagonal, purely imaginary off-diagonal (RX)
     K_ANTIDIAG = 3,  // m00 = m11 = 0 (Y)
-    K_SWAP = 4,      // m01 = m10 = 1, m00 = m11 = 0 (X, CNOT): pure exchange
-    K_DIAG = 5,      // m01 = m10 = 0 (RZ, Z, S, T, fused parity phases)
+    K_HADAMARD = 4,  // h * [[1, 1], [1, -1]], uncontrolled: add / subtract only, h joins the pass constant
+    K_SWAP = 5,      // m01 = m10 = 1, m00 = m11 = 0 (X, CNOT): pure exchange
+    K_DIAG = 6,      // m01 = m10 = 0 (RZ, Z, S, T, fused parity phases)
 };
 
 // Device instruction set.
 enum OpCode : int32_t {
-    OC_GATE = 0,        // + kind*4 + treg (kind 0..3): 2x2 on register bit treg; control none / thread-level
-    OC_CGEN = 16,       // + treg: general 2x2 on treg, control = register bit op.creg (rare)
-    OC_DIAG1 = 20,      // + r: registers with bit r set *= d1, the others *= d0 (unless d0 == 1)
-    OC_PHASE = 24,      // thread-level parity phase -> lazy per-thread scalar
-    OC_DIAGGEN = 25,    // generic parity phase with register bits in its masks (fallback)
-    OC_TABLE = 26,      // product of phase-table lookups -> lazy scalar (optional thread-level pivot)
-    OC_TABLE_REG = 27,  // + r: (table lookups | constant) x factors of the other register bits -> registers with bit r
-    OC_PAIR = 31,       // + pair id: registers with both bits set *= (m[0], m[1])
-    OC_SWITCH = 37,     // + from*3 + to: transpose through shared memory, optionally with a GF(2)-affine
+    OC_GATE = 0,        // + kind*4 + treg (kind 0..4): 2x2 on register bit treg; control none / thread-level
+    OC_CGEN = 20,       // + treg: general 2x2 on treg, control = register bit op.creg (rare)
+    OC_DIAG1 = 24,      // + r: registers with bit r set *= d1, the others *= d0 (unless d0 == 1)
+    OC_PHASE = 28,      // thread-level parity phase -> lazy per-thread scalar
+    OC_DIAGGEN = 29,    // generic parity phase with register bits in its masks (fallback)
+    OC_TABLE = 30,      // product of phase-table lookups -> lazy scalar (optional thread-level pivot)
+    OC_TABLE_REG = 31,  // + r: (table lookups | constant) x factors of the other register bits -> registers with bit r
+    OC_PAIR = 35,       // + pair id: registers with both bits set *= (m[0], m[1])
+    OC_SWITCH = 41,     // + from*3 + to: transpose through shared memory, optionally with a GF(2)-affine
                         //   permutation of the tile index (all pending X / CNOT gates)
-    OC_COUNT = 46,
+    OC_COUNT = 50,
 };
 DVD_HD int pair_id(int r0, int r1) {   // r0 < r1
     return r0 == 0 ? r1 - 1 : r0 == 1 ? r1 + 1 : 5;
@@ -79,37 +80,38 @@ enum OpFlags : uint8_t {
 };
 
 // One operation as the device sees it, fully decoded by the planner for the stage it runs in.
+// The ops of a pass travel as a kernel PARAMETER (PassParams, constant bank): every warp reads the
+// same op at the same time, so operands come through the constant cache / uniform datapath and
+// never touch shared memory or its instruction queue.
 struct alignas(16) DevOp {
     double m[8];       // m00.re m00.im m01.re m01.im m10.re m10.im m11.re m11.im  (or a PermPayload)
     uint64_t tmask;    // thread-level part of the target parity mask (diagonal ops, table pivot)
     uint64_t cmask;    // thread-level part of the control parity mask (0 = none)
     int32_t code;      // OpCode (+ operands)
-    int32_t tab;       // table ops: start of the op's table block, in units of 16 entries (see TableBlock)
+    int32_t tab;       // table ops: index of the op's table record in the pass (see TableDesc)
     int32_t gate_idx;  // caller's gate index (-1 for fused / layout ops)
     int8_t group;      // register group the op runs in (OC_SWITCH: the group it switches to)
     int8_t creg;       // OC_CGEN: control register bit
-    uint8_t regm;      // OC_DIAGGEN: tregm | cregm << 4;  table ops: bytes of the CTA base index with a sub-table
+    uint8_t regm;      // OC_DIAGGEN: tregm | cregm << 4
     uint8_t flags;     // OpFlags
 };
 static_assert(sizeof(DevOp) == 96, "DevOp layout");
 
-// The 16 header bytes of a DevOp, fetched with one 128-bit shared-memory load.
-struct alignas(16) OpHdr {
-    int32_t code, tab, gate_idx;
-    uint32_t packed;   // group | creg << 8 | regm << 16 | flags << 24
-    DVD_HD unsigned flags() const { return packed >> 24; }
-    DVD_HD unsigned regm() const { return (packed >> 16) & 255u; }
-    DVD_HD int creg() const { return (int)(int8_t)((packed >> 8) & 255u); }
-};
-DVD_HD OpHdr load_hdr(const DevOp& op) { return *reinterpret_cast<const OpHdr*>(&op.code); }
-
-// Phase table block of one table op (all entries complex128):
-//   [16: factor by thread-index bits 0..3][16: by thread-index bits 4..7][256 per set bit of regm: by
-//   byte b of the CTA's physical base index].  The first two depend only on the thread's position in
-//   the tile and are staged in shared memory with the op; the byte tables are looked up ONCE per CTA
-//   (they only see bits outside the tile) and staged as a single constant.
+// Phase tables of a pass (all entries complex128), one buffer per pass:
+//   [n_tab TableDesc records, 16 B each]
+//   [n_tab x TABLE_TILE_ENTRIES: factor by thread-index bits 0..3 (16 entries) and 4..7 (16 entries)]
+//   [byte tables: 256 entries per set bit of TableDesc::bytes, indexed by byte b of the CTA's physical base]
+// The thread-index factors depend only on the thread's position in the tile (read through L1, the
+// same 512 B for every CTA); the byte tables only see index bits outside the tile, so they are
+// reduced to ONE constant per CTA and table op in the kernel prologue.
 constexpr int TABLE_TILE_ENTRIES = 32;
-constexpr int TABLE_UNIT = 16;
+constexpr int MAX_TABLE_OPS = 128;         // per pass (shared-memory array of per-CTA constants)
+struct alignas(16) TableDesc {
+    uint32_t byte_off;   // start of the op's byte tables, in cplx entries from the start of the buffer
+    uint32_t bytes;      // bit b: byte b of the physical index has a sub-table
+    uint32_t pad[2];
+};
+static_assert(sizeof(TableDesc) == sizeof(cplx), "TableDesc is one table slot");
 
 // Payload of a permuting OC_SWITCH, stored over DevOp::m.  The amplitude at tile index i moves to
 //   i' = xor_{p : bit p of i} col[p]  ^  v0  ^  xor_k [parity(physical base & cond_mask_k)] cond_vec[k]
@@ -135,10 +137,16 @@ struct PassDesc {
     int32_t sorted_q[TILE_BITS];  // the same qubits in ascending order
     uint64_t rank_bits;           // this rank's value of the global (rank-index) qubits, in place
     const cplx* tables;           // phase tables of this pass (device pointer; host pointer in the replay)
-    uint64_t table_chunks;        // bit c: ops [32c, 32c+32) contain a table op (its tables get staged)
+    int32_t n_tab;                // table ops in this pass (<= MAX_TABLE_OPS)
+    int32_t stagger;              // cycles the second CTA of each SM waits in the first wave (0 = off), see k_tile_pass
 };
-constexpr int OPS_CHUNK = 32;
-constexpr int MAX_OPS_PER_PASS = 64 * OPS_CHUNK;
+// Kernel parameter block: the pass description and its whole op list (<= 32764 B of parameters).
+constexpr int MAX_OPS_PER_PASS = 336;
+struct PassParams {
+    PassDesc pd;
+    DevOp ops[MAX_OPS_PER_PASS];
+};
+static_assert(sizeof(PassParams) + 16 <= 32764, "kernel parameter space");
 
 // ---- index helpers ---------------------------------------------------------------------------
 // Tile index of register j of thread tid when group g's tile positions live in registers.
@@ -210,7 +218,10 @@ DVD_HD void flush_phase(cplx (&a)[NREG], ThreadCtx& ctx) {
 template <int KIND>
 DVD_HD void pair_update(cplx& a0, cplx& a1, const double (&m)[8]) {
     const cplx x = a0, y = a1;
-    if (KIND == K_GENERAL) {
+    if (KIND == K_HADAMARD) {        // the common factor h is folded into the pass constant by the planner
+        a0 = cplx{x.x + y.x, x.y + y.y};
+        a1 = cplx{x.x - y.x, x.y - y.y};
+    } else if (KIND == K_GENERAL) {
         a0 = cplx{x.x * m[0] - x.y * m[1] + y.x * m[2] - y.y * m[3], x.x * m[1] + x.y * m[0] + y.x * m[3] + y.y * m[2]};
         a1 = cplx{x.x * m[4] - x.y * m[5] + y.x * m[6] - y.y * m[7], x.x * m[5] + x.y * m[4] + y.x * m[7] + y.y * m[6]};
     } else if (KIND == K_REAL) {
@@ -232,7 +243,7 @@ template <int B, int KIND>
 DVD_HD void gate_all(cplx (&a)[NREG], const double* mp) {
     double m[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) m[k] = mp[k];
+    for (int k = 0; k < 8; ++k) m[k] = KIND == K_HADAMARD ? 0.0 : mp[k];
 #pragma unroll
     for (int k = 0; k < NREG / 2; ++k) {
         const int j0 = ((k >> B) << (B + 1)) | (k & ((1 << B) - 1));
@@ -268,14 +279,15 @@ DVD_HD void scale_pair(cplx (&a)[NREG], double wr, double wi) {
     for (int j = 0; j < NREG; ++j) if (((j >> B0) & 1) && ((j >> B1) & 1)) a[j] = cmul(a[j], wr, wi);
 }
 
-// CTA-constant part of a table op: product of the byte sub-tables at the CTA's physical base index.
-DVD_HD cplx table_cta_const(const cplx* __restrict__ tables, int tab, unsigned bytes, uint64_t gbase) {
+// CTA-constant part of table op `ti`: product of its byte sub-tables at the CTA's physical base index.
+DVD_HD cplx table_cta_const(const cplx* __restrict__ tables, int ti, uint64_t gbase) {
+    const TableDesc d = reinterpret_cast<const TableDesc*>(tables)[ti];
     cplx w{1.0, 0.0};
     bool first = true;
-    const cplx* t = tables + (size_t)tab * TABLE_UNIT + TABLE_TILE_ENTRIES;
+    const cplx* t = tables + d.byte_off;
 #pragma unroll
     for (int b = 0; b < MAX_INDEX_BYTES; ++b) {
-        if ((bytes >> b) & 1u) {
+        if ((d.bytes >> b) & 1u) {
             const cplx e = t[(unsigned)(gbase >> (8 * b)) & 255u];
             w = first ? e : cmul(w, e.x, e.y);
             first = false;
@@ -284,16 +296,25 @@ DVD_HD cplx table_cta_const(const cplx* __restrict__ tables, int tab, unsigned b
     }
     return w;
 }
+// Thread-index factors of table op `ti` inside a pass with n_tab table ops.
+DVD_HD const cplx* table_tile(const cplx* tables, int n_tab, int ti) {
+    return tables + n_tab + (size_t)ti * TABLE_TILE_ENTRIES;
+}
 // Full table value of a thread: CTA constant x the two thread-index factors.
-DVD_HD cplx table_value(const cplx* tl, const cplx* wc, int tid) {
+DVD_HD cplx table_value(const cplx* tl, cplx wc, int tid) {
+#ifdef __CUDA_ARCH__
+    const double2 lo = __ldg(reinterpret_cast<const double2*>(tl) + (tid & 15));
+    const double2 hi = __ldg(reinterpret_cast<const double2*>(tl) + 16 + (tid >> 4));
+#else
     const cplx lo = tl[tid & 15], hi = tl[16 + (tid >> 4)];
-    return cmul(cmul(*wc, lo.x, lo.y), hi.x, hi.y);
+#endif
+    return cmul(cmul(wc, lo.x, lo.y), hi.x, hi.y);
 }
 
 // Registers with bit B set *= W * prod_k f_k^{bit o_k of j}: W from the table (or the constant
 // m[6..7] when the op has none), f_k = m[2k..2k+1] for the other three register bits o_0<o_1<o_2.
 template <int B>
-DVD_HD void table_reg(cplx (&a)[NREG], const DevOp& op, unsigned flags, const ThreadCtx& ctx, const cplx* tl, const cplx* wc) {
+DVD_HD void table_reg(cplx (&a)[NREG], const DevOp& op, unsigned flags, const ThreadCtx& ctx, const cplx* tl, cplx wc) {
     constexpr int O0 = B == 0 ? 1 : 0, O1 = B <= 1 ? 2 : 1, O2 = B <= 2 ? 3 : 2;
     const unsigned pm = (flags >> F_PM_SHIFT) & 7u;
     const cplx w = (flags & F_TABLE) ? table_value(tl, wc, ctx.tid) : cplx{op.m[6], op.m[7]};
@@ -348,10 +369,10 @@ DVD_HD unsigned perm_index(const DevOp& op, unsigned v, unsigned idx) {
     case (base) + 3: { constexpr int B = 3; STMT; } break;
 
 // Apply one op (anything but OC_SWITCH) to the 16 register-resident amplitudes of a thread.
-// h: the op's header (already fetched); tl / wc: the op's staged table entries and CTA constant.
-DVD_HD void apply_op(cplx (&a)[NREG], const OpHdr& h, const DevOp& op, ThreadCtx& ctx, const cplx* tl, const cplx* wc) {
-    const int code = h.code;
-    const unsigned flags = h.flags();
+// tables / n_tab: the pass's table buffer; wcs: per-CTA constants of its table ops (kernel prologue).
+DVD_HD void apply_op(cplx (&a)[NREG], const DevOp& op, ThreadCtx& ctx, const cplx* tables, int n_tab, const cplx* wcs) {
+    const int code = op.code;
+    const unsigned flags = op.flags;
     if ((flags & F_TCTRL) && !parity64(ctx.pidx & op.cmask)) return;   // thread-level control
     const double* m = op.m;
     switch (code) {
@@ -359,7 +380,8 @@ DVD_HD void apply_op(cplx (&a)[NREG], const OpHdr& h, const DevOp& op, ThreadCtx
         DVD_CASE4(OC_GATE + 4 * K_REAL, (gate_all<B, K_REAL>(a, m)))
         DVD_CASE4(OC_GATE + 4 * K_RXLIKE, (gate_all<B, K_RXLIKE>(a, m)))
         DVD_CASE4(OC_GATE + 4 * K_ANTIDIAG, (gate_all<B, K_ANTIDIAG>(a, m)))
-        DVD_CASE4(OC_CGEN, (cgen<B>(a, m, h.creg())))
+        DVD_CASE4(OC_GATE + 4 * K_HADAMARD, (gate_all<B, K_HADAMARD>(a, m)))
+        DVD_CASE4(OC_CGEN, (cgen<B>(a, m, op.creg)))
         DVD_CASE4(OC_DIAG1, (diag_regbit<B>(a, m, (flags & F_D0_ONE) != 0)))
         case OC_PHASE: {
             const bool tpar = parity64(ctx.pidx & op.tmask) != 0;
@@ -369,7 +391,7 @@ DVD_HD void apply_op(cplx (&a)[NREG], const OpHdr& h, const DevOp& op, ThreadCtx
             }
         } break;
         case OC_DIAGGEN: {   // control handled here: thread-level and register-level parts combine
-            const int tregm = h.regm() & 15, cregm = h.regm() >> 4;
+            const int tregm = op.regm & 15, cregm = op.regm >> 4;
             const bool has_ctrl = (flags & F_HAS_CTRL) != 0;
             const bool cpar = op.cmask != 0 && parity64(ctx.pidx & op.cmask) != 0;
             const bool tpar = parity64(ctx.pidx & op.tmask) != 0;
@@ -383,12 +405,13 @@ DVD_HD void apply_op(cplx (&a)[NREG], const OpHdr& h, const DevOp& op, ThreadCtx
         } break;
         case OC_TABLE: {
             if (op.tmask == 0 || parity64(ctx.pidx & op.tmask)) {
-                const cplx w = table_value(tl, wc, ctx.tid);
+                const cplx w = table_value(table_tile(tables, n_tab, op.tab), wcs[op.tab], ctx.tid);
                 ctx.ph = cmul(ctx.ph, w.x, w.y);
                 ctx.ph_dirty = true;
             }
         } break;
-        DVD_CASE4(OC_TABLE_REG, (table_reg<B>(a, op, flags, ctx, tl, wc)))
+        DVD_CASE4(OC_TABLE_REG, (table_reg<B>(a, op, flags, ctx, (flags & F_TABLE) ? table_tile(tables, n_tab, op.tab) : tables,
+                                              (flags & F_TABLE) ? wcs[op.tab] : cplx{1.0, 0.0})))
         case OC_PAIR + 0: scale_pair<0, 1>(a, m[0], m[1]); break;
         case OC_PAIR + 1: scale_pair<0, 2>(a, m[0], m[1]); break;
         case OC_PAIR + 2: scale_pair<0, 3>(a, m[0], m[1]); break;

@@ -27,6 +27,10 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
     for (uint64_t cta = 0; cta < ctas; ++cta) {
         const uint64_t base = cta_base(pd, cta);
         const uint64_t gbase = base | pd.rank_bits;
+        if (pd.n_tab > MAX_TABLE_OPS || pd.n_ops > MAX_OPS_PER_PASS || (size_t)pd.n_ops != pass.ops.size())
+            throw std::runtime_error("emu: pass exceeds the kernel parameter limits");
+        std::vector<cplx> wcs(pd.n_tab > 0 ? pd.n_tab : 1);     // kernel prologue: per-CTA table constants
+        for (int ti = 0; ti < pd.n_tab; ++ti) wcs[ti] = table_cta_const(pd.tables, ti, gbase);
         for (int tid = 0; tid < NTHREADS; ++tid) {
             for (int j = 0; j < NREG; ++j) regs[tid][j] = amp[base + tile_offset(pd, stage_idx(IO_GROUP, tid, j))];
             ctx[tid].pidx = gbase | tile_offset(pd, stage_idx(IO_GROUP, tid, 0));
@@ -60,14 +64,8 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
                 continue;
             }
             if (op.group != cur) throw std::runtime_error("emu: op not in its register group");
-            const OpHdr h = load_hdr(op);
-            cplx wc{1.0, 0.0};
-            const cplx* tl = nullptr;
-            if (is_table_op(h.code) && (h.flags() & F_TABLE)) {
-                tl = pd.tables + (size_t)h.tab * TABLE_UNIT;
-                wc = table_cta_const(pd.tables, h.tab, h.regm(), gbase);
-            }
-            for (int tid = 0; tid < NTHREADS; ++tid) apply_op(regs[tid], h, op, ctx[tid], tl, &wc);
+            if (is_table_op(op.code) && (op.flags & F_TABLE) && (op.tab < 0 || op.tab >= pd.n_tab)) throw std::runtime_error("emu: bad table index");
+            for (int tid = 0; tid < NTHREADS; ++tid) apply_op(regs[tid], op, ctx[tid], pd.tables, pd.n_tab, wcs.data());
         }
         for (int tid = 0; tid < NTHREADS; ++tid) flush_phase(regs[tid], ctx[tid]);
         if (cur != IO_GROUP) throw std::runtime_error("emu: pass does not end in the IO layout");
