@@ -49,7 +49,53 @@ HostGate make_gate(int target, int control, const double m[8], int gate_idx) {
 // parity(x & rows[control])).  Whenever A is back to the identity the run so far equals the product
 // of the collected parity phases -- all diagonal, all commuting, no amplitude moves.
 // ---------------------------------------------------------------------------------------------------
-std::vector<HostGate> fuse_diagonal_runs(const std::vector<HostGate>& gates) {
+// Level 0a: runs of uncontrolled single-qubit gates on one qubit (H RX RY RZ ...) collapse into one 2x2.
+// A run is deferred while the gates in between do not touch its qubit (they commute with it) and is
+// emitted just before the first gate that does.  Runs with at most one non-diagonal gate stay as they
+// are: their diagonal gates are free in the phase polynomial (or fold into the gate as K_REALPH).
+std::vector<HostGate> merge_single_qubit_runs(const std::vector<HostGate>& gates) {
+    using cld = std::complex<long double>;
+    std::vector<HostGate> out;
+    out.reserve(gates.size());
+    std::vector<std::vector<HostGate>> open(64);
+    auto close = [&](int q) {
+        std::vector<HostGate>& run = open[q];
+        if (run.empty()) return;
+        int n_nondiag = 0;
+        for (const HostGate& g : run) n_nondiag += g.diag ? 0 : 1;
+        // one non-diagonal gate: the diagonal gates around it are free or nearly so in the phase polynomial
+        // (folded into the gate as K_REALPH, or into a twiddle that is emitted anyway)
+        const bool keep = run.size() == 1 || n_nondiag <= 1;
+        if (keep) {
+            for (const HostGate& g : run) out.push_back(g);
+        } else {
+            cld m[4] = {cld(1, 0), cld(0, 0), cld(0, 0), cld(1, 0)};
+            for (const HostGate& g : run) {          // later gates multiply from the left
+                cld a[4];
+                for (int k = 0; k < 4; ++k) a[k] = cld((long double)g.m[2 * k], (long double)g.m[2 * k + 1]);
+                const cld r[4] = {a[0] * m[0] + a[1] * m[2], a[0] * m[1] + a[1] * m[3],
+                                  a[2] * m[0] + a[3] * m[2], a[2] * m[1] + a[3] * m[3]};
+                for (int k = 0; k < 4; ++k) m[k] = r[k];
+            }
+            double md[8];
+            for (int k = 0; k < 4; ++k) { md[2 * k] = (double)m[k].real(); md[2 * k + 1] = (double)m[k].imag(); }
+            out.push_back(make_gate(q, -1, md, -1));
+        }
+        run.clear();
+    };
+    for (const HostGate& g : gates) {
+        const bool single = g.cmask == 0 && g.tmask != 0 && (g.tmask & (g.tmask - 1)) == 0;
+        if (single) { open[g.target()].push_back(g); continue; }
+        uint64_t touched = g.tmask | g.cmask;
+        while (touched) { const int q = __builtin_ctzll(touched); touched &= touched - 1; close(q); }
+        out.push_back(g);
+    }
+    for (int q = 0; q < 64; ++q) close(q);
+    return out;
+}
+
+std::vector<HostGate> fuse_diagonal_runs(const std::vector<HostGate>& gates_in) {
+    const std::vector<HostGate> gates = merge_single_qubit_runs(gates_in);
     std::vector<HostGate> out;
     out.reserve(gates.size());
     uint64_t rows[64];
@@ -246,6 +292,22 @@ struct StageEmitter {
     int regq[REG_BITS];
     uint64_t regphys = 0;
     PermAcc perm;
+    // last_real[q]: index in pass.ops of the latest uncontrolled real 2x2 (K_REAL / K_REALPH) on qubit q with
+    // nothing non-diagonal on q since: a lone phase on q (RY then RZ) is folded into that op for free
+    int last_real[64];
+    void reset_last() { for (int q = 0; q < 64; ++q) last_real[q] = -1; }
+    bool fold_into_last(int q, const cl& A) {
+        const int k = last_real[q];
+        if (k < 0) return false;
+        DevOp& p = pass.ops[k];
+        const int treg = (p.code - OC_GATE) % 4;
+        cl w(1, 0);
+        if ((p.code - OC_GATE) / 4 == K_REALPH) w = cl((long double)p.m[1], (long double)p.m[3]);
+        w *= A;
+        p.code = OC_GATE + 4 * K_REALPH + treg;
+        p.m[1] = (double)w.real(); p.m[3] = (double)w.imag();
+        return true;
+    }
 
     void set_stage(int g) {
         group = g; regphys = 0;
@@ -326,7 +388,7 @@ struct StageEmitter {
         }
     }
     // Emit every accumulated term that involves qubit q, in the current stage's layout.
-    void flush_qubit(int q, cl* fold_K = nullptr) {
+    void flush_qubit(int q) {
         const int r = reg_of(q);
         cl A(1, 0);
         { auto it = acc.a.find(q); if (it != acc.a.end()) { A = it->second; acc.a.erase(it); } }
@@ -340,6 +402,10 @@ struct StageEmitter {
                 if (rc >= 0) rpart.push_back({rc, it->second}); else tpart.push_back({c, it->second});
             }
             it = acc.b.erase(it);
+        }
+        if (tpart.empty() && rpart.empty()) {
+            if (is_one(A)) return;
+            if (fold_into_last(q, A)) return;
         }
         if (r < 0) {
             // q is thread-level: its own factor and its thread-level partners form a pivot table;
@@ -372,11 +438,9 @@ struct StageEmitter {
             if (is_one(A)) return;
             DevOp op = blank(-1);
             op.code = OC_DIAG1 + r;
-            cl d0(1, 0);
-            if (fold_K && !is_one(*fold_K)) { d0 = *fold_K; *fold_K = cl(1, 0); }   // the pass constant rides along
-            else op.flags = F_D0_ONE;
-            const cplx f0 = to_cplx(d0), f1 = to_cplx(d0 * A);
-            op.m[0] = f0.x; op.m[1] = f0.y; op.m[6] = f1.x; op.m[7] = f1.y;
+            op.flags = F_D0_ONE;
+            const cplx f1 = to_cplx(A);
+            op.m[0] = 1.0; op.m[6] = f1.x; op.m[7] = f1.y;
             pass.ops.push_back(op);
             return;
         }
@@ -402,14 +466,18 @@ struct StageEmitter {
         }
         pass.ops.push_back(op);
     }
-    // End of the pass: everything that is left.
+    // End of a pass that is not the last: lone single-qubit phases that fold into a gate of this pass for free.
+    void fold_free_phases() {
+        for (auto it = acc.a.begin(); it != acc.a.end();) {
+            const int q = it->first;
+            bool lone = last_real[q] >= 0 && !is_one(it->second);
+            for (auto& kv : acc.b) if (lone && (kv.first.first == q || kv.first.second == q) && !is_one(kv.second)) lone = false;
+            if (lone && fold_into_last(q, it->second)) it = acc.a.erase(it); else ++it;
+        }
+    }
+    // End of the gate list: everything that is left.
     void flush_all() {
-        // if nothing thread-level is left, the constant K can ride on a register-bit op for free
-        bool thread_terms = false;
-        for (auto& kv : acc.a) if (reg_of(kv.first) < 0 && !is_one(kv.second)) thread_terms = true;
-        for (auto& kv : acc.b)
-            if (reg_of(kv.first.first) < 0 && reg_of(kv.first.second) < 0 && !is_one(kv.second)) thread_terms = true;
-        for (int k = 0; k < REG_BITS; ++k) flush_qubit(regq[k], thread_terms ? nullptr : &acc.K);
+        for (int k = 0; k < REG_BITS; ++k) flush_qubit(regq[k]);
         // only thread-level qubits remain
         std::vector<std::pair<int, cl>> ones;
         for (auto& kv : acc.a) if (!is_one(kv.second)) ones.push_back({kv.first, kv.second});
@@ -479,6 +547,7 @@ struct StageEmitter {
     void emit_perm(const HostGate& g) {
         const int t = g.target();
         flush_qubit(t);              // phases on t do not commute with a flip of t
+        last_real[t] = -1;
         const int c = g.control();
         if (c < 0) perm.add_x(pos_of[t]);
         else if (pos_of[c] >= 0) perm.add_cnot(pos_of[c], pos_of[t]);
@@ -506,17 +575,26 @@ struct StageEmitter {
         const int t = g.target();
         const int treg = reg_of(t);
         if (treg < 0) throw std::runtime_error("plan_local: gate outside its register group");
+        const size_t n_before = pass.ops.size();
         flush_qubit(t);
         DevOp op = blank(g.gate_idx);
         std::memcpy(op.m, g.m, sizeof(op.m));
         int32_t kind; int8_t d0;
         classify_gate(g.m, &kind, &d0);
-        if (kind == K_SWAP) kind = K_ANTIDIAG;   // only reached by X-like gates that could not join a permutation
+        if (kind == K_SWAP) kind = K_ANTIDIAG;   // X-like gate outside a permutation (never emitted by the sweep today)
         const int c = g.control();
         const int creg = c >= 0 ? reg_of(c) : -1;
         if (kind == K_HADAMARD) {
             if (c >= 0) kind = K_REAL;                   // the factor cannot leave a controlled gate
-            else acc.K *= cl((long double)g.m[0], 0);    // h [[1,1],[1,-1]]: the kernel adds / subtracts, h joins the pass constant
+            else {
+                acc.K *= cl((long double)g.m[0], 0);     // h [[1,1],[1,-1]]: the kernel adds / subtracts, h joins the pass constant
+                if (pass.ops.size() > n_before && pass.ops.back().code == OC_TABLE_REG + treg) {
+                    // the twiddle that flush_qubit just emitted and this butterfly run as one op
+                    pass.ops.back().code = OC_TWHAD + treg;
+                    last_real[t] = -1;
+                    return;
+                }
+            }
         }
         if (creg >= 0) {
             op.code = OC_CGEN + treg; op.creg = (int8_t)creg;
@@ -525,6 +603,7 @@ struct StageEmitter {
             op.code = OC_GATE + kind * 4 + treg;
         }
         pass.ops.push_back(op);
+        last_real[t] = (op.code == OC_GATE + K_REAL * 4 + treg && !(op.flags & F_TCTRL)) ? (int)pass.ops.size() - 1 : -1;
     }
 };
 
@@ -552,7 +631,12 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
     const int min_low = std::min(opt.min_low, TILE_BITS);
 
     int gate_budget = opt.max_ops_per_pass;
+    // The phase polynomial outlives a pass: a term is only emitted when a non-diagonal gate is about to hit
+    // one of its qubits (or when the gate list ends), so a controlled phase between a qubit of this pass's
+    // tile and one of a later pass's tile costs nothing here and folds into a per-CTA constant there.
+    DiagAcc acc;
     while (!pending.empty()) {
+        const DiagAcc acc_start = acc;
         // ---- pass level: grow the tile greedily, take everything that commutes to the front ----
         // Candidate c hands the free tile positions to the qubits in first-come order but refuses the
         // first c newcomers: on layered circuits (entangler chains) that slides the window along the
@@ -636,35 +720,76 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
         // A later gate may run in this stage only if it commutes past both sets; permutation gates
         // compose among themselves in program order, so they only need to pass b2.
         std::vector<int> remaining = taken;
-        DiagAcc acc;
         StageEmitter em{pass, acc, n_total, pos_of};
+        em.reset_last();
         em.set_stage(IO_GROUP);
-        while (!remaining.empty()) {
-            {
-                int want = em.group;
-                for (int gi : remaining) {
-                    const HostGate& g = gates[gi];
-                    if (!g.diag && !StageEmitter::is_perm_gate(g)) { want = pos_of[g.target()] / REG_BITS; break; }
-                }
-                em.emit_switch(want);    // no-op when nothing is pending and the group stays
-            }
-            const int cur = em.group;
+        // One sweep over `remaining` for register group `grp`.  X / CNOT gates whose target is a register
+        // bit of the stage run at once as register exchanges; the others join the pending permutation that
+        // the next switch executes.  em == nullptr: dry run, returns the weight of what would execute.
+        auto sweep = [&](int grp, StageEmitter* emit, std::vector<int>* rem_out) {
             Blocked b2, pp;
-            std::vector<int> rem2;
+            int n_cond = 0, score = 0;
+            std::vector<uint64_t> cond_masks;
             for (int gi : remaining) {
                 const HostGate& g = gates[gi];
-                bool ok;
                 const bool is_perm = StageEmitter::is_perm_gate(g);
-                if (is_perm) ok = b2.can_pass(g) && em.perm_capacity(g);
-                else ok = b2.can_pass(g) && pp.can_pass(g) && (g.diag || pos_of[g.target()] / REG_BITS == cur);
-                if (!ok) { b2.skip(g); rem2.push_back(gi); continue; }
-                if (is_perm) { em.emit_perm(g); pp.skip(g); }
-                else em.emit_gate(g);
+                const bool in_regs = !g.diag && pos_of[g.target()] / REG_BITS == grp;
+                bool ok, as_perm = false;
+                if (is_perm) {
+                    as_perm = true;
+                    ok = b2.can_pass(g);
+                    if (ok) {      // capacity of the switch payload for controls outside the tile
+                        const int c = g.control();
+                        if (c >= 0 && pos_of[c] < 0) {
+                            if (emit) ok = emit->perm_capacity(g);
+                            else if (std::find(cond_masks.begin(), cond_masks.end(), g.cmask) == cond_masks.end()) {
+                                if (n_cond < PERM_MAX_COND) { cond_masks.push_back(g.cmask); ++n_cond; } else ok = false;
+                            }
+                        }
+                    }
+                } else {
+                    ok = b2.can_pass(g) && pp.can_pass(g) && (g.diag || in_regs);
+                }
+                if (!ok) { b2.skip(g); if (rem_out) rem_out->push_back(gi); continue; }
+                if (as_perm) { if (emit) emit->emit_perm(g); pp.skip(g); }
+                else {
+                    if (emit) emit->emit_gate(g);
+                    if (!g.diag) score += is_perm ? 1 : 4;
+                }
             }
+            return score;
+        };
+        while (!remaining.empty()) {
+            {
+                // next stage: the register group in which the most work can run (ties: stay, then the
+                // group of the first waiting gate)
+                int want = em.group, best = -1;
+                int first_grp = em.group;
+                for (int gi : remaining) {
+                    const HostGate& g = gates[gi];
+                    if (!g.diag && !StageEmitter::is_perm_gate(g)) { first_grp = pos_of[g.target()] / REG_BITS; break; }
+                }
+                int order[NGROUPS + 2], n_order = 0;
+                order[n_order++] = em.group; order[n_order++] = first_grp;
+                for (int g2 = 0; g2 < NGROUPS; ++g2) order[n_order++] = g2;
+                bool seen_grp[NGROUPS] = {false, false, false};
+                for (int k = 0; k < n_order && opt.best_group; ++k) {
+                    const int grp = order[k];
+                    if (seen_grp[grp]) continue;
+                    seen_grp[grp] = true;
+                    const int sc = sweep(grp, nullptr, nullptr);
+                    if (sc > best) { best = sc; want = grp; }
+                }
+                if (best <= 0 || !opt.best_group) want = first_grp;
+                em.emit_switch(want);    // no-op when nothing is pending and the group stays
+            }
+            std::vector<int> rem2;
+            sweep(em.group, &em, &rem2);
             if (rem2.size() == remaining.size()) throw std::runtime_error("plan_local: stage made no progress");
             remaining.swap(rem2);
         }
-        em.flush_all();
+        if (rest.empty()) em.flush_all();
+        else em.fold_free_phases();
         em.emit_switch(IO_GROUP);
         pass.desc.n_ops = (int)pass.ops.size();
         pass.desc.n_tab = (int)pass.tab_desc.size();
@@ -672,6 +797,7 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
             // the op list is a kernel parameter of bounded size: take fewer gates and plan this pass again
             if (taken.size() <= 1) throw std::runtime_error("plan_local: one gate does not fit a pass");
             gate_budget = (int)taken.size() / 2;
+            acc = acc_start;
             continue;
         }
         gate_budget = opt.max_ops_per_pass;

@@ -48,23 +48,26 @@ enum OpKind : int32_t {
     K_RXLIKE = 2,    // real diagonal, purely imaginary off-diagonal (RX)
     K_ANTIDIAG = 3,  // m00 = m11 = 0 (Y)
     K_HADAMARD = 4,  // h * [[1, 1], [1, -1]], uncontrolled: add / subtract only, h joins the pass constant
-    K_SWAP = 5,      // m01 = m10 = 1, m00 = m11 = 0 (X, CNOT): pure exchange
-    K_DIAG = 6,      // m01 = m10 = 0 (RZ, Z, S, T, fused parity phases)
+    K_REALPH = 5,    // real 2x2 followed by diag(1, w) on the same qubit (RY then RZ): w = (m[1], m[3]); planner peephole
+    K_SWAP = 6,      // m01 = m10 = 1, m00 = m11 = 0 (X, CNOT): pure exchange
+    K_DIAG = 7,      // m01 = m10 = 0 (RZ, Z, S, T, fused parity phases)
 };
 
 // Device instruction set.
 enum OpCode : int32_t {
-    OC_GATE = 0,        // + kind*4 + treg (kind 0..4): 2x2 on register bit treg; control none / thread-level
-    OC_CGEN = 20,       // + treg: general 2x2 on treg, control = register bit op.creg (rare)
-    OC_DIAG1 = 24,      // + r: registers with bit r set *= d1, the others *= d0 (unless d0 == 1)
-    OC_PHASE = 28,      // thread-level parity phase -> lazy per-thread scalar
-    OC_DIAGGEN = 29,    // generic parity phase with register bits in its masks (fallback)
-    OC_TABLE = 30,      // product of phase-table lookups -> lazy scalar (optional thread-level pivot)
-    OC_TABLE_REG = 31,  // + r: (table lookups | constant) x factors of the other register bits -> registers with bit r
-    OC_PAIR = 35,       // + pair id: registers with both bits set *= (m[0], m[1])
-    OC_SWITCH = 41,     // + from*3 + to: transpose through shared memory, optionally with a GF(2)-affine
+    OC_GATE = 0,        // + kind*4 + treg (kind 0..5): 2x2 on register bit treg; control none / thread-level
+    OC_CGEN = 28,       // + treg: general 2x2 on treg, control = register bit op.creg (rare)
+    OC_DIAG1 = 36,      // + r: registers with bit r set *= (m[6], m[7])
+    OC_PHASE = 40,      // thread-level parity phase -> lazy per-thread scalar
+    OC_DIAGGEN = 41,    // generic parity phase with register bits in its masks (fallback)
+    OC_TABLE = 42,      // product of phase-table lookups -> lazy scalar (optional thread-level pivot)
+    OC_TABLE_REG = 43,  // + r: (table lookups | constant) x factors of the other register bits -> registers with bit r
+    OC_PAIR = 47,       // + pair id: registers with both bits set *= (m[0], m[1])
+    OC_TWHAD = 53,      // + r: OC_TABLE_REG + r immediately followed by the (uncontrolled) Hadamard on r: the
+                        //   twiddle-then-butterfly step of a QFT, one dispatch instead of two
+    OC_SWITCH = 57,     // + from*3 + to: transpose through shared memory, optionally with a GF(2)-affine
                         //   permutation of the tile index (all pending X / CNOT gates)
-    OC_COUNT = 50,
+    OC_COUNT = 66,
 };
 DVD_HD int pair_id(int r0, int r1) {   // r0 < r1
     return r0 == 0 ? r1 - 1 : r0 == 1 ? r1 + 1 : 5;
@@ -221,6 +224,10 @@ DVD_HD void pair_update(cplx& a0, cplx& a1, const double (&m)[8]) {
     if (KIND == K_HADAMARD) {        // the common factor h is folded into the pass constant by the planner
         a0 = cplx{x.x + y.x, x.y + y.y};
         a1 = cplx{x.x - y.x, x.y - y.y};
+    } else if (KIND == K_REALPH) {   // real rows, then row 1 times w = (m[1], m[3])
+        a0 = cplx{x.x * m[0] + y.x * m[2], x.y * m[0] + y.y * m[2]};
+        const cplx t{x.x * m[4] + y.x * m[6], x.y * m[4] + y.y * m[6]};
+        a1 = cmul(t, m[1], m[3]);
     } else if (KIND == K_GENERAL) {
         a0 = cplx{x.x * m[0] - x.y * m[1] + y.x * m[2] - y.y * m[3], x.x * m[1] + x.y * m[0] + y.x * m[3] + y.y * m[2]};
         a1 = cplx{x.x * m[4] - x.y * m[5] + y.x * m[6] - y.y * m[7], x.x * m[5] + x.y * m[4] + y.x * m[7] + y.y * m[6]};
@@ -263,15 +270,13 @@ DVD_HD void cgen(cplx (&a)[NREG], const double* mp, int creg) {
     }
 }
 
-// Multiply register j by (bit B of j ? d1 : d0); d0 == 1 is skipped.
+// Multiply the registers with bit B set by d1 (the planner normalises d0 to 1 and keeps it in the pass constant).
 template <int B>
-DVD_HD void diag_regbit(cplx (&a)[NREG], const double* m, bool d0one) {
-    const double r0 = m[0], i0 = m[1], r1 = m[6], i1 = m[7];
+DVD_HD void diag_regbit(cplx (&a)[NREG], const double* m) {
+    const double r1 = m[6], i1 = m[7];
 #pragma unroll
-    for (int j = 0; j < NREG; ++j) {
+    for (int j = 0; j < NREG; ++j)
         if ((j >> B) & 1) a[j] = cmul(a[j], r1, i1);
-        else if (!d0one) a[j] = cmul(a[j], r0, i0);
-    }
 }
 template <int B0, int B1>
 DVD_HD void scale_pair(cplx (&a)[NREG], double wr, double wi) {
@@ -381,8 +386,9 @@ DVD_HD void apply_op(cplx (&a)[NREG], const DevOp& op, ThreadCtx& ctx, const cpl
         DVD_CASE4(OC_GATE + 4 * K_RXLIKE, (gate_all<B, K_RXLIKE>(a, m)))
         DVD_CASE4(OC_GATE + 4 * K_ANTIDIAG, (gate_all<B, K_ANTIDIAG>(a, m)))
         DVD_CASE4(OC_GATE + 4 * K_HADAMARD, (gate_all<B, K_HADAMARD>(a, m)))
+        DVD_CASE4(OC_GATE + 4 * K_REALPH, (gate_all<B, K_REALPH>(a, m)))
         DVD_CASE4(OC_CGEN, (cgen<B>(a, m, op.creg)))
-        DVD_CASE4(OC_DIAG1, (diag_regbit<B>(a, m, (flags & F_D0_ONE) != 0)))
+        DVD_CASE4(OC_DIAG1, (diag_regbit<B>(a, m)))
         case OC_PHASE: {
             const bool tpar = parity64(ctx.pidx & op.tmask) != 0;
             if (!((flags & F_D0_ONE) && !tpar)) {
@@ -412,6 +418,8 @@ DVD_HD void apply_op(cplx (&a)[NREG], const DevOp& op, ThreadCtx& ctx, const cpl
         } break;
         DVD_CASE4(OC_TABLE_REG, (table_reg<B>(a, op, flags, ctx, (flags & F_TABLE) ? table_tile(tables, n_tab, op.tab) : tables,
                                               (flags & F_TABLE) ? wcs[op.tab] : cplx{1.0, 0.0})))
+        DVD_CASE4(OC_TWHAD, (table_reg<B>(a, op, flags, ctx, (flags & F_TABLE) ? table_tile(tables, n_tab, op.tab) : tables,
+                                          (flags & F_TABLE) ? wcs[op.tab] : cplx{1.0, 0.0}), gate_all<B, K_HADAMARD>(a, m)))
         case OC_PAIR + 0: scale_pair<0, 1>(a, m[0], m[1]); break;
         case OC_PAIR + 1: scale_pair<0, 2>(a, m[0], m[1]); break;
         case OC_PAIR + 2: scale_pair<0, 3>(a, m[0], m[1]); break;
@@ -421,6 +429,6 @@ DVD_HD void apply_op(cplx (&a)[NREG], const DevOp& op, ThreadCtx& ctx, const cpl
         default: break;
     }
 }
-DVD_HD bool is_table_op(int code) { return code >= OC_TABLE && code < OC_PAIR; }
+DVD_HD bool is_table_op(int code) { return (code >= OC_TABLE && code < OC_PAIR) || (code >= OC_TWHAD && code < OC_TWHAD + 4); }
 
 }  // namespace dvd
