@@ -67,7 +67,6 @@ struct dvd_state {
     double* d_bar = nullptr;
     dvd_stats stats;
     bool unfused = false;
-    double stagger_frac = 0.0;  // DVD_STAGGER: fraction of the estimated CTA lifetime the second CTA per SM is held back
     PlanOptions opt;
 };
 
@@ -157,8 +156,8 @@ static int create_common(int n_qubits, int device, int rank, int world, const vo
     s->n_qubits = n_qubits; s->n_local = n_qubits - g; s->rank = rank; s->world = world; s->device = device;
     s->n_amps = 1ull << s->n_local;
     s->rank_bits = (uint64_t)rank << s->n_local;
-    if (const char* e = getenv("DVD_STAGGER")) s->stagger_frac = atof(e);
     if (const char* e = getenv("DVD_PLAN_CANDIDATES")) s->opt.candidates = std::max(1, atoi(e));
+    if (const char* e = getenv("DVD_MACRO_OPS")) s->opt.macro_ops = atoi(e) != 0;
     s->perm.resize(n_qubits);
     for (int q = 0; q < n_qubits; ++q) s->perm[q] = q;
     auto cleanup = [&](int code) { dvd_destroy(s); return code; };
@@ -300,23 +299,6 @@ int dvd_apply_circuit(dvd_state* s, const dvd_gate* gates, int64_t n) {
 }  // extern "C"
 
 // ---- flush ---------------------------------------------------------------------------------------
-// Rough SM cycles one CTA pair spends on a pass (measured per-op costs on B200, 2 CTAs per SM).
-static double pass_cycle_estimate(const Pass& p) {
-    double c = 12000.0;   // tile load + store at the HBM rate
-    for (const DevOp& op : p.ops) {
-        const int code = op.code;
-        if (code >= OC_SWITCH) c += 2600.0;
-        else if (code < OC_GATE + 4 * K_REAL) c += 1150.0;
-        else if (code < OC_GATE + 4 * K_HADAMARD) c += 600.0;
-        else if (code < OC_CGEN) c += 300.0;
-        else if (code < OC_DIAG1) c += 800.0;
-        else if (code < OC_PHASE) c += 300.0;
-        else if (code >= OC_TABLE_REG && code < OC_PAIR) c += 650.0;
-        else c += 150.0;
-    }
-    return c;
-}
-
 static SimpleOp simple_op(const HostGate& g) {
     SimpleOp op;
     std::memcpy(op.m, g.m, sizeof op.m);
@@ -462,7 +444,6 @@ static int flush_impl(dvd_state* s) {
                 pp.pd = p.desc;
                 pp.pd.rank_bits = s->rank_bits;
                 pp.pd.tables = s->d_tabs + tat;
-                pp.pd.stagger = s->stagger_frac > 0.0 ? (int32_t)(s->stagger_frac * pass_cycle_estimate(p)) : 0;
                 std::memcpy(pp.ops, p.ops.data(), p.ops.size() * sizeof(DevOp));
                 CU(launch_tile_pass(s->amp, pp, s->stream));
                 tat += p.tables.size();

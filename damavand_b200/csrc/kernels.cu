@@ -9,6 +9,8 @@
 // The path is HBM-bound complex128 streaming work: no tensor cores by design.
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace dvd {
 
 // =================================================================================================
@@ -74,6 +76,8 @@ __device__ __forceinline__ void switch_store(cplx* tile, const cplx (&a)[NREG], 
 
 // One launch = one pass: every amplitude is read once and written once; pp.ops is applied in between.
 // The op list lives in the kernel's parameter space (constant bank): op fields are warp-uniform loads.
+// SET: op classes compiled in (see OpClass); launch_tile_pass picks the smallest variant covering the pass.
+template <unsigned SET>
 __global__ void __launch_bounds__(NTHREADS, 2)
 k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -82,13 +86,6 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     const PassDesc& pd = pp.pd;
 
     const int tid = threadIdx.x;
-    // Two CTAs share an SM and run the same op list: started together they sit in the same phase
-    // (HBM / fp64 / shared-memory transposes) all the time.  Holding back the second CTA of every SM
-    // by about half a CTA lifetime in the FIRST wave puts the pair in antiphase for the whole launch.
-    if (pd.stagger > 0 && blockIdx.x >= 148u && blockIdx.x < 296u) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < (long long)pd.stagger) __nanosleep(200);
-    }
     cplx a[NREG];
     {
         const IoAddr io = io_addr(amp, pd);
@@ -131,7 +128,7 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
             ctx.pidx = thread_pidx(pd, gbase, to, tid);
             continue;
         }
-        apply_op(a, op, ctx, tables, n_tab, s_wc);
+        k += apply_op<SET>(a, &op, ctx, tables, n_tab, s_wc);
     }
     flush_phase(a, ctx);   // the planner always ends a pass in the IO layout
 
@@ -461,17 +458,39 @@ static inline unsigned grid_for(uint64_t work_items, int per_cta, unsigned cap) 
 }
 constexpr unsigned STREAM_CAP = 148 * 32;  // grid-stride kernels: a multiple of the SM count
 
+// Kernel variants by op-class set, most specific first; the last one runs everything.
+constexpr unsigned V_LAYERED = C_REAL | C_HAD | C_DIAG | C_MACRO_R;                  // RY/RZ/CNOT ansatz layers
+constexpr unsigned V_FOURIER = C_HAD | C_DIAG | C_TABLE | C_MACRO_T;                 // Hadamards + controlled phases
+constexpr unsigned V_COMMON = C_GENERAL | C_REAL | C_RX | C_HAD | C_DIAG | C_TABLE;  // everything but rare ops / macros
+constexpr unsigned VARIANTS[] = {V_LAYERED, V_FOURIER, V_COMMON, C_ALL};
+typedef void (*TileKernel)(cplx*, const PassParams);
+static TileKernel tile_kernel(int v) {
+    switch (v) {
+        case 0: return k_tile_pass<V_LAYERED>;
+        case 1: return k_tile_pass<V_FOURIER>;
+        case 2: return k_tile_pass<V_COMMON>;
+        default: return k_tile_pass<C_ALL>;
+    }
+}
+
 cudaError_t kernels_init() {
-    cudaError_t e = cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TILE_SLOTS * (int)sizeof(cplx));
-    if (e != cudaSuccess) return e;
+    for (int v = 0; v < 4; ++v) {
+        cudaError_t e = cudaFuncSetAttribute(tile_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             TILE_SLOTS * (int)sizeof(cplx));
+        if (e != cudaSuccess) return e;
+    }
     return cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 SAMPLE_WARPS * (2 << BLK_BITS) * (int)sizeof(double));
 }
 
 cudaError_t launch_tile_pass(cplx* amp, const PassParams& pp, cudaStream_t s) {
     const uint64_t ctas = 1ull << (pp.pd.n_local - TILE_BITS);
-    k_tile_pass<<<(unsigned)ctas, NTHREADS, TILE_SLOTS * sizeof(cplx), s>>>(amp, pp);
+    unsigned need = 0;
+    for (int k = 0; k < pp.pd.n_ops; ++k) need |= op_class(pp.ops[k].code);
+    int v = 0;
+    while (v < 3 && (need & ~VARIANTS[v])) ++v;
+    if (const char* e = getenv("DVD_KERNEL_VARIANT")) v = atoi(e) & 3;   // development: force a variant (3 = all ops)
+    tile_kernel(v)<<<(unsigned)ctas, NTHREADS, TILE_SLOTS * sizeof(cplx), s>>>(amp, pp);
     return cudaGetLastError();
 }
 

@@ -171,6 +171,44 @@ std::vector<HostGate> fuse_diagonal_runs(const std::vector<HostGate>& gates_in) 
     return out;
 }
 
+// Macro-ops: four consecutive ops of one shape on the four register bits run under one dispatch
+// (the interpreter's per-op decode costs about as much as a Hadamard).  Done last: it reorders ops.
+static void fuse_macro_ops(std::vector<DevOp>& ops) {
+    // a macro-op only pays on the specialised kernel variant that holds it (kernels.cu: V_LAYERED, V_FOURIER);
+    // a pass that needs other op classes runs on a general variant and keeps its ops one by one
+    unsigned classes = 0;
+    for (const DevOp& o : ops) classes |= op_class(o.code);
+    const bool allow_r = !(classes & ~(C_REAL | C_HAD | C_DIAG));
+    const bool allow_t = !(classes & ~(C_HAD | C_DIAG | C_TABLE));
+    for (size_t i = 0; i + 3 < ops.size(); ++i) {
+        // four uncontrolled real(+phase) gates on four different register bits: they commute, sort them by bit
+        bool ok = true;
+        unsigned bits = 0;
+        for (int k = 0; k < 4 && ok; ++k) {
+            const DevOp& o = ops[i + k];
+            const int kind = (o.code - OC_GATE) / 4;
+            ok = o.code >= OC_GATE && o.code < OC_CGEN && (kind == K_REAL || kind == K_REALPH) && !(o.flags & F_TCTRL);
+            if (ok) bits |= 1u << ((o.code - OC_GATE) % 4);
+        }
+        if (ok && bits == 15u && allow_r) {
+            DevOp sorted[4];
+            for (int k = 0; k < 4; ++k) {
+                DevOp o = ops[i + k];
+                const int treg = (o.code - OC_GATE) % 4;
+                if ((o.code - OC_GATE) / 4 == K_REAL) { o.m[1] = 1.0; o.m[3] = 0.0; o.code = OC_GATE + 4 * K_REALPH + treg; }
+                sorted[treg] = o;
+            }
+            sorted[0].code = OC_REALPH4;
+            for (int k = 0; k < 4; ++k) ops[i + k] = sorted[k];
+            i += 3;
+            continue;
+        }
+        ok = true;
+        for (int k = 0; k < 4 && ok; ++k) ok = ops[i + k].code == OC_TWHAD + k && !(ops[i + k].flags & F_TCTRL);
+        if (ok && allow_t) { ops[i].code = OC_TWHAD4; i += 3; }
+    }
+}
+
 void Pass::finish_tables() {
     tables.clear();
     if (tab_desc.empty()) return;
@@ -791,6 +829,7 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
         if (rest.empty()) em.flush_all();
         else em.fold_free_phases();
         em.emit_switch(IO_GROUP);
+        if (opt.macro_ops) fuse_macro_ops(pass.ops);
         pass.desc.n_ops = (int)pass.ops.size();
         pass.desc.n_tab = (int)pass.tab_desc.size();
         if (pass.desc.n_ops > MAX_OPS_PER_PASS || pass.desc.n_tab > MAX_TABLE_OPS) {

@@ -51,6 +51,7 @@ struct PlanOptions {
     int window = 16384;        // look-ahead (gates) when filling a pass
     int candidates = 12;       // tile candidates scored per pass (1 = first-come only)
     int max_ops_per_pass = 1024;   // gates taken into one pass (halved and retried while the op stream exceeds MAX_OPS_PER_PASS)
+    bool macro_ops = true;     // fuse 4-op runs on the four register bits into one dispatch (OC_REALPH4, OC_TWHAD4)
     bool best_group = false;   // stage order: group with the most runnable work (true) or group of the first waiting gate
 };
 

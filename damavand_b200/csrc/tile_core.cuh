@@ -65,10 +65,28 @@ enum OpCode : int32_t {
     OC_PAIR = 47,       // + pair id: registers with both bits set *= (m[0], m[1])
     OC_TWHAD = 53,      // + r: OC_TABLE_REG + r immediately followed by the (uncontrolled) Hadamard on r: the
                         //   twiddle-then-butterfly step of a QFT, one dispatch instead of two
-    OC_SWITCH = 57,     // + from*3 + to: transpose through shared memory, optionally with a GF(2)-affine
+    OC_REALPH4 = 57,    // macro-op: the next four ops are uncontrolled K_REALPH gates on register bits 0,1,2,3 (one dispatch)
+    OC_TWHAD4 = 58,     // macro-op: the next four ops are OC_TWHAD + 0,1,2,3 in this order (a radix-16 QFT butterfly)
+    OC_SWITCH = 59,     // + from*3 + to: transpose through shared memory, optionally with a GF(2)-affine
                         //   permutation of the tile index (all pending X / CNOT gates)
-    OC_COUNT = 66,
+    OC_COUNT = 68,
 };
+// Op classes: k_tile_pass is compiled for a few class subsets (fewer live registers, shorter decode,
+// smaller code) and a pass runs on the smallest variant that covers the classes of its ops.
+enum OpClass : unsigned {
+    C_GENERAL = 1u << 0,   // K_GENERAL gates
+    C_REAL = 1u << 1,      // K_REAL / K_REALPH gates
+    C_RX = 1u << 2,        // K_RXLIKE gates
+    C_HAD = 1u << 3,       // K_HADAMARD gates
+    C_RARE = 1u << 4,      // K_ANTIDIAG, OC_CGEN, OC_DIAGGEN
+    C_DIAG = 1u << 5,      // OC_DIAG1, OC_PHASE, OC_PAIR
+    C_TABLE = 1u << 6,     // OC_TABLE, OC_TABLE_REG, OC_TWHAD
+    C_MACRO_R = 1u << 7,   // OC_REALPH4
+    C_MACRO_T = 1u << 8,   // OC_TWHAD4
+    C_ALL = (1u << 9) - 1,
+};
+DVD_HD unsigned op_class(int code);
+
 DVD_HD int pair_id(int r0, int r1) {   // r0 < r1
     return r0 == 0 ? r1 - 1 : r0 == 1 ? r1 + 1 : 5;
 }
@@ -141,7 +159,7 @@ struct PassDesc {
     uint64_t rank_bits;           // this rank's value of the global (rank-index) qubits, in place
     const cplx* tables;           // phase tables of this pass (device pointer; host pointer in the replay)
     int32_t n_tab;                // table ops in this pass (<= MAX_TABLE_OPS)
-    int32_t stagger;              // cycles the second CTA of each SM waits in the first wave (0 = off), see k_tile_pass
+    int32_t pad;
 };
 // Kernel parameter block: the pass description and its whole op list (<= 32764 B of parameters).
 constexpr int MAX_OPS_PER_PASS = 336;
@@ -367,36 +385,49 @@ DVD_HD unsigned perm_index(const DevOp& op, unsigned v, unsigned idx) {
     return r;
 }
 
-#define DVD_CASE4(base, STMT)        \
-    case (base) + 0: { constexpr int B = 0; STMT; } break; \
-    case (base) + 1: { constexpr int B = 1; STMT; } break; \
-    case (base) + 2: { constexpr int B = 2; STMT; } break; \
-    case (base) + 3: { constexpr int B = 3; STMT; } break;
+#define DVD_CASE4(cls, base, STMT)        \
+    case (base) + 0: if constexpr ((SET & (cls)) != 0) { constexpr int B = 0; STMT; } break; \
+    case (base) + 1: if constexpr ((SET & (cls)) != 0) { constexpr int B = 1; STMT; } break; \
+    case (base) + 2: if constexpr ((SET & (cls)) != 0) { constexpr int B = 2; STMT; } break; \
+    case (base) + 3: if constexpr ((SET & (cls)) != 0) { constexpr int B = 3; STMT; } break;
 
-// Apply one op (anything but OC_SWITCH) to the 16 register-resident amplitudes of a thread.
+// Twiddle on the registers with bit B (table_reg) followed by the Hadamard butterfly along B.
+template <int B>
+DVD_HD void twhad(cplx (&a)[NREG], const DevOp& op, const ThreadCtx& ctx, const cplx* tables, int n_tab, const cplx* wcs) {
+    const unsigned flags = op.flags;
+    table_reg<B>(a, op, flags, ctx, (flags & F_TABLE) ? table_tile(tables, n_tab, op.tab) : tables,
+                 (flags & F_TABLE) ? wcs[op.tab] : cplx{1.0, 0.0});
+    gate_all<B, K_HADAMARD>(a, op.m);
+}
+
+// Apply the op at opk[0] (anything but OC_SWITCH) to the 16 register-resident amplitudes of a thread.
 // tables / n_tab: the pass's table buffer; wcs: per-CTA constants of its table ops (kernel prologue).
-DVD_HD void apply_op(cplx (&a)[NREG], const DevOp& op, ThreadCtx& ctx, const cplx* tables, int n_tab, const cplx* wcs) {
+// Returns how many FOLLOWING ops the op consumed (macro-ops run opk[0..3] in one dispatch).
+// SET: the op classes this instantiation can execute (the others compile to nothing).
+template <unsigned SET = C_ALL>
+DVD_HD int apply_op(cplx (&a)[NREG], const DevOp* opk, ThreadCtx& ctx, const cplx* tables, int n_tab, const cplx* wcs) {
+    const DevOp& op = opk[0];
     const int code = op.code;
     const unsigned flags = op.flags;
-    if ((flags & F_TCTRL) && !parity64(ctx.pidx & op.cmask)) return;   // thread-level control
+    if ((flags & F_TCTRL) && !parity64(ctx.pidx & op.cmask)) return 0;   // thread-level control
     const double* m = op.m;
     switch (code) {
-        DVD_CASE4(OC_GATE + 4 * K_GENERAL, (gate_all<B, K_GENERAL>(a, m)))
-        DVD_CASE4(OC_GATE + 4 * K_REAL, (gate_all<B, K_REAL>(a, m)))
-        DVD_CASE4(OC_GATE + 4 * K_RXLIKE, (gate_all<B, K_RXLIKE>(a, m)))
-        DVD_CASE4(OC_GATE + 4 * K_ANTIDIAG, (gate_all<B, K_ANTIDIAG>(a, m)))
-        DVD_CASE4(OC_GATE + 4 * K_HADAMARD, (gate_all<B, K_HADAMARD>(a, m)))
-        DVD_CASE4(OC_GATE + 4 * K_REALPH, (gate_all<B, K_REALPH>(a, m)))
-        DVD_CASE4(OC_CGEN, (cgen<B>(a, m, op.creg)))
-        DVD_CASE4(OC_DIAG1, (diag_regbit<B>(a, m)))
-        case OC_PHASE: {
+        DVD_CASE4(C_GENERAL, OC_GATE + 4 * K_GENERAL, (gate_all<B, K_GENERAL>(a, m)))
+        DVD_CASE4(C_REAL, OC_GATE + 4 * K_REAL, (gate_all<B, K_REAL>(a, m)))
+        DVD_CASE4(C_RX, OC_GATE + 4 * K_RXLIKE, (gate_all<B, K_RXLIKE>(a, m)))
+        DVD_CASE4(C_RARE, OC_GATE + 4 * K_ANTIDIAG, (gate_all<B, K_ANTIDIAG>(a, m)))
+        DVD_CASE4(C_HAD, OC_GATE + 4 * K_HADAMARD, (gate_all<B, K_HADAMARD>(a, m)))
+        DVD_CASE4(C_REAL, OC_GATE + 4 * K_REALPH, (gate_all<B, K_REALPH>(a, m)))
+        DVD_CASE4(C_RARE, OC_CGEN, (cgen<B>(a, m, op.creg)))
+        DVD_CASE4(C_DIAG, OC_DIAG1, (diag_regbit<B>(a, m)))
+        case OC_PHASE: if constexpr ((SET & C_DIAG) != 0) {
             const bool tpar = parity64(ctx.pidx & op.tmask) != 0;
             if (!((flags & F_D0_ONE) && !tpar)) {
                 ctx.ph = cmul(ctx.ph, tpar ? m[6] : m[0], tpar ? m[7] : m[1]);
                 ctx.ph_dirty = true;
             }
         } break;
-        case OC_DIAGGEN: {   // control handled here: thread-level and register-level parts combine
+        case OC_DIAGGEN: if constexpr ((SET & C_RARE) != 0) {   // control handled here: thread-level and register-level parts combine
             const int tregm = op.regm & 15, cregm = op.regm >> 4;
             const bool has_ctrl = (flags & F_HAS_CTRL) != 0;
             const bool cpar = op.cmask != 0 && parity64(ctx.pidx & op.cmask) != 0;
@@ -409,26 +440,49 @@ DVD_HD void apply_op(cplx (&a)[NREG], const DevOp& op, ThreadCtx& ctx, const cpl
                 if (on && !(d0one && !bit)) a[j] = cmul(a[j], bit ? m[6] : m[0], bit ? m[7] : m[1]);
             }
         } break;
-        case OC_TABLE: {
+        case OC_TABLE: if constexpr ((SET & C_TABLE) != 0) {
             if (op.tmask == 0 || parity64(ctx.pidx & op.tmask)) {
                 const cplx w = table_value(table_tile(tables, n_tab, op.tab), wcs[op.tab], ctx.tid);
                 ctx.ph = cmul(ctx.ph, w.x, w.y);
                 ctx.ph_dirty = true;
             }
         } break;
-        DVD_CASE4(OC_TABLE_REG, (table_reg<B>(a, op, flags, ctx, (flags & F_TABLE) ? table_tile(tables, n_tab, op.tab) : tables,
+        DVD_CASE4(C_TABLE, OC_TABLE_REG, (table_reg<B>(a, op, flags, ctx, (flags & F_TABLE) ? table_tile(tables, n_tab, op.tab) : tables,
                                               (flags & F_TABLE) ? wcs[op.tab] : cplx{1.0, 0.0})))
-        DVD_CASE4(OC_TWHAD, (table_reg<B>(a, op, flags, ctx, (flags & F_TABLE) ? table_tile(tables, n_tab, op.tab) : tables,
-                                          (flags & F_TABLE) ? wcs[op.tab] : cplx{1.0, 0.0}), gate_all<B, K_HADAMARD>(a, m)))
-        case OC_PAIR + 0: scale_pair<0, 1>(a, m[0], m[1]); break;
-        case OC_PAIR + 1: scale_pair<0, 2>(a, m[0], m[1]); break;
-        case OC_PAIR + 2: scale_pair<0, 3>(a, m[0], m[1]); break;
-        case OC_PAIR + 3: scale_pair<1, 2>(a, m[0], m[1]); break;
-        case OC_PAIR + 4: scale_pair<1, 3>(a, m[0], m[1]); break;
-        case OC_PAIR + 5: scale_pair<2, 3>(a, m[0], m[1]); break;
+        DVD_CASE4(C_TABLE, OC_TWHAD, (twhad<B>(a, op, ctx, tables, n_tab, wcs)))
+        case OC_PAIR + 0: if constexpr ((SET & C_DIAG) != 0) scale_pair<0, 1>(a, m[0], m[1]); break;
+        case OC_PAIR + 1: if constexpr ((SET & C_DIAG) != 0) scale_pair<0, 2>(a, m[0], m[1]); break;
+        case OC_PAIR + 2: if constexpr ((SET & C_DIAG) != 0) scale_pair<0, 3>(a, m[0], m[1]); break;
+        case OC_PAIR + 3: if constexpr ((SET & C_DIAG) != 0) scale_pair<1, 2>(a, m[0], m[1]); break;
+        case OC_PAIR + 4: if constexpr ((SET & C_DIAG) != 0) scale_pair<1, 3>(a, m[0], m[1]); break;
+        case OC_PAIR + 5: if constexpr ((SET & C_DIAG) != 0) scale_pair<2, 3>(a, m[0], m[1]); break;
+        case OC_REALPH4: if constexpr ((SET & C_MACRO_R) != 0) {
+            gate_all<0, K_REALPH>(a, opk[0].m); gate_all<1, K_REALPH>(a, opk[1].m);
+            gate_all<2, K_REALPH>(a, opk[2].m); gate_all<3, K_REALPH>(a, opk[3].m);
+            return 3;
+        } break;
+        case OC_TWHAD4: if constexpr ((SET & C_MACRO_T) != 0) {
+            twhad<0>(a, opk[0], ctx, tables, n_tab, wcs); twhad<1>(a, opk[1], ctx, tables, n_tab, wcs);
+            twhad<2>(a, opk[2], ctx, tables, n_tab, wcs); twhad<3>(a, opk[3], ctx, tables, n_tab, wcs);
+            return 3;
+        } break;
         default: break;
     }
+    return 0;
 }
-DVD_HD bool is_table_op(int code) { return (code >= OC_TABLE && code < OC_PAIR) || (code >= OC_TWHAD && code < OC_TWHAD + 4); }
+DVD_HD unsigned op_class(int code) {
+    if (code < OC_CGEN) {
+        const int kind = (code - OC_GATE) / 4;
+        return kind == K_GENERAL ? C_GENERAL : (kind == K_REAL || kind == K_REALPH) ? C_REAL : kind == K_RXLIKE ? C_RX
+             : kind == K_HADAMARD ? C_HAD : C_RARE;
+    }
+    if (code < OC_DIAG1 || code == OC_DIAGGEN) return C_RARE;
+    if (code < OC_DIAGGEN || (code >= OC_PAIR && code < OC_TWHAD)) return C_DIAG;   // OC_DIAG1, OC_PHASE, OC_PAIR
+    if (code < OC_PAIR || (code >= OC_TWHAD && code < OC_REALPH4)) return C_TABLE;
+    if (code == OC_REALPH4) return C_MACRO_R;
+    if (code == OC_TWHAD4) return C_MACRO_T;
+    return 0;   // OC_SWITCH
+}
+DVD_HD bool is_table_op(int code) { return (code >= OC_TABLE && code < OC_PAIR) || (code >= OC_TWHAD && code < OC_TWHAD + 4) || code == OC_TWHAD4; }
 
 }  // namespace dvd

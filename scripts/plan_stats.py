@@ -25,7 +25,7 @@ def stats(name, fuse=1, n_local=None):
         passes.append((tile, sw, nops, kinds))
     tot = sum(p[2] for p in passes)
     print(f"{name} fuse={fuse}: gates {ng} -> ops {tot}, passes {len(passes)}, switches {sum(p[1] for p in passes)}")
-    names = [(0, "gate"), (28, "cgen"), (36, "diag1"), (40, "phase"), (41, "diaggen"), (42, "table"), (43, "table_reg"), (47, "pair"), (53, "twhad"), (57, "switch"), (66, "?")]
+    names = [(0, "gate"), (28, "cgen"), (36, "diag1"), (40, "phase"), (41, "diaggen"), (42, "table"), (43, "table_reg"), (47, "pair"), (53, "twhad"), (57, "realph4"), (58, "twhad4"), (59, "switch"), (68, "?")]
     def nm(c):
         for (lo, n), (hi, _) in zip(names, names[1:]):
             if lo <= c < hi: return n

@@ -39,7 +39,8 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
             ctx[tid].tid = tid;
         }
         int cur = IO_GROUP;
-        for (const DevOp& op : pass.ops) {
+        for (size_t oi = 0; oi < pass.ops.size(); ++oi) {
+            const DevOp& op = pass.ops[oi];
             if (op.code < 0 || op.code >= OC_COUNT) throw std::runtime_error("emu: bad opcode");
             if (op.code >= OC_SWITCH) {
                 const int from = (op.code - OC_SWITCH) / NGROUPS, to = (op.code - OC_SWITCH) % NGROUPS;
@@ -65,7 +66,12 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
             }
             if (op.group != cur) throw std::runtime_error("emu: op not in its register group");
             if (is_table_op(op.code) && (op.flags & F_TABLE) && (op.tab < 0 || op.tab >= pd.n_tab)) throw std::runtime_error("emu: bad table index");
-            for (int tid = 0; tid < NTHREADS; ++tid) apply_op(regs[tid], op, ctx[tid], pd.tables, pd.n_tab, wcs.data());
+            int consumed = 0;
+            if ((op.code == OC_REALPH4 || op.code == OC_TWHAD4) && oi + 3 >= pass.ops.size()) throw std::runtime_error("emu: truncated macro-op");
+            for (int tid = 0; tid < NTHREADS; ++tid) consumed = apply_op(regs[tid], &op, ctx[tid], pd.tables, pd.n_tab, wcs.data());
+            if ((op.code == OC_REALPH4 || op.code == OC_TWHAD4) && consumed != 3) throw std::runtime_error("emu: macro-op did not run");
+            for (int e = 1; e <= consumed; ++e) if (pass.ops[oi + e].group != cur) throw std::runtime_error("emu: macro-op crosses a stage");
+            oi += (size_t)consumed;
         }
         for (int tid = 0; tid < NTHREADS; ++tid) flush_phase(regs[tid], ctx[tid]);
         if (cur != IO_GROUP) throw std::runtime_error("emu: pass does not end in the IO layout");

@@ -108,3 +108,47 @@ def test_forward_twice_accumulates():
     st2, _ = emu_run(c, state=flat)
     c.forward(); c.forward()
     assert rel_err(st2, c.amplitudes()) < TOL
+
+
+def test_phase_folding_run_merging_and_macro_ops():
+    # RY+RZ pairs fold into one K_REALPH op per qubit and layer; H RX RY RZ runs merge into one 2x2
+    c = OracleCircuit(14); g = circuits.hea(c, 14, 6); s = _check(c)
+    assert s["ops"] - s["switches"] <= 14 * 6 + 4 * s["passes"]          # one op per (qubit, layer) + leftovers
+    c = OracleCircuit(13); g = circuits.layered(c, 13, 4); s = _check(c)
+    assert s["ops"] - s["switches"] <= 13 * 4 + 4 * s["passes"]          # H RX RY RZ -> one general 2x2
+    c = OracleCircuit(16); g = circuits.qft_like(c, 16); s = _check(c)
+    assert s["ops"] - s["switches"] <= 16 + 8                              # one twiddle+Hadamard op per qubit
+
+
+def _cross_pass_phase_circuit(n):
+    rng = np.random.default_rng(5)
+    c = OracleCircuit(n)
+    for q in range(n):
+        c.add_hadamard_gate(q)
+    for a in range(n):
+        for b in range(a + 1, n, 3):
+            phi = float(rng.random())
+            c.add_rotation_z_gate(b, phi); c.add_cnot_gate(a, b); c.add_rotation_z_gate(b, -phi); c.add_cnot_gate(a, b)
+    for q in range(n - 1, -1, -1):
+        c.add_rotation_x_gate(q, 0.3 + 0.05 * q)
+        c.add_pauli_x_gate((q + 5) % n, False)
+    for q in range(n):
+        c.add_rotation_z_gate(q, 0.1 * q); c.add_hadamard_gate(q)
+    return c
+
+
+def test_phases_deferred_across_passes():
+    # controlled phases between qubits that sit in different passes' tiles, with non-diagonal gates on both
+    # sides: the term is carried over and must be emitted before the later Hadamard / RX hits its qubit
+    s = _check(_cross_pass_phase_circuit(16))
+    assert s["passes"] >= 2
+    _check(_cross_pass_phase_circuit(16), 4)
+    _check(_cross_pass_phase_circuit(14), 2)
+
+
+def test_distributed_list_scheduling_needs_few_swaps():
+    # a layered ansatz on 8 ranks: the whole light cone of a layout runs before any swap is paid for
+    n = 16
+    c = OracleCircuit(n); circuits.hea(c, n, 5)
+    s = _check(c, 8)
+    assert s["swaps"] <= 9          # 3 rank-index qubits in, 3 back (+ slack); one swap per gate would be 15+
