@@ -55,7 +55,11 @@ struct dvd_state {
     std::vector<HostGate> pending;
     std::vector<int> perm;      // logical -> physical (identity between flushes)
     PassParams pass_params;     // staging for the kernel parameter block (copied at launch)
-    cplx* d_tabs = nullptr; cplx* h_tabs = nullptr; size_t tabs_cap = 0;   // phase tables of the queued passes
+    // phase / offset tables of the queued passes: two staging sets used alternately, so that the host can plan
+    // and upload flush f + 1 while the GPU still runs the passes of flush f
+    struct TabSet { cplx* d = nullptr; cplx* h = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool in_flight = false; };
+    TabSet tabs[2];
+    uint64_t n_flushes = 0;
     double* d_tree = nullptr; bool tree_valid = false;
     double* d_scratch = nullptr; size_t scratch_doubles = 0;
     ncclComm_t comm = nullptr;
@@ -245,8 +249,11 @@ int dvd_destroy(dvd_state* s) {
     if (s->amp) cudaFree(s->amp);
     if (s->d_tree) cudaFree(s->d_tree);
     if (s->d_scratch) cudaFree(s->d_scratch);
-    if (s->d_tabs) cudaFree(s->d_tabs);
-    if (s->h_tabs) cudaFreeHost(s->h_tabs);
+    for (auto& t : s->tabs) {
+        if (t.d) cudaFree(t.d);
+        if (t.h) cudaFreeHost(t.h);
+        if (t.done) cudaEventDestroy(t.done);
+    }
     for (auto& b : s->swap_buf) if (b) cudaFree(b);
     for (auto& p : s->peer_amp) if (p) cudaIpcCloseMemHandle(p);
     if (s->d_bar) cudaFree(s->d_bar);
@@ -415,25 +422,28 @@ static int flush_impl(dvd_state* s) {
             return fail(DVD_ERR_INTERNAL, std::string("planner: ") + e.what());
         }
         if (total_tabs) {
-            CU(cudaStreamSynchronize(s->stream));   // the pinned staging buffer may still be in flight
-            if (total_tabs > s->tabs_cap) {
-                if (s->h_tabs) CU(cudaFreeHost(s->h_tabs));
-                if (s->d_tabs) CU(cudaFree(s->d_tabs));
-                s->h_tabs = nullptr; s->d_tabs = nullptr; s->tabs_cap = 0;
+            dvd_state::TabSet& ts = s->tabs[s->n_flushes & 1];
+            if (!ts.done) CU(cudaEventCreateWithFlags(&ts.done, cudaEventDisableTiming));
+            if (ts.in_flight) { CU(cudaEventSynchronize(ts.done)); ts.in_flight = false; }   // the flush before last is over
+            if (total_tabs > ts.cap) {
+                if (ts.h) CU(cudaFreeHost(ts.h));
+                if (ts.d) CU(cudaFree(ts.d));
+                ts.h = nullptr; ts.d = nullptr; ts.cap = 0;
                 const size_t cap = std::max<size_t>(total_tabs * 2, 64 * TABLE_ENTRIES);
-                CU(cudaMallocHost(&s->h_tabs, cap * sizeof(cplx)));
-                CU(cudaMalloc(&s->d_tabs, cap * sizeof(cplx)));
-                s->tabs_cap = cap;
+                CU(cudaMallocHost(&ts.h, cap * sizeof(cplx)));
+                CU(cudaMalloc(&ts.d, cap * sizeof(cplx)));
+                ts.cap = cap;
             }
             size_t tat = 0;
             for (auto& pl : plans)
                 for (auto& p : pl) {
-                    if (!p.tables.empty()) std::memcpy(s->h_tabs + tat, p.tables.data(), p.tables.size() * sizeof(cplx));
+                    if (!p.tables.empty()) std::memcpy(ts.h + tat, p.tables.data(), p.tables.size() * sizeof(cplx));
                     tat += p.tables.size();
                 }
-            CU(cudaMemcpyAsync(s->d_tabs, s->h_tabs, total_tabs * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
+            CU(cudaMemcpyAsync(ts.d, ts.h, total_tabs * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
         }
     }
+    cplx* const d_tabs = s->tabs[s->n_flushes & 1].d;
     size_t tat = 0;
     for (size_t i = 0; i < steps.size(); ++i) {
         DistStep& st = steps[i];
@@ -443,7 +453,8 @@ static int flush_impl(dvd_state* s) {
                 PassParams& pp = s->pass_params;
                 pp.pd = p.desc;
                 pp.pd.rank_bits = s->rank_bits;
-                pp.pd.tables = s->d_tabs + tat;
+                pp.pd.tables = d_tabs + tat;
+                pp.pd.tid_off = reinterpret_cast<const uint64_t*>(d_tabs + tat + p.tid_off_slot);
                 std::memcpy(pp.ops, p.ops.data(), p.ops.size() * sizeof(DevOp));
                 CU(launch_tile_pass(s->amp, pp, s->stream));
                 tat += p.tables.size();
@@ -459,6 +470,12 @@ static int flush_impl(dvd_state* s) {
             }
         }
     }
+    if (tiled && total_tabs) {
+        dvd_state::TabSet& ts = s->tabs[s->n_flushes & 1];
+        CU(cudaEventRecord(ts.done, s->stream));
+        ts.in_flight = true;
+    }
+    s->n_flushes++;
     s->pending.clear();
     s->tree_valid = false;
     return DVD_OK;

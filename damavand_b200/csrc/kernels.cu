@@ -57,15 +57,27 @@ __device__ __forceinline__ cplx ld_stream(const cplx* p) {
     return cplx{v.x, v.y};
 }
 __device__ __forceinline__ void st_stream(cplx* p, cplx v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
+template <int G>
 __device__ __forceinline__ IoAddr io_addr(cplx* amp, const PassDesc& pd) {
     unsigned tid, cta;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(cta));
     IoAddr io;
-    io.p0 = amp + cta_base(pd, (uint64_t)cta) + tile_offset(pd, stage_idx(IO_GROUP, (int)tid, 0));
+    io.p0 = amp + cta_base_runs(pd, (uint64_t)cta) + tid_offset(pd, G, (int)tid);
 #pragma unroll
-    for (int k = 0; k < REG_BITS; ++k) io.hs[k] = 1ull << pd.tile_q[IO_GROUP * REG_BITS + k];
+    for (int k = 0; k < REG_BITS; ++k) io.hs[k] = 1ull << pd.tile_q[G * REG_BITS + k];
     return io;
+}
+template <int G>
+__device__ __forceinline__ void tile_store(cplx* amp, const PassDesc& pd, const cplx (&a)[NREG]) {
+    const IoAddr io = io_addr<G>(amp, pd);
+#pragma unroll
+    for (int j = 0; j < NREG; ++j) {
+        uint64_t off = 0;
+#pragma unroll
+        for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += io.hs[k];
+        st_stream(io.p0 + off, a[j]);
+    }
 }
 
 template <int FROM>
@@ -88,7 +100,7 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     const int tid = threadIdx.x;
     cplx a[NREG];
     {
-        const IoAddr io = io_addr(amp, pd);
+        const IoAddr io = io_addr<IO_GROUP>(amp, pd);
 #pragma unroll
         for (int j = 0; j < NREG; ++j) {
             uint64_t off = 0;
@@ -98,7 +110,7 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
         }
     }
 
-    const uint64_t gbase = cta_base(pd, (uint64_t)blockIdx.x) | pd.rank_bits;
+    const uint64_t gbase = cta_base_runs(pd, (uint64_t)blockIdx.x) | pd.rank_bits;
     const cplx* __restrict__ tables = pd.tables;
     const int n_tab = pd.n_tab;
     if (n_tab > 0) {   // byte tables only see index bits outside the tile: one constant per CTA and table op
@@ -106,11 +118,13 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
         __syncthreads();
     }
     ThreadCtx ctx;
-    ctx.pidx = thread_pidx(pd, gbase, IO_GROUP, tid);
+    ctx.pidx = gbase | tid_offset(pd, IO_GROUP, tid);
     ctx.ph = cplx{1.0, 0.0};
     ctx.ph_dirty = false;
     ctx.tid = tid;
     const int n_ops = pd.n_ops;
+    // (fetching the next op's code one iteration ahead was measured: the extra live register spills and
+    // costs 2-9 %)
     for (int k = 0; k < n_ops; ++k) {
         const DevOp& op = pp.ops[k];
         const int code = op.code;
@@ -125,23 +139,15 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
             if (to == 0) stage_load<0>(tile, a, tid);
             else if (to == 1) stage_load<1>(tile, a, tid);
             else stage_load<2>(tile, a, tid);
-            ctx.pidx = thread_pidx(pd, gbase, to, tid);
+            ctx.pidx = gbase | tid_offset(pd, to, tid);
             continue;
         }
-        k += apply_op<SET>(a, &op, ctx, tables, n_tab, s_wc);
+        k += apply_op<SET>(a, &op, code, ctx, tables, n_tab, s_wc);
     }
-    flush_phase(a, ctx);   // the planner always ends a pass in the IO layout
-
-    {
-        const IoAddr io = io_addr(amp, pd);
-#pragma unroll
-        for (int j = 0; j < NREG; ++j) {
-            uint64_t off = 0;
-#pragma unroll
-            for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += io.hs[k];
-            st_stream(io.p0 + off, a[j]);
-        }
-    }
+    flush_phase(a, ctx);
+    // the planner ends a pass in the group-2 or the group-1 layout: both store 128-byte segments per quarter warp
+    if (pd.io_out == IO_GROUP) tile_store<IO_GROUP>(amp, pd, a);
+    else tile_store<1>(amp, pd, a);
 }
 
 // =================================================================================================

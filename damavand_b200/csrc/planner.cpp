@@ -211,9 +211,9 @@ static void fuse_macro_ops(std::vector<DevOp>& ops) {
 
 void Pass::finish_tables() {
     tables.clear();
-    if (tab_desc.empty()) return;
     const size_t n_tab = tab_desc.size(), byte_base = n_tab + tab_tile.size();
-    tables.resize(byte_base + tab_bytes.size());
+    tid_off_slot = byte_base + tab_bytes.size();
+    tables.resize(tid_off_slot + (size_t)NGROUPS * NTHREADS / 2);
     for (size_t i = 0; i < n_tab; ++i) {
         TableDesc d = tab_desc[i];
         d.byte_off += (uint32_t)byte_base;
@@ -221,6 +221,10 @@ void Pass::finish_tables() {
     }
     if (!tab_tile.empty()) std::memcpy(&tables[n_tab], tab_tile.data(), tab_tile.size() * sizeof(cplx));
     if (!tab_bytes.empty()) std::memcpy(&tables[byte_base], tab_bytes.data(), tab_bytes.size() * sizeof(cplx));
+    uint64_t* off = reinterpret_cast<uint64_t*>(&tables[tid_off_slot]);
+    for (int g = 0; g < NGROUPS; ++g)
+        for (int tid = 0; tid < NTHREADS; ++tid) off[g * NTHREADS + tid] = tile_offset(desc, stage_idx(g, tid, 0));
+    fill_cta_runs(desc);
 }
 
 namespace {
@@ -723,7 +727,10 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
             if (!((tile >> q) & 1)) { tile |= 1ull << q; ++tile_n; }
 
         // ---- tile positions: pinned low run, then by first non-permutation target use -----------
-        Pass pass;
+        // Two hand-out orders of the free tile positions are planned and the one with fewer stage switches
+        // wins: the group-0 positions go to the last-used qubits (a pass must end in the group-2 or group-1
+        // layout to store coalesced, so ending in group 0 costs one more switch) or to the middle ones.
+        auto build_pass = [&](int variant, DiagAcc& acc, Pass& pass) {
         std::memset(&pass.desc, 0, sizeof(pass.desc));
         pass.desc.n_local = n_local;
         std::vector<int> order;  // qubits by first use as the target of a gate that needs registers
@@ -741,9 +748,12 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
             // free positions, in the order they are handed out: IO group first (no switch needed
             // for the first gates), then the middle groups downwards, then the rest of group 0.
             std::vector<int> free_pos;
-            for (int g = NGROUPS - 1; g >= 0; --g)
+            static const int handout[2][NGROUPS] = {{2, 1, 0}, {2, 0, 1}};
+            for (int gi = 0; gi < NGROUPS; ++gi) {
+                const int g = handout[variant][gi];
                 for (int p = g * REG_BITS; p < (g + 1) * REG_BITS; ++p)
                     if (p >= min_low) free_pos.push_back(p);
+            }
             if (order.size() != free_pos.size()) throw std::runtime_error("plan_local: tile size");
             for (size_t i = 0; i < order.size(); ++i) {
                 pass.desc.tile_q[free_pos[i]] = order[i];
@@ -828,11 +838,27 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
         }
         if (rest.empty()) em.flush_all();
         else em.fold_free_phases();
-        em.emit_switch(IO_GROUP);
+        // store layout: stay in group 1 or 2 (a pending permutation still needs its same-group switch)
+        em.emit_switch(em.group == 0 ? IO_GROUP : em.group);
+        pass.desc.io_out = em.group;
         if (opt.macro_ops) fuse_macro_ops(pass.ops);
+        };
+        Pass pass;
+        {
+            Pass cand[2];
+            DiagAcc cacc[2] = {acc_start, acc_start};
+            int best = 0;
+            for (int v = 0; v < 2; ++v) {
+                build_pass(v, cacc[v], cand[v]);
+                if (v > 0 && (cand[v].n_switches < cand[best].n_switches ||
+                              (cand[v].n_switches == cand[best].n_switches && cand[v].ops.size() < cand[best].ops.size()))) best = v;
+            }
+            pass = std::move(cand[best]);
+            acc = cacc[best];
+        }
         pass.desc.n_ops = (int)pass.ops.size();
         pass.desc.n_tab = (int)pass.tab_desc.size();
-        if (pass.desc.n_ops > MAX_OPS_PER_PASS || pass.desc.n_tab > MAX_TABLE_OPS) {
+        if (pass.desc.n_ops >= MAX_OPS_PER_PASS || pass.desc.n_tab > MAX_TABLE_OPS) {
             // the op list is a kernel parameter of bounded size: take fewer gates and plan this pass again
             if (taken.size() <= 1) throw std::runtime_error("plan_local: one gate does not fit a pass");
             gate_budget = (int)taken.size() / 2;

@@ -42,7 +42,8 @@ struct Pass {
     std::vector<TableDesc> tab_desc;   // one record per table op, in op order (ops[].tab indexes it)
     std::vector<cplx> tab_tile;        // TABLE_TILE_ENTRIES thread-index factors per table op
     std::vector<cplx> tab_bytes;       // byte sub-tables (TABLE_ENTRIES each)
-    void finish_tables();              // concatenate [desc][tile][bytes] into `tables`
+    size_t tid_off_slot = 0;           // start (in cplx slots) of the [NGROUPS][NTHREADS] thread-offset table inside `tables`
+    void finish_tables();              // concatenate [desc][tile][bytes][thread offsets] into `tables`, fill desc.run_*
     int n_switches = 0;        // stage switches inside the pass (shared-memory transposes)
 };
 

@@ -35,7 +35,8 @@ constexpr int NREG = 1 << REG_BITS;
 constexpr int THREAD_BITS = TILE_BITS - REG_BITS;
 constexpr int NTHREADS = 1 << THREAD_BITS; // 256
 constexpr int NGROUPS = TILE_BITS / REG_BITS;  // 3 register groups: tile positions [4g, 4g+4)
-constexpr int IO_GROUP = NGROUPS - 1;      // global loads/stores use the group-2 layout (coalesced)
+constexpr int IO_GROUP = NGROUPS - 1;      // global loads use the group-2 layout; stores the group-2 or group-1 layout
+                                           // (in both, lanes cover tile positions 0..2 = 128 contiguous bytes)
 constexpr int TILE_AMPS = 1 << TILE_BITS;
 constexpr int TABLE_ENTRIES = 256;         // one phase sub-table per byte of the physical index
 constexpr int MAX_INDEX_BYTES = 8;
@@ -159,7 +160,14 @@ struct PassDesc {
     uint64_t rank_bits;           // this rank's value of the global (rank-index) qubits, in place
     const cplx* tables;           // phase tables of this pass (device pointer; host pointer in the replay)
     int32_t n_tab;                // table ops in this pass (<= MAX_TABLE_OPS)
-    int32_t pad;
+    int32_t io_out;               // register group whose layout the tile is stored from (1 or 2; loads use IO_GROUP)
+    // Index arithmetic precomputed by the planner (the bit-by-bit loops below cost ~17 % of the kernel's
+    // instructions when every thread runs them at every stage switch):
+    const uint64_t* tid_off;      // [NGROUPS][NTHREADS]: tile_offset(stage_idx(g, tid, 0)), device pointer
+    int8_t n_runs;                // cta_base as runs of non-tile bits: bits [src, src+len) of the CTA index
+    int8_t run_src[TILE_BITS + 1];    //   land at bit position dst of the physical index
+    int8_t run_len[TILE_BITS + 1];
+    int8_t run_dst[TILE_BITS + 1];
 };
 // Kernel parameter block: the pass description and its whole op list (<= 32764 B of parameters).
 constexpr int MAX_OPS_PER_PASS = 336;
@@ -200,6 +208,25 @@ DVD_HD uint64_t cta_base(const PassDesc& pd, uint64_t cta) {
         b = ((b >> q) << (q + 1)) | (b & ((1ull << q) - 1));
     }
     return b;
+}
+
+// The same from the run-compressed form (PassDesc::run_*): a handful of shifts instead of TILE_BITS steps.
+DVD_HD uint64_t cta_base_runs(const PassDesc& pd, uint64_t cta) {
+    uint64_t b = 0;
+    for (int r = 0; r < pd.n_runs; ++r)
+        b |= ((cta >> pd.run_src[r]) & ((1ull << pd.run_len[r]) - 1)) << pd.run_dst[r];
+    return b;
+}
+// Host: fill PassDesc::run_* from sorted_q / n_local.
+inline void fill_cta_runs(PassDesc& pd) {
+    int n = 0, src = 0, prev = 0;    // prev: first physical bit not yet covered
+    for (int p = 0; p <= TILE_BITS; ++p) {
+        const int q = p < TILE_BITS ? pd.sorted_q[p] : pd.n_local;
+        const int len = q - prev;    // non-tile bits [prev, q)
+        if (len > 0) { pd.run_src[n] = (int8_t)src; pd.run_len[n] = (int8_t)len; pd.run_dst[n] = (int8_t)prev; ++n; src += len; }
+        prev = q + 1;
+    }
+    pd.n_runs = (int8_t)n;
 }
 
 // Local index of element h of the half-chunk whose bit lq equals bitval (global<->local qubit swap).
@@ -365,6 +392,14 @@ DVD_HD void table_reg(cplx (&a)[NREG], const DevOp& op, unsigned flags, const Th
 DVD_HD uint64_t thread_pidx(const PassDesc& pd, uint64_t gbase, int g, int tid) {
     return gbase | tile_offset(pd, stage_idx(g, tid, 0));
 }
+// The same through the planner's table.
+DVD_HD uint64_t tid_offset(const PassDesc& pd, int g, int tid) {
+#ifdef __CUDA_ARCH__
+    return __ldg(reinterpret_cast<const unsigned long long*>(pd.tid_off) + g * NTHREADS + tid);
+#else
+    return pd.tid_off[g * NTHREADS + tid];
+#endif
+}
 // Constant part of a permuting switch for one CTA: v0 ^ conditional flips.
 DVD_HD unsigned perm_const(const DevOp& op, uint64_t gbase) {
     const PermPayload& pp = *reinterpret_cast<const PermPayload*>(op.m);
@@ -405,9 +440,8 @@ DVD_HD void twhad(cplx (&a)[NREG], const DevOp& op, const ThreadCtx& ctx, const 
 // Returns how many FOLLOWING ops the op consumed (macro-ops run opk[0..3] in one dispatch).
 // SET: the op classes this instantiation can execute (the others compile to nothing).
 template <unsigned SET = C_ALL>
-DVD_HD int apply_op(cplx (&a)[NREG], const DevOp* opk, ThreadCtx& ctx, const cplx* tables, int n_tab, const cplx* wcs) {
+DVD_HD int apply_op(cplx (&a)[NREG], const DevOp* opk, int code, ThreadCtx& ctx, const cplx* tables, int n_tab, const cplx* wcs) {
     const DevOp& op = opk[0];
-    const int code = op.code;
     const unsigned flags = op.flags;
     if ((flags & F_TCTRL) && !parity64(ctx.pidx & op.cmask)) return 0;   // thread-level control
     const double* m = op.m;

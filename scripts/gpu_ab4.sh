@@ -17,5 +17,5 @@ except Exception as e:
 PY
   done
 }
-run m0 DVD_MACRO_OPS=0
-run m1 DVD_MACRO_OPS=1
+run pf0 DVD_LIB_PATH=$PWD/damavand_b200/libdvd_pf0.so
+run pf1 DVD_MACRO_OPS=1

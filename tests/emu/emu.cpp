@@ -20,20 +20,24 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
     PassDesc pd = pass.desc;
     pd.rank_bits = rank_bits;
     pd.tables = pass.tables.data();
+    pd.tid_off = reinterpret_cast<const uint64_t*>(pass.tables.data() + pass.tid_off_slot);
     const uint64_t ctas = 1ull << (pd.n_local - TILE_BITS);
     std::vector<cplx> tile(TILE_SLOTS);
     static cplx regs[NTHREADS][NREG];
     static ThreadCtx ctx[NTHREADS];
     for (uint64_t cta = 0; cta < ctas; ++cta) {
         const uint64_t base = cta_base(pd, cta);
+        if (cta_base_runs(pd, cta) != base) throw std::runtime_error("emu: run-compressed CTA base differs");
         const uint64_t gbase = base | pd.rank_bits;
-        if (pd.n_tab > MAX_TABLE_OPS || pd.n_ops > MAX_OPS_PER_PASS || (size_t)pd.n_ops != pass.ops.size())
+        if (pd.n_tab > MAX_TABLE_OPS || pd.n_ops >= MAX_OPS_PER_PASS || (size_t)pd.n_ops != pass.ops.size())
             throw std::runtime_error("emu: pass exceeds the kernel parameter limits");
         std::vector<cplx> wcs(pd.n_tab > 0 ? pd.n_tab : 1);     // kernel prologue: per-CTA table constants
         for (int ti = 0; ti < pd.n_tab; ++ti) wcs[ti] = table_cta_const(pd.tables, ti, gbase);
         for (int tid = 0; tid < NTHREADS; ++tid) {
             for (int j = 0; j < NREG; ++j) regs[tid][j] = amp[base + tile_offset(pd, stage_idx(IO_GROUP, tid, j))];
             ctx[tid].pidx = gbase | tile_offset(pd, stage_idx(IO_GROUP, tid, 0));
+            for (int g = 0; g < NGROUPS; ++g)
+                if (cta == 0 && tid_offset(pd, g, tid) != tile_offset(pd, stage_idx(g, tid, 0))) throw std::runtime_error("emu: thread offset table differs");
             ctx[tid].ph = cplx{1.0, 0.0};
             ctx[tid].ph_dirty = false;
             ctx[tid].tid = tid;
@@ -68,15 +72,15 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
             if (is_table_op(op.code) && (op.flags & F_TABLE) && (op.tab < 0 || op.tab >= pd.n_tab)) throw std::runtime_error("emu: bad table index");
             int consumed = 0;
             if ((op.code == OC_REALPH4 || op.code == OC_TWHAD4) && oi + 3 >= pass.ops.size()) throw std::runtime_error("emu: truncated macro-op");
-            for (int tid = 0; tid < NTHREADS; ++tid) consumed = apply_op(regs[tid], &op, ctx[tid], pd.tables, pd.n_tab, wcs.data());
+            for (int tid = 0; tid < NTHREADS; ++tid) consumed = apply_op(regs[tid], &op, op.code, ctx[tid], pd.tables, pd.n_tab, wcs.data());
             if ((op.code == OC_REALPH4 || op.code == OC_TWHAD4) && consumed != 3) throw std::runtime_error("emu: macro-op did not run");
             for (int e = 1; e <= consumed; ++e) if (pass.ops[oi + e].group != cur) throw std::runtime_error("emu: macro-op crosses a stage");
             oi += (size_t)consumed;
         }
         for (int tid = 0; tid < NTHREADS; ++tid) flush_phase(regs[tid], ctx[tid]);
-        if (cur != IO_GROUP) throw std::runtime_error("emu: pass does not end in the IO layout");
+        if (cur != pd.io_out || (cur != IO_GROUP && cur != 1)) throw std::runtime_error("emu: pass does not end in its store layout");
         for (int tid = 0; tid < NTHREADS; ++tid)
-            for (int j = 0; j < NREG; ++j) amp[base + tile_offset(pd, stage_idx(IO_GROUP, tid, j))] = regs[tid][j];
+            for (int j = 0; j < NREG; ++j) amp[base + tile_offset(pd, stage_idx(cur, tid, j))] = regs[tid][j];
     }
 }
 
