@@ -41,15 +41,17 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    # development: DVD_BUILD_DEFS="-DX -DY" DVD_BUILD_OUT=path builds an A/B variant next to the product library
+    out = os.environ.get("DVD_BUILD_OUT") or LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + os.environ.get("DVD_BUILD_DEFS", "").split() + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libdamavand_b200.so")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

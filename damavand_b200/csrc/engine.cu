@@ -71,6 +71,10 @@ struct dvd_state {
     double* d_bar = nullptr;
     dvd_stats stats;
     bool unfused = false;
+    // lazy reset: the state is |0..0> but the buffer has not been written; the next tile pass synthesises its
+    // input (no memset, no read), anything else materialises it first
+    bool zero_pending = false;
+    bool lazy_zero = true;
     PlanOptions opt;
 };
 
@@ -83,15 +87,23 @@ static int ensure_scratch(dvd_state* s, size_t doubles) {
     return DVD_OK;
 }
 
-static int set_zero_state(dvd_state* s) {
+static int write_zero_state(dvd_state* s) {
     CU(cudaMemsetAsync(s->amp, 0, s->n_amps * sizeof(cplx), s->stream));
     if (s->rank == 0) {   // amplitude 0 lives on the first rank (circuit.rs:168-170, kernels.cu:62-81)
         CU(launch_set_basis_state(s->amp, 0, s->stream));
         s->stats.kernel_launches++;
     }
-    s->tree_valid = false;
+    s->zero_pending = false;
     return DVD_OK;
 }
+// Reset to |0..0>.  When the next thing to touch the state is a tile pass, that pass writes every amplitude
+// anyway: it starts from zeros in registers and the 16 B/amplitude memset plus the pass's own read are saved.
+static int set_zero_state(dvd_state* s) {
+    s->tree_valid = false;
+    if (s->lazy_zero && !s->unfused && s->n_local >= TILE_BITS) { s->zero_pending = true; return DVD_OK; }
+    return write_zero_state(s);
+}
+static int materialize(dvd_state* s) { return s->zero_pending ? write_zero_state(s) : DVD_OK; }
 
 // Stream-ordered barrier over all ranks: a one-element allreduce completes on a rank only after every
 // rank's stream has reached it, i.e. after all earlier kernels on every rank's stream have finished.
@@ -162,6 +174,7 @@ static int create_common(int n_qubits, int device, int rank, int world, const vo
     s->rank_bits = (uint64_t)rank << s->n_local;
     if (const char* e = getenv("DVD_PLAN_CANDIDATES")) s->opt.candidates = std::max(1, atoi(e));
     if (const char* e = getenv("DVD_MACRO_OPS")) s->opt.macro_ops = atoi(e) != 0;
+    if (const char* e = getenv("DVD_LAZY_ZERO")) s->lazy_zero = atoi(e) != 0;
     s->perm.resize(n_qubits);
     for (int q = 0; q < n_qubits; ++q) s->perm[q] = q;
     auto cleanup = [&](int code) { dvd_destroy(s); return code; };
@@ -447,12 +460,13 @@ static int flush_impl(dvd_state* s) {
     size_t tat = 0;
     for (size_t i = 0; i < steps.size(); ++i) {
         DistStep& st = steps[i];
-        if (st.kind == DistStep::GLOBAL_SWAP) { TRY(global_swap(s, st.gq, st.lq)); continue; }
+        if (st.kind == DistStep::GLOBAL_SWAP) { TRY(materialize(s)); TRY(global_swap(s, st.gq, st.lq)); continue; }
         if (tiled) {
             for (auto& p : plans[i]) {
                 PassParams& pp = s->pass_params;
                 pp.pd = p.desc;
                 pp.pd.rank_bits = s->rank_bits;
+                pp.pd.zero_input = s->zero_pending ? 1 : 0;
                 pp.pd.tables = d_tabs + tat;
                 pp.pd.tid_off = reinterpret_cast<const uint64_t*>(d_tabs + tat + p.tid_off_slot);
                 std::memcpy(pp.ops, p.ops.data(), p.ops.size() * sizeof(DevOp));
@@ -460,9 +474,11 @@ static int flush_impl(dvd_state* s) {
                 tat += p.tables.size();
                 s->stats.kernel_launches++; s->stats.tile_passes++;
                 s->stats.stage_switches += p.n_switches;
-                s->stats.pass_bytes += 2.0 * chunk_bytes;
+                s->stats.pass_bytes += (s->zero_pending ? 1.0 : 2.0) * chunk_bytes;
+                s->zero_pending = false;
             }
         } else {
+            TRY(materialize(s));
             for (const HostGate& g : st.gates) {
                 CU(launch_simple_gate(s->amp, s->n_local, s->rank_bits, simple_op(g), s->stream));
                 s->stats.kernel_launches++; s->stats.simple_passes++;
@@ -481,8 +497,15 @@ static int flush_impl(dvd_state* s) {
     return DVD_OK;
 }
 
-static int ensure_tree(dvd_state* s) {
+// Everything queued has run and the buffer holds the state (observation points).
+static int sync_state(dvd_state* s) {
     TRY(flush_impl(s));
+    CU(cudaSetDevice(s->device));
+    return materialize(s);
+}
+
+static int ensure_tree(dvd_state* s) {
+    TRY(sync_state(s));
     if (s->tree_valid) return DVD_OK;
     CU(launch_build_tree(s->amp, s->n_local, s->d_tree, s->stream));
     s->stats.kernel_launches += 1 + std::max(0, s->n_local - BLK_BITS);
@@ -508,7 +531,7 @@ int dvd_synchronize(dvd_state* s) {
 int dvd_probabilities(dvd_state* s, double* out, int64_t first, int64_t count) {
     if (!s || (!out && count > 0)) return fail(DVD_ERR_ARG, "null argument");
     if (first < 0 || count < 0 || (uint64_t)(first + count) > s->n_amps) return fail(DVD_ERR_ARG, "range outside the local chunk");
-    TRY(flush_impl(s));
+    TRY(sync_state(s));
     const uint64_t CH = 1ull << 24;
     TRY(ensure_scratch(s, std::min<uint64_t>(CH, std::max<int64_t>(count, 1))));
     for (uint64_t done = 0; done < (uint64_t)count; done += CH) {
@@ -608,7 +631,7 @@ int dvd_extract_expectation_values(dvd_state* s, const uint64_t* samples, int64_
 
 int dvd_expectation_z(dvd_state* s, double* out) {
     if (!s || !out) return fail(DVD_ERR_ARG, "null argument");
-    TRY(flush_impl(s));
+    TRY(sync_state(s));
     TRY(ensure_scratch(s, ez_partial_size() + 128));
     double* d_out = s->d_scratch + ez_partial_size();
     CU(launch_expectation_z(s->amp, s->n_local, s->n_qubits, s->rank_bits, s->d_scratch, d_out, s->stream));
@@ -622,7 +645,7 @@ int dvd_expectation_z(dvd_state* s, double* out) {
 int dvd_read_state(dvd_state* s, double* re, double* im, int64_t first, int64_t count) {
     if (!s || ((!re || !im) && count > 0)) return fail(DVD_ERR_ARG, "null argument");
     if (first < 0 || count < 0 || (uint64_t)(first + count) > s->n_amps) return fail(DVD_ERR_ARG, "range outside the local chunk");
-    TRY(flush_impl(s));
+    TRY(sync_state(s));
     const uint64_t CH = 1ull << 22;
     std::vector<cplx> tmp(std::min<uint64_t>(CH, std::max<int64_t>(count, 1)));
     for (uint64_t done = 0; done < (uint64_t)count; done += CH) {
@@ -637,7 +660,7 @@ int dvd_read_state(dvd_state* s, double* re, double* im, int64_t first, int64_t 
 int dvd_load_state(dvd_state* s, const double* re, const double* im, int64_t first, int64_t count) {
     if (!s || ((!re || !im) && count > 0)) return fail(DVD_ERR_ARG, "null argument");
     if (first < 0 || count < 0 || (uint64_t)(first + count) > s->n_amps) return fail(DVD_ERR_ARG, "range outside the local chunk");
-    TRY(flush_impl(s));
+    TRY(sync_state(s));
     const uint64_t CH = 1ull << 22;
     std::vector<cplx> tmp(std::min<uint64_t>(CH, std::max<int64_t>(count, 1)));
     for (uint64_t done = 0; done < (uint64_t)count; done += CH) {
@@ -654,8 +677,8 @@ int dvd_fidelity(dvd_state* a, dvd_state* b, double* out) {
     if (!a || !b || !out) return fail(DVD_ERR_ARG, "null argument");
     if (a->n_qubits != b->n_qubits || a->world != b->world || a->rank != b->rank || a->device != b->device)
         return fail(DVD_ERR_ARG, "states have different shapes");
-    TRY(flush_impl(a));
-    TRY(flush_impl(b));
+    TRY(sync_state(a));
+    TRY(sync_state(b));
     CU(cudaStreamSynchronize(b->stream));
     TRY(ensure_scratch(a, 148 * 4 * 2 + 8));
     double* d_out = a->d_scratch + 148 * 4 * 2;
@@ -673,11 +696,12 @@ int dvd_copy_state(dvd_state* dst, dvd_state* src) {
     if (!dst || !src) return fail(DVD_ERR_ARG, "null argument");
     if (dst->n_qubits != src->n_qubits || dst->world != src->world || dst->device != src->device)
         return fail(DVD_ERR_ARG, "states have different shapes");
-    TRY(flush_impl(src));
+    TRY(sync_state(src));
     dst->pending.clear();
     CU(cudaStreamSynchronize(src->stream));
     CU(cudaMemcpyAsync(dst->amp, src->amp, src->n_amps * sizeof(cplx), cudaMemcpyDeviceToDevice, dst->stream));
     dst->tree_valid = false;
+    dst->zero_pending = false;
     return DVD_OK;
 }
 

@@ -57,20 +57,20 @@ __device__ __forceinline__ cplx ld_stream(const cplx* p) {
     return cplx{v.x, v.y};
 }
 __device__ __forceinline__ void st_stream(cplx* p, cplx v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
+// `cbase` = cta_base_runs(tile index): the tile's physical base, computed once per tile by the caller.
 template <int G>
-__device__ __forceinline__ IoAddr io_addr(cplx* amp, const PassDesc& pd) {
-    unsigned tid, cta;
+__device__ __forceinline__ IoAddr io_addr(cplx* amp, const PassDesc& pd, uint64_t cbase) {
+    unsigned tid;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(cta));
     IoAddr io;
-    io.p0 = amp + cta_base_runs(pd, (uint64_t)cta) + tid_offset(pd, G, (int)tid);
+    io.p0 = amp + cbase + tid_offset(pd, G, (int)tid);
 #pragma unroll
     for (int k = 0; k < REG_BITS; ++k) io.hs[k] = 1ull << pd.tile_q[G * REG_BITS + k];
     return io;
 }
 template <int G>
-__device__ __forceinline__ void tile_store(cplx* amp, const PassDesc& pd, const cplx (&a)[NREG]) {
-    const IoAddr io = io_addr<G>(amp, pd);
+__device__ __forceinline__ void tile_store(cplx* amp, const PassDesc& pd, const cplx (&a)[NREG], uint64_t cbase) {
+    const IoAddr io = io_addr<G>(amp, pd, cbase);
 #pragma unroll
     for (int j = 0; j < NREG; ++j) {
         uint64_t off = 0;
@@ -78,6 +78,35 @@ __device__ __forceinline__ void tile_store(cplx* amp, const PassDesc& pd, const 
         for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += io.hs[k];
         st_stream(io.p0 + off, a[j]);
     }
+}
+// |0..0> as the pass input (lazy reset): amplitude 0 lives in register 0 of thread 0 of tile 0 on rank 0.
+__device__ __forceinline__ void tile_zero_input(cplx (&a)[NREG], const PassDesc& pd, unsigned tile_id, int tid) {
+#pragma unroll
+    for (int j = 0; j < NREG; ++j) a[j] = cplx{0.0, 0.0};
+    if (tile_id == 0 && tid == 0 && pd.rank_bits == 0) a[0].x = 1.0;
+}
+
+// Asynchronous global -> shared copies (LDGSTS): the next tile travels while the current one is computed on.
+__device__ __forceinline__ void cp_async16(cplx* smem_dst, const cplx* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// Every thread fetches exactly the 16 amplitudes it will hold in the group-G layout, into the slots
+// stage_load<G> reads them back from: the staging needs no barrier of its own.
+template <int G>
+__device__ __forceinline__ void tile_prefetch(cplx* tile, cplx* amp, const PassDesc& pd, uint64_t cbase, int tid) {
+    const IoAddr io = io_addr<G>(amp, pd, cbase);
+    cplx* sp = tile + smem_slot(stage_idx(G, tid, 0));
+#pragma unroll
+    for (int j = 0; j < NREG; ++j) {
+        uint64_t off = 0;
+#pragma unroll
+        for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += io.hs[k];
+        cp_async16(sp + smem_slot(j << (REG_BITS * G)), io.p0 + off);
+    }
+    cp_async_commit();
 }
 
 template <int FROM>
@@ -98,9 +127,18 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     const PassDesc& pd = pp.pd;
 
     const int tid = threadIdx.x;
+    const uint64_t cbase = cta_base_runs(pd, (uint64_t)blockIdx.x);
+    const uint64_t gbase = cbase | pd.rank_bits;
+    const cplx* __restrict__ tables = pd.tables;
+    const int n_tab = pd.n_tab;
+    // byte tables only see index bits outside the tile: one constant per CTA and table op.  The two dependent
+    // lookups start before the tile's own loads queue up in front of them.
+    if (tid < n_tab) s_wc[tid] = table_cta_const(tables, tid, gbase);
     cplx a[NREG];
-    {
-        const IoAddr io = io_addr<IO_GROUP>(amp, pd);
+    if (pd.zero_input) {
+        tile_zero_input(a, pd, blockIdx.x, tid);
+    } else {
+        const IoAddr io = io_addr<IO_GROUP>(amp, pd, cbase);
 #pragma unroll
         for (int j = 0; j < NREG; ++j) {
             uint64_t off = 0;
@@ -110,13 +148,7 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
         }
     }
 
-    const uint64_t gbase = cta_base_runs(pd, (uint64_t)blockIdx.x) | pd.rank_bits;
-    const cplx* __restrict__ tables = pd.tables;
-    const int n_tab = pd.n_tab;
-    if (n_tab > 0) {   // byte tables only see index bits outside the tile: one constant per CTA and table op
-        if (tid < n_tab) s_wc[tid] = table_cta_const(tables, tid, gbase);
-        __syncthreads();
-    }
+    if (n_tab > 0) __syncthreads();
     ThreadCtx ctx;
     ctx.pidx = gbase | tid_offset(pd, IO_GROUP, tid);
     ctx.ph = cplx{1.0, 0.0};
@@ -146,8 +178,88 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     }
     flush_phase(a, ctx);
     // the planner ends a pass in the group-2 or the group-1 layout: both store 128-byte segments per quarter warp
-    if (pd.io_out == IO_GROUP) tile_store<IO_GROUP>(amp, pd, a);
-    else tile_store<1>(amp, pd, a);
+    // (rank bits lie above the local index bits, so gbase - rank_bits is the tile's base again)
+    if (pd.io_out == IO_GROUP) tile_store<IO_GROUP>(amp, pd, a, gbase - pd.rank_bits);
+    else tile_store<1>(amp, pd, a, gbase - pd.rank_bits);
+}
+
+// Persistent form of the same pass: one CTA per resident slot loops over tiles t = blockIdx.x, + gridDim.x, ...
+// As soon as the last transpose of tile t has been read back, the shared-memory tile is free, so the
+// amplitudes of tile t + gridDim.x are fetched into it with cp.async (no registers involved) while the last
+// group's gates and the write-back of tile t run; the per-CTA table constants of the next tile are
+// computed in the same shadow.  The load latency, which the one-tile-per-CTA form exposes once per
+// tile (its stalls are ~20 % of the warp time in profiles/r1_ncu_full_tile_qft30_v8.csv), is hidden.
+template <unsigned SET>
+__global__ void __launch_bounds__(NTHREADS, 2)
+k_tile_pass_persist(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* tile = reinterpret_cast<cplx*>(smem_raw);
+    __shared__ cplx s_wc[2][MAX_TABLE_OPS];
+    const PassDesc& pd = pp.pd;
+    const int tid = threadIdx.x;
+    const unsigned n_tiles = 1u << (pd.n_local - TILE_BITS);
+    const cplx* __restrict__ tables = pd.tables;
+    const int n_tab = pd.n_tab;
+    const int n_ops = pd.n_ops;
+    const int last_switch = pd.last_switch;
+    const bool zero_in = pd.zero_input != 0;
+    unsigned t = blockIdx.x;
+    if (t >= n_tiles) return;
+    {
+        const uint64_t cb = cta_base_runs(pd, (uint64_t)t);
+        if (!zero_in) tile_prefetch<IO_GROUP>(tile, amp, pd, cb, tid);
+        if (tid < n_tab) s_wc[0][tid] = table_cta_const(tables, tid, cb | pd.rank_bits);
+    }
+    int buf = 0;
+    for (; t < n_tiles; t += gridDim.x, buf ^= 1) {
+        cplx a[NREG];
+        cp_async_wait_all();
+        __syncthreads();               // s_wc[buf] is visible; nobody still reads the previous tile's transposes
+        if (zero_in) tile_zero_input(a, pd, t, tid);
+        else stage_load<IO_GROUP>(tile, a, tid);
+        const unsigned tn = t + gridDim.x;
+        const uint64_t gbase = cta_base_runs(pd, (uint64_t)t) | pd.rank_bits;
+        const cplx* wcs = s_wc[buf];
+        if (last_switch < 0 && tn < n_tiles) {   // no transpose in this pass: the tile buffer is free right away
+            __syncthreads();
+            const uint64_t cb = cta_base_runs(pd, (uint64_t)tn);
+            if (!zero_in) tile_prefetch<IO_GROUP>(tile, amp, pd, cb, tid);
+            if (tid < n_tab) s_wc[buf ^ 1][tid] = table_cta_const(tables, tid, cb | pd.rank_bits);
+        }
+        ThreadCtx ctx;
+        ctx.pidx = gbase | tid_offset(pd, IO_GROUP, tid);
+        ctx.ph = cplx{1.0, 0.0};
+        ctx.ph_dirty = false;
+        ctx.tid = tid;
+        for (int k = 0; k < n_ops; ++k) {
+            const DevOp& op = pp.ops[k];
+            const int code = op.code;
+            if (code >= OC_SWITCH) {
+                const int from = (code - OC_SWITCH) / NGROUPS, to = (code - OC_SWITCH) % NGROUPS;
+                flush_phase(a, ctx);
+                __syncthreads();
+                if (from == 0) switch_store<0>(tile, a, tid, op, gbase);
+                else if (from == 1) switch_store<1>(tile, a, tid, op, gbase);
+                else switch_store<2>(tile, a, tid, op, gbase);
+                __syncthreads();
+                if (to == 0) stage_load<0>(tile, a, tid);
+                else if (to == 1) stage_load<1>(tile, a, tid);
+                else stage_load<2>(tile, a, tid);
+                ctx.pidx = gbase | tid_offset(pd, to, tid);
+                if (k == last_switch && tn < n_tiles) {
+                    __syncthreads();   // every thread has read its registers back: the tile buffer is free
+                    const uint64_t cb = cta_base_runs(pd, (uint64_t)tn);
+                    if (!zero_in) tile_prefetch<IO_GROUP>(tile, amp, pd, cb, tid);
+                    if (tid < n_tab) s_wc[buf ^ 1][tid] = table_cta_const(tables, tid, cb | pd.rank_bits);
+                }
+                continue;
+            }
+            k += apply_op<SET>(a, &op, code, ctx, tables, n_tab, wcs);
+        }
+        flush_phase(a, ctx);
+        if (pd.io_out == IO_GROUP) tile_store<IO_GROUP>(amp, pd, a, gbase - pd.rank_bits);
+        else tile_store<1>(amp, pd, a, gbase - pd.rank_bits);
+    }
 }
 
 // =================================================================================================
@@ -470,33 +582,52 @@ constexpr unsigned V_FOURIER = C_HAD | C_DIAG | C_TABLE | C_MACRO_T;            
 constexpr unsigned V_COMMON = C_GENERAL | C_REAL | C_RX | C_HAD | C_DIAG | C_TABLE;  // everything but rare ops / macros
 constexpr unsigned VARIANTS[] = {V_LAYERED, V_FOURIER, V_COMMON, C_ALL};
 typedef void (*TileKernel)(cplx*, const PassParams);
-static TileKernel tile_kernel(int v) {
+static TileKernel tile_kernel(int v, bool persist) {
     switch (v) {
-        case 0: return k_tile_pass<V_LAYERED>;
-        case 1: return k_tile_pass<V_FOURIER>;
-        case 2: return k_tile_pass<V_COMMON>;
-        default: return k_tile_pass<C_ALL>;
+        case 0: return persist ? k_tile_pass_persist<V_LAYERED> : k_tile_pass<V_LAYERED>;
+        case 1: return persist ? k_tile_pass_persist<V_FOURIER> : k_tile_pass<V_FOURIER>;
+        case 2: return persist ? k_tile_pass_persist<V_COMMON> : k_tile_pass<V_COMMON>;
+        default: return persist ? k_tile_pass_persist<C_ALL> : k_tile_pass<C_ALL>;
     }
 }
 
+static int g_sm_count = 148;
+static int g_persist = 0;     // DVD_PERSIST: 0 = one tile per CTA, 1 = persistent CTAs with cp.async prefetch
+static int g_persist_ctas_per_sm = 2;
+
 cudaError_t kernels_init() {
-    for (int v = 0; v < 4; ++v) {
-        cudaError_t e = cudaFuncSetAttribute(tile_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             TILE_SLOTS * (int)sizeof(cplx));
-        if (e != cudaSuccess) return e;
-    }
+    for (int p = 0; p < 2; ++p)
+        for (int v = 0; v < 4; ++v) {
+            cudaError_t e = cudaFuncSetAttribute(tile_kernel(v, p != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 TILE_SLOTS * (int)sizeof(cplx));
+            if (e != cudaSuccess) return e;
+        }
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+        g_sm_count = sms;
+    if (const char* e = getenv("DVD_PERSIST")) g_persist = atoi(e) != 0;
+    if (const char* e = getenv("DVD_PERSIST_CTAS")) g_persist_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 2;
     return cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 SAMPLE_WARPS * (2 << BLK_BITS) * (int)sizeof(double));
 }
 
-cudaError_t launch_tile_pass(cplx* amp, const PassParams& pp, cudaStream_t s) {
+cudaError_t launch_tile_pass(cplx* amp, PassParams& pp, cudaStream_t s) {
     const uint64_t ctas = 1ull << (pp.pd.n_local - TILE_BITS);
     unsigned need = 0;
-    for (int k = 0; k < pp.pd.n_ops; ++k) need |= op_class(pp.ops[k].code);
+    int last_switch = -1;
+    for (int k = 0; k < pp.pd.n_ops; ++k) {
+        need |= op_class(pp.ops[k].code);
+        if (pp.ops[k].code >= OC_SWITCH) last_switch = k;
+    }
+    pp.pd.last_switch = (int16_t)last_switch;
     int v = 0;
     while (v < 3 && (need & ~VARIANTS[v])) ++v;
     if (const char* e = getenv("DVD_KERNEL_VARIANT")) v = atoi(e) & 3;   // development: force a variant (3 = all ops)
-    tile_kernel(v)<<<(unsigned)ctas, NTHREADS, TILE_SLOTS * sizeof(cplx), s>>>(amp, pp);
+    const uint64_t resident = (uint64_t)g_sm_count * g_persist_ctas_per_sm;
+    if (g_persist && ctas > resident)
+        tile_kernel(v, true)<<<(unsigned)resident, NTHREADS, TILE_SLOTS * sizeof(cplx), s>>>(amp, pp);
+    else
+        tile_kernel(v, false)<<<(unsigned)ctas, NTHREADS, TILE_SLOTS * sizeof(cplx), s>>>(amp, pp);
     return cudaGetLastError();
 }
 

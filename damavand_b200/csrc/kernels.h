@@ -12,7 +12,7 @@ constexpr int BLK_BITS = 10;  // sampler / reduction leaf block: 2^10 amplitudes
 cudaError_t kernels_init();   // one-time function attributes (dynamic shared memory opt-in)
 
 // Tiled multi-gate pass (n_local >= TILE_BITS).  pp (description + op list) travels as the kernel parameter.
-cudaError_t launch_tile_pass(cplx* amp, const PassParams& pp, cudaStream_t s);
+cudaError_t launch_tile_pass(cplx* amp, PassParams& pp, cudaStream_t s);   // fills pp.pd.last_switch
 
 // One gate, one pass, any size (used when n_local < TILE_BITS, and as the un-fused debug path).
 struct SimpleOp { double m[8]; int32_t tbit; int32_t cbit; };   // cbit < 0: no control

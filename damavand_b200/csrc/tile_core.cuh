@@ -17,6 +17,7 @@
 // and emits it as byte-indexed phase tables (thread-level bits), per-register-bit factors and
 // register-pair factors, at the latest point the commutation rules allow.
 #pragma once
+#include <math.h>
 #include <stdint.h>
 
 #ifdef __CUDACC__
@@ -168,6 +169,9 @@ struct PassDesc {
     int8_t run_src[TILE_BITS + 1];    //   land at bit position dst of the physical index
     int8_t run_len[TILE_BITS + 1];
     int8_t run_dst[TILE_BITS + 1];
+    // Set by the engine / launcher, not by the planner:
+    int8_t zero_input;            // the state is |0..0> (lazy reset): the pass synthesises its input instead of loading it
+    int16_t last_switch;          // index of the last OC_SWITCH in ops (-1: none); after it the shared-memory tile is free
 };
 // Kernel parameter block: the pass description and its whole op list (<= 32764 B of parameters).
 constexpr int MAX_OPS_PER_PASS = 336;
@@ -267,8 +271,11 @@ template <int KIND>
 DVD_HD void pair_update(cplx& a0, cplx& a1, const double (&m)[8]) {
     const cplx x = a0, y = a1;
     if (KIND == K_HADAMARD) {        // the common factor h is folded into the pass constant by the planner
+        // in place, no temporary: a1 = (x + y) - 2y with one rounding in the fma.  |error| <= 2^-53 (|x+y| + |x-y|),
+        // and the register-to-register moves that the x - y form needs at every butterfly (14 % of the
+        // instructions of a Fourier pass, profiles/r1_ncu_mix_qft30_v8.txt) disappear
         a0 = cplx{x.x + y.x, x.y + y.y};
-        a1 = cplx{x.x - y.x, x.y - y.y};
+        a1 = cplx{fma(-2.0, y.x, a0.x), fma(-2.0, y.y, a0.y)};
     } else if (KIND == K_REALPH) {   // real rows, then row 1 times w = (m[1], m[3])
         a0 = cplx{x.x * m[0] + y.x * m[2], x.y * m[0] + y.y * m[2]};
         const cplx t{x.x * m[4] + y.x * m[6], x.y * m[4] + y.y * m[6]};

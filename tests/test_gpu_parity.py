@@ -268,3 +268,66 @@ def test_large_state_properties(name, n):
         scale = 2.0 ** (-n / 2)
         assert np.abs((ra - rb) + 1j * (ia - ib)).max() < 1e-12 * max(scale, np.abs(ra + 1j * ia).max())
     assert np.abs(ez - b.expectation_z()).max() < 1e-11
+
+
+@pytest.fixture
+def env(monkeypatch):
+    """Engine knobs are read when a state is created (dvd_create -> kernels_init)."""
+    def set_(**kw):
+        for k, v in kw.items():
+            monkeypatch.setenv(k, str(v))
+    return set_
+
+
+@pytest.mark.parametrize("kind,n,persist,lazy", [
+    ("random", 21, 1, 1), ("random", 21, 1, 0), ("random", 21, 0, 1), ("random", 21, 0, 0),
+    ("qft", 21, 1, 1), ("qft", 21, 0, 1), ("hea", 21, 1, 1), ("layered", 21, 1, 0)])
+def test_kernel_forms_agree_with_oracle(env, kind, n, persist, lazy):
+    """Persistent (cp.async prefetch) and one-tile-per-CTA forms of the pass, with and without the lazy
+    |0..0> input, against the oracle (2^21 amplitudes so that the persistent form really loops)."""
+    env(DVD_PERSIST=persist, DVD_LAZY_ZERO=lazy)
+    build = {"random": lambda c: circuits.random_circuit(c, n, 120, 21),
+             "qft": lambda c: circuits.qft_like(c, n),
+             "hea": lambda c: circuits.hea(c, n, 2),
+             "layered": lambda c: circuits.layered(c, n, 2)}[kind]
+    g, o = both(n, build)
+    assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
+    if kind == "random":   # a second forward starts from a non-zero state (no lazy input)
+        g.forward(); o.forward()
+        assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
+    g.reset_amplitudes(); g.forward()   # reset + forward reproduces the first result bit for bit
+    first = o.amplitudes() if kind != "random" else None
+    if first is not None:
+        assert rel_err(g.state_numpy(), first) < TOL
+
+
+def test_lazy_reset_observation_points(env):
+    """reset_amplitudes() only marks the state as |0..0>; every observation must still see it."""
+    import ctypes
+    env(DVD_LAZY_ZERO=1)
+    n = 14
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    g = gpu_circuit(n)
+    p = g.measure_numpy()
+    assert p[0] == 1.0 and p.sum() == 1.0
+    assert g.norm() == 1.0
+    assert g.sample(5, uniforms=[0.0, 0.3, 0.5, 0.9, 1.0 - 2 ** -53]) == [0] * 5
+    assert list(g.expectation_z()) == [1.0] * n
+    g.add_hadamard_gate(13); g.forward()
+    g.reset_amplitudes()
+    z = g.state_numpy()
+    assert z[0] == 1.0 and np.abs(z[1:]).max() == 0.0
+    g.reset_amplitudes()
+    re, im = np.full(16, 0.25), np.zeros(16)
+    from damavand_b200._lib import check as _check
+    _check(g._lib.dvd_load_state(g._handle, dp(re), dp(im), 32, 16), "load")   # partial load after a lazy reset
+    z = g.state_numpy()
+    assert z[0] == 1.0 and (z[32:48] == 0.25).all() and np.abs(z[48:]).max() == 0.0 and np.abs(z[1:32]).max() == 0.0
+    # two fresh states: <0|0> = 1
+    a, b = gpu_circuit(n), gpu_circuit(n)
+    f = ctypes.c_double()
+    _check(a._lib.dvd_fidelity(a._handle, b._handle, ctypes.byref(f)), "fidelity")
+    assert f.value == 1.0
+    # unfused mode after a lazy reset goes through the one-gate kernel on a materialised state
+    c = gpu_circuit(n); c.set_unfused(True); c.add_pauli_x_gate(7, False); c.forward()
+    assert c.measure_numpy()[1 << 7] == 1.0
