@@ -118,10 +118,13 @@ def workload_desc(name):
 # --------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle's restatement of the reference `multithreading` method on a bounded sample
 # --------------------------------------------------------------------------------------------------
+CPU_MAX_QUBITS = 30   # 16 GiB state + 16 GiB clone, ~1.5 s per gate: keeps a CPU step of 2 gates at a few seconds
+
+
 def cpu_sample_gates(name: str, n: int, mem_gib: float):
-    """Pick the qubit count the host can hold (state + clone = 32 B/amp) and the gates per step."""
-    need = 32.0 * (1 << n) / 2**30
-    n_cpu = n
+    """Qubit count of the CPU sample: what the host can hold (state + clone = 32 B/amp), at most CPU_MAX_QUBITS."""
+    n_cpu = min(n, CPU_MAX_QUBITS)
+    need = 32.0 * (1 << n_cpu) / 2**30
     while need + 4 > mem_gib and n_cpu > 20:
         n_cpu -= 1
         need /= 2
@@ -169,11 +172,15 @@ def run_cpu(name: str, steps: int, warmup: int, gates_per_step: int):
         if s >= warmup:
             times.append(dt)
     sec = float(np.sum(times))
-    gps = steps * gates_per_step / sec
-    scale = "" if n_cpu == n else f" at {n_cpu} qubits (host RAM cannot hold the {n}-qubit state + clone)"
-    desc = (f"{steps} steps x {gates_per_step} consecutive gates of the {name} circuit{scale}, "
+    # the CPU path streams the whole state once per gate (clone + update), so its cost per gate is proportional to
+    # 2^n: a sample taken at n_cpu < n qubits is scaled by 2^(n_cpu - n) to the workload's size and labelled so
+    factor = 2.0 ** (n_cpu - n)
+    gps = steps * gates_per_step / sec * factor
+    scale = "" if n_cpu == n else (f", timed at {n_cpu} qubits (same generator) and scaled by 2^{n_cpu - n} to {n} qubits: "
+                                   f"the per-gate cost of clone + update is linear in the state size")
+    desc = (f"{steps} steps x {gates_per_step} consecutive gates of the {name} circuit{scale}; "
             f"oracle port of circuit_multithreading.rs:9-54 (clone + per-amplitude update), OpenMP {cores} threads")
-    return gps, sec / steps, desc, cores, n_cpu
+    return gps, sec / steps / factor, desc, cores, n_cpu
 
 
 def reference_arm(args):

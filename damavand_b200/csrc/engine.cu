@@ -175,6 +175,7 @@ static int create_common(int n_qubits, int device, int rank, int world, const vo
     if (const char* e = getenv("DVD_PLAN_CANDIDATES")) s->opt.candidates = std::max(1, atoi(e));
     if (const char* e = getenv("DVD_MACRO_OPS")) s->opt.macro_ops = atoi(e) != 0;
     if (const char* e = getenv("DVD_LAZY_ZERO")) s->lazy_zero = atoi(e) != 0;
+    if (const char* e = getenv("DVD_BEST_GROUP")) s->opt.best_group = atoi(e) != 0;
     s->perm.resize(n_qubits);
     for (int q = 0; q < n_qubits; ++q) s->perm[q] = q;
     auto cleanup = [&](int code) { dvd_destroy(s); return code; };
@@ -757,6 +758,8 @@ static std::vector<HostGate> to_host_gates(const dvd_gate* gates, int64_t n) {
 int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates, int fuse, int32_t* out, int64_t cap) {
     try {
         PlanOptions opt;
+        if (const char* e = getenv("DVD_BEST_GROUP")) opt.best_group = atoi(e) != 0;
+        if (const char* e = getenv("DVD_PLAN_CANDIDATES")) opt.candidates = std::max(1, atoi(e));
         std::vector<Pass> passes = plan_local(fuse ? fuse_diagonal_runs(to_host_gates(gates, n_gates)) : to_host_gates(gates, n_gates), n_local, n_total, opt);
         std::vector<int32_t> v;
         v.push_back((int32_t)passes.size());
