@@ -35,6 +35,7 @@ class Stats(ctypes.Structure):
         ("swap_bytes_sent", ctypes.c_int64),
         ("pass_bytes", ctypes.c_double),
         ("gate_algorithmic_bytes", ctypes.c_double),
+        ("plan_cache_hits", ctypes.c_int64),
     ]
 
     def as_dict(self):

@@ -66,6 +66,7 @@ class Circuit:
         self.apply_method = method
         self.gates: List[list] = []        # [name, target, control, parameter]
         self.observables: List[int] = []
+        self._gate_cache = None            # (contents key, marshalled dvd_gate array) of the last forward
         self._handle = ctypes.c_void_p()
         self._profilers = {k: _Profiler() for k in ("forward", "inter_node", "inter_gpu", "sampling")}
         if self._lib.dvd_device_count() == 0:
@@ -169,11 +170,17 @@ class Circuit:
     def _gate_array(self):
         obs = set(self.observables)
         todo = [g for i, g in enumerate(self.gates) if i not in obs]     # :347-349
+        # `gates` / `observables` are public lists (the reference's fields): the marshalled array is reused only
+        # while their contents are unchanged
+        key = tuple(tuple(g) for g in todo)
+        if self._gate_cache is not None and self._gate_cache[0] == key:
+            return self._gate_cache[1], len(todo)
         arr = (_lib.Gate * max(1, len(todo)))()
         for k, (name, t, c, p) in enumerate(todo):
             arr[k].target = t
             arr[k].control = -1 if c is None else c
             arr[k].m[:] = gates.matrix(name, p)
+        self._gate_cache = (key, arr)
         return arr, len(todo)
 
     def forward(self):

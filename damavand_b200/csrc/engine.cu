@@ -75,6 +75,16 @@ struct dvd_state {
     // input (no memset, no read), anything else materialises it first
     bool zero_pending = false;
     bool lazy_zero = true;
+    // last plan, reused when the same gate list is flushed again (sampling loops re-run one circuit):
+    // key = the queued gates, bit for bit, plus the mode they were planned in
+    struct PlanCache {
+        std::vector<uint64_t> key;
+        std::vector<DistStep> steps;
+        std::vector<std::vector<Pass>> plans;
+        size_t total_tabs = 0;
+        bool valid = false;
+    } cache;
+    bool plan_cache = true;
     PlanOptions opt;
 };
 
@@ -176,6 +186,7 @@ static int create_common(int n_qubits, int device, int rank, int world, const vo
     if (const char* e = getenv("DVD_MACRO_OPS")) s->opt.macro_ops = atoi(e) != 0;
     if (const char* e = getenv("DVD_LAZY_ZERO")) s->lazy_zero = atoi(e) != 0;
     if (const char* e = getenv("DVD_BEST_GROUP")) s->opt.best_group = atoi(e) != 0;
+    if (const char* e = getenv("DVD_PLAN_CACHE")) s->plan_cache = atoi(e) != 0;
     s->perm.resize(n_qubits);
     for (int q = 0; q < n_qubits; ++q) s->perm[q] = q;
     auto cleanup = [&](int code) { dvd_destroy(s); return code; };
@@ -402,39 +413,66 @@ static int global_swap(dvd_state* s, int gq, int lq) {
 static int flush_impl(dvd_state* s) {
     if (s->pending.empty()) return DVD_OK;
     CU(cudaSetDevice(s->device));
-    std::vector<DistStep> steps;
     const bool tiled = !s->unfused && s->n_local >= TILE_BITS;
     const double chunk_bytes = (double)s->n_amps * 16.0;
     for (const HostGate& g : s->pending) {
         s->stats.gates_applied++;
         s->stats.gate_algorithmic_bytes += (g.cmask ? 1.0 : 2.0) * chunk_bytes;
     }
-    try {
-        // level 0 (fused mode only): CNOT-conjugated diagonal runs -> parity phases
-        const std::vector<HostGate> fused = tiled ? fuse_diagonal_runs(s->pending) : s->pending;
-        if (s->world > 1) {
-            steps = plan_distributed(fused, s->n_qubits, s->n_local, s->perm, /*restore_identity=*/true);
-        } else {
-            DistStep st; st.kind = DistStep::LOCAL_GATES; st.gates = fused;
-            steps.push_back(std::move(st));
+    // plan cache key: every field the planners read
+    std::vector<uint64_t> key;
+    if (s->plan_cache) {
+        key.reserve(s->pending.size() * 11 + 2);
+        key.push_back(tiled ? 1 : 0);
+        key.push_back((uint64_t)s->pending.size());
+        for (const HostGate& g : s->pending) {
+            key.push_back(g.tmask); key.push_back(g.cmask ^ (g.diag ? 1ull << 63 : 0));
+            for (int k = 0; k < 8; ++k) { uint64_t b; std::memcpy(&b, &g.m[k], 8); key.push_back(b); }
+            key.push_back((uint64_t)(int64_t)g.gate_idx);
         }
-    } catch (const std::exception& e) {
-        return fail(DVD_ERR_INTERNAL, std::string("planner: ") + e.what());
     }
-    // plan every local step up front so that all phase tables go to the device in one copy; the op
-    // lists travel as kernel parameters
-    std::vector<std::vector<Pass>> plans(steps.size());
-    size_t total_tabs = 0;
-    if (tiled) {
+    const bool hit = s->plan_cache && s->cache.valid && s->cache.key == key;
+    if (hit) s->stats.plan_cache_hits++;
+    if (!hit) {
+        s->cache.valid = false;
+        std::vector<DistStep> steps;
         try {
-            for (size_t i = 0; i < steps.size(); ++i)
-                if (steps[i].kind == DistStep::LOCAL_GATES) {
-                    plans[i] = plan_local(steps[i].gates, s->n_local, s->n_qubits, s->opt);
-                    for (auto& p : plans[i]) total_tabs += p.tables.size();
-                }
+            // level 0 (fused mode only): CNOT-conjugated diagonal runs -> parity phases
+            const std::vector<HostGate> fused = tiled ? fuse_diagonal_runs(s->pending) : s->pending;
+            if (s->world > 1) {
+                steps = plan_distributed(fused, s->n_qubits, s->n_local, s->perm, /*restore_identity=*/true);
+            } else {
+                DistStep st; st.kind = DistStep::LOCAL_GATES; st.gates = fused;
+                steps.push_back(std::move(st));
+            }
         } catch (const std::exception& e) {
             return fail(DVD_ERR_INTERNAL, std::string("planner: ") + e.what());
         }
+        // plan every local step up front so that all phase tables go to the device in one copy; the op
+        // lists travel as kernel parameters
+        std::vector<std::vector<Pass>> plans(steps.size());
+        size_t total_tabs = 0;
+        if (tiled) {
+            try {
+                for (size_t i = 0; i < steps.size(); ++i)
+                    if (steps[i].kind == DistStep::LOCAL_GATES) {
+                        plans[i] = plan_local(steps[i].gates, s->n_local, s->n_qubits, s->opt);
+                        for (auto& p : plans[i]) total_tabs += p.tables.size();
+                    }
+            } catch (const std::exception& e) {
+                return fail(DVD_ERR_INTERNAL, std::string("planner: ") + e.what());
+            }
+        }
+        s->cache.steps = std::move(steps);
+        s->cache.plans = std::move(plans);
+        s->cache.total_tabs = total_tabs;
+        s->cache.key = std::move(key);
+        s->cache.valid = s->plan_cache;
+    }
+    std::vector<DistStep>& steps = s->cache.steps;
+    std::vector<std::vector<Pass>>& plans = s->cache.plans;
+    const size_t total_tabs = s->cache.total_tabs;
+    if (tiled) {
         if (total_tabs) {
             dvd_state::TabSet& ts = s->tabs[s->n_flushes & 1];
             if (!ts.done) CU(cudaEventCreateWithFlags(&ts.done, cudaEventDisableTiming));

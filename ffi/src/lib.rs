@@ -28,6 +28,7 @@ pub struct dvd_stats {
     pub swap_bytes_sent: i64,
     pub pass_bytes: c_double,
     pub gate_algorithmic_bytes: c_double,
+    pub plan_cache_hits: i64,
 }
 
 pub const DVD_NCCL_ID_BYTES: usize = 128;

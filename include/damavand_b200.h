@@ -122,8 +122,10 @@ typedef struct {
     int64_t stage_switches;
     int64_t global_swaps;         /* global<->local qubit swaps (NVLink exchanges) */
     int64_t swap_bytes_sent;      /* per rank */
-    double pass_bytes;            /* HBM bytes the gate passes must move: 32 * 2^n_local per pass */
+    double pass_bytes;            /* HBM bytes the gate passes must move: 32 * 2^n_local per pass (16 * 2^n_local for
+                                     the first pass after a reset, which does not read) */
     double gate_algorithmic_bytes;/* sum over gates of 32*2^n_local (16*2^n_local if controlled) */
+    int64_t plan_cache_hits;      /* flushes that reused the previous plan (identical gate list) */
 } dvd_stats;
 int dvd_get_stats(const dvd_state* s, dvd_stats* out);
 int dvd_stats_reset(dvd_state* s);

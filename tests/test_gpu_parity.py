@@ -331,3 +331,20 @@ def test_lazy_reset_observation_points(env):
     # unfused mode after a lazy reset goes through the one-gate kernel on a materialised state
     c = gpu_circuit(n); c.set_unfused(True); c.add_pauli_x_gate(7, False); c.forward()
     assert c.measure_numpy()[1 << 7] == 1.0
+
+
+def test_plan_cache_reuses_only_identical_gate_lists():
+    n = 14
+    g = gpu_circuit(n); o = OracleCircuit(n)
+    for c in (g, o):
+        circuits.hea(c, n, 2)
+    g.forward(); o.forward()
+    assert g.stats()["plan_cache_hits"] == 0
+    g.reset_amplitudes(); g.forward()                      # same gates: the plan and the marshalled array are reused
+    assert g.stats()["plan_cache_hits"] == 1
+    assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
+    params = [0.01 * i for i in range(2 * n * 2)]
+    for c in (g, o):
+        c.set_parameters(params); c.reset_amplitudes(); c.forward()
+    assert g.stats()["plan_cache_hits"] == 1               # new angles: planned again
+    assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
