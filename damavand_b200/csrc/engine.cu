@@ -71,10 +71,13 @@ struct dvd_state {
     double* d_bar = nullptr;
     dvd_stats stats;
     bool unfused = false;
-    // lazy reset: the state is |0..0> but the buffer has not been written; the next tile pass synthesises its
-    // input (no memset, no read), anything else materialises it first
-    bool zero_pending = false;
+    // Support tracking: after a reset only amplitude 0 is stored; `support` holds the local qubits that a
+    // non-diagonal gate has touched since.  Amplitudes with a bit outside `support` set are zero by construction
+    // (and their memory is unwritten): tile passes neither read them nor launch the tiles that consist of them,
+    // and anything else that looks at the buffer materialises the zeros first.
+    uint64_t support = ~0ull;     // all ones = dense (nothing implied)
     bool lazy_zero = true;
+    uint64_t zero_mask() const { return ~support & (n_amps - 1); }
     // last plan, reused when the same gate list is flushed again (sampling loops re-run one circuit):
     // key = the queued gates, bit for bit, plus the mode they were planned in
     struct PlanCache {
@@ -97,23 +100,29 @@ static int ensure_scratch(dvd_state* s, size_t doubles) {
     return DVD_OK;
 }
 
-static int write_zero_state(dvd_state* s) {
-    CU(cudaMemsetAsync(s->amp, 0, s->n_amps * sizeof(cplx), s->stream));
-    if (s->rank == 0) {   // amplitude 0 lives on the first rank (circuit.rs:168-170, kernels.cu:62-81)
-        CU(launch_set_basis_state(s->amp, 0, s->stream));
-        s->stats.kernel_launches++;
-    }
-    s->zero_pending = false;
-    return DVD_OK;
-}
-// Reset to |0..0>.  When the next thing to touch the state is a tile pass, that pass writes every amplitude
-// anyway: it starts from zeros in registers and the 16 B/amplitude memset plus the pass's own read are saved.
+// Reset to |0..0>: amplitude 0 lives on the first rank (circuit.rs:168-170, kernels.cu:62-81).  With support
+// tracking only that one amplitude is written (16 B instead of 16 B per amplitude).
 static int set_zero_state(dvd_state* s) {
     s->tree_valid = false;
-    if (s->lazy_zero && !s->unfused && s->n_local >= TILE_BITS) { s->zero_pending = true; return DVD_OK; }
-    return write_zero_state(s);
+    if (s->lazy_zero && !s->unfused && s->n_local >= TILE_BITS) {
+        s->support = ~(s->n_amps - 1);    // no local qubit touched yet; rank-index bits always count as touched
+    } else {
+        CU(cudaMemsetAsync(s->amp, 0, s->n_amps * sizeof(cplx), s->stream));
+        s->support = ~0ull;
+    }
+    CU(launch_set_basis_state(s->amp, 0, s->rank == 0 ? 1.0 : 0.0, s->stream));
+    s->stats.kernel_launches++;
+    return DVD_OK;
 }
-static int materialize(dvd_state* s) { return s->zero_pending ? write_zero_state(s) : DVD_OK; }
+// Store the zeros that support tracking implied (no-op once every local qubit has been touched).
+static int materialize(dvd_state* s) {
+    const uint64_t zm = s->zero_mask();
+    if (zm == 0) return DVD_OK;
+    CU(launch_zero_outside_support(s->amp, s->n_local, zm, s->stream));
+    s->stats.kernel_launches++;
+    s->support = ~0ull;
+    return DVD_OK;
+}
 
 // Stream-ordered barrier over all ranks: a one-element allreduce completes on a rank only after every
 // rank's stream has reached it, i.e. after all earlier kernels on every rank's stream have finished.
@@ -505,7 +514,16 @@ static int flush_impl(dvd_state* s) {
                 PassParams& pp = s->pass_params;
                 pp.pd = p.desc;
                 pp.pd.rank_bits = s->rank_bits;
-                pp.pd.zero_input = s->zero_pending ? 1 : 0;
+                // support tracking: implied zeros are not read, all-zero tiles are not launched
+                const uint64_t zm = s->zero_mask();
+                pp.pd.zero_mask = zm;
+                uint64_t tile_mask = 0;
+                for (int k = 0; k < TILE_BITS; ++k) tile_mask |= 1ull << pp.pd.tile_q[k];
+                int zregs = 0;
+                for (int k = 0; k < REG_BITS; ++k)
+                    if ((zm >> pp.pd.tile_q[IO_GROUP * REG_BITS + k]) & 1ull) zregs |= 1 << k;
+                pp.pd.zero_regbits = (int8_t)zregs;
+                if (zm & ~tile_mask) fill_cta_runs_sparse(pp.pd, zm & ~tile_mask);   // on failure the full grid stays
                 pp.pd.tables = d_tabs + tat;
                 pp.pd.tid_off = reinterpret_cast<const uint64_t*>(d_tabs + tat + p.tid_off_slot);
                 std::memcpy(pp.ops, p.ops.data(), p.ops.size() * sizeof(DevOp));
@@ -513,8 +531,11 @@ static int flush_impl(dvd_state* s) {
                 tat += p.tables.size();
                 s->stats.kernel_launches++; s->stats.tile_passes++;
                 s->stats.stage_switches += p.n_switches;
-                s->stats.pass_bytes += (s->zero_pending ? 1.0 : 2.0) * chunk_bytes;
-                s->zero_pending = false;
+                {   // HBM bytes this launch moves: its tiles are written in full, read where the input can be non-zero
+                    const double tiles_bytes = (double)(1ull << pp.pd.n_cta_bits) * TILE_AMPS * sizeof(cplx);
+                    s->stats.pass_bytes += tiles_bytes * (1.0 + 1.0 / (double)(1ull << __builtin_popcountll(zm & tile_mask)));
+                }
+                s->support |= p.touch_mask;
             }
         } else {
             TRY(materialize(s));
@@ -740,7 +761,7 @@ int dvd_copy_state(dvd_state* dst, dvd_state* src) {
     CU(cudaStreamSynchronize(src->stream));
     CU(cudaMemcpyAsync(dst->amp, src->amp, src->n_amps * sizeof(cplx), cudaMemcpyDeviceToDevice, dst->stream));
     dst->tree_valid = false;
-    dst->zero_pending = false;
+    dst->support = ~0ull;
     return DVD_OK;
 }
 

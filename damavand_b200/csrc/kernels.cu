@@ -79,13 +79,6 @@ __device__ __forceinline__ void tile_store(cplx* amp, const PassDesc& pd, const 
         st_stream(io.p0 + off, a[j]);
     }
 }
-// |0..0> as the pass input (lazy reset): amplitude 0 lives in register 0 of thread 0 of tile 0 on rank 0.
-__device__ __forceinline__ void tile_zero_input(cplx (&a)[NREG], const PassDesc& pd, unsigned tile_id, int tid) {
-#pragma unroll
-    for (int j = 0; j < NREG; ++j) a[j] = cplx{0.0, 0.0};
-    if (tile_id == 0 && tid == 0 && pd.rank_bits == 0) a[0].x = 1.0;
-}
-
 // Asynchronous global -> shared copies (LDGSTS): the next tile travels while the current one is computed on.
 __device__ __forceinline__ void cp_async16(cplx* smem_dst, const cplx* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -134,17 +127,22 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     // byte tables only see index bits outside the tile: one constant per CTA and table op.  The two dependent
     // lookups start before the tile's own loads queue up in front of them.
     if (tid < n_tab) s_wc[tid] = table_cta_const(tables, tid, gbase);
+    // Support tracking (PassDesc::zero_mask): amplitudes with a bit of zero_mask set are zero by construction and
+    // their memory is never read (after a reset it has not even been written).  A tile whose fixed bits hit the
+    // mask is all zero on input, hence on output: nothing to do (the engine normally does not launch those).
+    const uint64_t zmask = pd.zero_mask;
+    if (cbase & zmask) return;
     cplx a[NREG];
-    if (pd.zero_input) {
-        tile_zero_input(a, pd, blockIdx.x, tid);
-    } else {
+    {
         const IoAddr io = io_addr<IO_GROUP>(amp, pd, cbase);
+        const bool thread_zero = (tid_offset(pd, IO_GROUP, tid) & zmask) != 0;
+        const int zregs = pd.zero_regbits;
 #pragma unroll
         for (int j = 0; j < NREG; ++j) {
             uint64_t off = 0;
 #pragma unroll
             for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += io.hs[k];
-            a[j] = ld_stream(io.p0 + off);
+            a[j] = (thread_zero || (j & zregs)) ? cplx{0.0, 0.0} : ld_stream(io.p0 + off);
         }
     }
 
@@ -197,17 +195,16 @@ k_tile_pass_persist(cplx* __restrict__ amp, const __grid_constant__ PassParams p
     __shared__ cplx s_wc[2][MAX_TABLE_OPS];
     const PassDesc& pd = pp.pd;
     const int tid = threadIdx.x;
-    const unsigned n_tiles = 1u << (pd.n_local - TILE_BITS);
+    const unsigned n_tiles = 1u << pd.n_cta_bits;   // launched for dense states only (zero_mask == 0)
     const cplx* __restrict__ tables = pd.tables;
     const int n_tab = pd.n_tab;
     const int n_ops = pd.n_ops;
     const int last_switch = pd.last_switch;
-    const bool zero_in = pd.zero_input != 0;
     unsigned t = blockIdx.x;
     if (t >= n_tiles) return;
     {
         const uint64_t cb = cta_base_runs(pd, (uint64_t)t);
-        if (!zero_in) tile_prefetch<IO_GROUP>(tile, amp, pd, cb, tid);
+        tile_prefetch<IO_GROUP>(tile, amp, pd, cb, tid);
         if (tid < n_tab) s_wc[0][tid] = table_cta_const(tables, tid, cb | pd.rank_bits);
     }
     int buf = 0;
@@ -215,15 +212,14 @@ k_tile_pass_persist(cplx* __restrict__ amp, const __grid_constant__ PassParams p
         cplx a[NREG];
         cp_async_wait_all();
         __syncthreads();               // s_wc[buf] is visible; nobody still reads the previous tile's transposes
-        if (zero_in) tile_zero_input(a, pd, t, tid);
-        else stage_load<IO_GROUP>(tile, a, tid);
+        stage_load<IO_GROUP>(tile, a, tid);
         const unsigned tn = t + gridDim.x;
         const uint64_t gbase = cta_base_runs(pd, (uint64_t)t) | pd.rank_bits;
         const cplx* wcs = s_wc[buf];
         if (last_switch < 0 && tn < n_tiles) {   // no transpose in this pass: the tile buffer is free right away
             __syncthreads();
             const uint64_t cb = cta_base_runs(pd, (uint64_t)tn);
-            if (!zero_in) tile_prefetch<IO_GROUP>(tile, amp, pd, cb, tid);
+            tile_prefetch<IO_GROUP>(tile, amp, pd, cb, tid);
             if (tid < n_tab) s_wc[buf ^ 1][tid] = table_cta_const(tables, tid, cb | pd.rank_bits);
         }
         ThreadCtx ctx;
@@ -249,7 +245,7 @@ k_tile_pass_persist(cplx* __restrict__ amp, const __grid_constant__ PassParams p
                 if (k == last_switch && tn < n_tiles) {
                     __syncthreads();   // every thread has read its registers back: the tile buffer is free
                     const uint64_t cb = cta_base_runs(pd, (uint64_t)tn);
-                    if (!zero_in) tile_prefetch<IO_GROUP>(tile, amp, pd, cb, tid);
+                    tile_prefetch<IO_GROUP>(tile, amp, pd, cb, tid);
                     if (tid < n_tab) s_wc[buf ^ 1][tid] = table_cta_const(tables, tid, cb | pd.rank_bits);
                 }
                 continue;
@@ -296,7 +292,15 @@ k_simple_gate(cplx* __restrict__ amp, int n_local, uint64_t rank_bits, const __g
     }
 }
 
-__global__ void k_set_basis_state(cplx* amp, uint64_t index) { amp[index] = cplx{1.0, 0.0}; }
+__global__ void k_set_basis_state(cplx* amp, uint64_t index, double value) { amp[index] = cplx{value, 0.0}; }
+
+// Materialise the zeros that support tracking implied: every amplitude with a bit of zmask set becomes 0.0.
+__global__ void __launch_bounds__(256)
+k_zero_outside_support(cplx* __restrict__ amp, uint64_t n, uint64_t zmask) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (i & zmask) st_stream(amp + i, cplx{0.0, 0.0});
+}
 
 // =================================================================================================
 // Probabilities, pairwise summation tree, sampler
@@ -605,14 +609,16 @@ cudaError_t kernels_init() {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
         g_sm_count = sms;
-    if (const char* e = getenv("DVD_PERSIST")) g_persist = atoi(e) != 0;
-    if (const char* e = getenv("DVD_PERSIST_CTAS")) g_persist_ctas_per_sm = atoi(e) > 0 ? atoi(e) : 2;
+    const char* e = getenv("DVD_PERSIST");        // re-read at every dvd_create: absent means the default again
+    g_persist = e ? atoi(e) != 0 : 0;
+    e = getenv("DVD_PERSIST_CTAS");
+    g_persist_ctas_per_sm = (e && atoi(e) > 0) ? atoi(e) : 2;
     return cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 SAMPLE_WARPS * (2 << BLK_BITS) * (int)sizeof(double));
 }
 
 cudaError_t launch_tile_pass(cplx* amp, PassParams& pp, cudaStream_t s) {
-    const uint64_t ctas = 1ull << (pp.pd.n_local - TILE_BITS);
+    const uint64_t ctas = 1ull << pp.pd.n_cta_bits;
     unsigned need = 0;
     int last_switch = -1;
     for (int k = 0; k < pp.pd.n_ops; ++k) {
@@ -624,7 +630,7 @@ cudaError_t launch_tile_pass(cplx* amp, PassParams& pp, cudaStream_t s) {
     while (v < 3 && (need & ~VARIANTS[v])) ++v;
     if (const char* e = getenv("DVD_KERNEL_VARIANT")) v = atoi(e) & 3;   // development: force a variant (3 = all ops)
     const uint64_t resident = (uint64_t)g_sm_count * g_persist_ctas_per_sm;
-    if (g_persist && ctas > resident)
+    if (g_persist && pp.pd.zero_mask == 0 && ctas > resident)
         tile_kernel(v, true)<<<(unsigned)resident, NTHREADS, TILE_SLOTS * sizeof(cplx), s>>>(amp, pp);
     else
         tile_kernel(v, false)<<<(unsigned)ctas, NTHREADS, TILE_SLOTS * sizeof(cplx), s>>>(amp, pp);
@@ -637,8 +643,14 @@ cudaError_t launch_simple_gate(cplx* amp, int n_local, uint64_t rank_bits, const
     return cudaGetLastError();
 }
 
-cudaError_t launch_set_basis_state(cplx* amp, uint64_t index, cudaStream_t s) {
-    k_set_basis_state<<<1, 1, 0, s>>>(amp, index);
+cudaError_t launch_set_basis_state(cplx* amp, uint64_t index, double value, cudaStream_t s) {
+    k_set_basis_state<<<1, 1, 0, s>>>(amp, index, value);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_zero_outside_support(cplx* amp, int n_local, uint64_t zmask, cudaStream_t s) {
+    if (zmask == 0) return cudaSuccess;
+    k_zero_outside_support<<<grid_for(1ull << n_local, 256, STREAM_CAP), 256, 0, s>>>(amp, 1ull << n_local, zmask);
     return cudaGetLastError();
 }
 

@@ -18,7 +18,9 @@ cudaError_t launch_tile_pass(cplx* amp, PassParams& pp, cudaStream_t s);   // fi
 struct SimpleOp { double m[8]; int32_t tbit; int32_t cbit; };   // cbit < 0: no control
 cudaError_t launch_simple_gate(cplx* amp, int n_local, uint64_t rank_bits, const SimpleOp& op, cudaStream_t s);
 
-cudaError_t launch_set_basis_state(cplx* amp, uint64_t index, cudaStream_t s);
+cudaError_t launch_set_basis_state(cplx* amp, uint64_t index, double value, cudaStream_t s);
+// amp[i] = 0 for every i with (i & zmask) != 0: turns the implied zeros of support tracking into stored zeros
+cudaError_t launch_zero_outside_support(cplx* amp, int n_local, uint64_t zmask, cudaStream_t s);
 
 // probs[i] = re^2 + im^2 for i in [first, first+count)
 cudaError_t launch_probabilities(const cplx* amp, uint64_t first, uint64_t count, double* probs, cudaStream_t s);

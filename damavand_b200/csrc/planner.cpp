@@ -858,6 +858,8 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
         }
         pass.desc.n_ops = (int)pass.ops.size();
         pass.desc.n_tab = (int)pass.tab_desc.size();
+        pass.touch_mask = 0;
+        for (int gi : taken) if (!gates[gi].diag) pass.touch_mask |= gates[gi].tmask;
         if (pass.desc.n_ops >= MAX_OPS_PER_PASS || pass.desc.n_tab > MAX_TABLE_OPS) {
             // the op list is a kernel parameter of bounded size: take fewer gates and plan this pass again
             if (taken.size() <= 1) throw std::runtime_error("plan_local: one gate does not fit a pass");

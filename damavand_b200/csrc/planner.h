@@ -45,6 +45,8 @@ struct Pass {
     size_t tid_off_slot = 0;           // start (in cplx slots) of the [NGROUPS][NTHREADS] thread-offset table inside `tables`
     void finish_tables();              // concatenate [desc][tile][bytes][thread offsets] into `tables`, fill desc.run_*
     int n_switches = 0;        // stage switches inside the pass (shared-memory transposes)
+    uint64_t touch_mask = 0;   // targets of the pass's non-diagonal gates (X / CNOT included): the only qubits whose
+                               //   |0> can turn into a superposition in this pass (support tracking in the engine)
 };
 
 struct PlanOptions {

@@ -170,8 +170,12 @@ struct PassDesc {
     int8_t run_len[TILE_BITS + 1];
     int8_t run_dst[TILE_BITS + 1];
     // Set by the engine / launcher, not by the planner:
-    int8_t zero_input;            // the state is |0..0> (lazy reset): the pass synthesises its input instead of loading it
+    int8_t n_cta_bits;            // log2(tiles the launch covers): non-tile bits that can be 1 on input (see zero_mask)
+    int8_t zero_regbits;          // register bits of the load layout (IO_GROUP) whose qubit is in zero_mask
     int16_t last_switch;          // index of the last OC_SWITCH in ops (-1: none); after it the shared-memory tile is free
+    uint64_t zero_mask;           // local qubits that are still |0> in every populated basis state (support tracking after
+                                  //   a reset): amplitudes with one of these bits set are zero by construction, are never
+                                  //   read, and tiles whose fixed bits hit the mask are not launched at all.  0 = dense state
 };
 // Kernel parameter block: the pass description and its whole op list (<= 32764 B of parameters).
 constexpr int MAX_OPS_PER_PASS = 336;
@@ -231,6 +235,26 @@ inline void fill_cta_runs(PassDesc& pd) {
         prev = q + 1;
     }
     pd.n_runs = (int8_t)n;
+    pd.n_cta_bits = (int8_t)src;
+}
+// Host: the same for a launch that only covers the tiles whose fixed bits avoid `skip` (bits known to be 0 in every
+// populated basis state).  Returns false when the run list would not fit (then the caller launches the full grid).
+inline bool fill_cta_runs_sparse(PassDesc& pd, uint64_t skip) {
+    uint64_t tile = 0;
+    for (int p = 0; p < TILE_BITS; ++p) tile |= 1ull << pd.tile_q[p];
+    int n = 0, src = 0, q = 0;
+    int8_t rs[TILE_BITS + 1], rl[TILE_BITS + 1], rd[TILE_BITS + 1];
+    while (q < pd.n_local) {
+        if (((tile | skip) >> q) & 1ull) { ++q; continue; }
+        int len = 0;
+        while (q + len < pd.n_local && !(((tile | skip) >> (q + len)) & 1ull)) ++len;
+        if (n > TILE_BITS) return false;   // run arrays hold TILE_BITS + 1 entries
+        rs[n] = (int8_t)src; rl[n] = (int8_t)len; rd[n] = (int8_t)q; ++n; src += len; q += len;
+    }
+    for (int r = 0; r < n; ++r) { pd.run_src[r] = rs[r]; pd.run_len[r] = rl[r]; pd.run_dst[r] = rd[r]; }
+    pd.n_runs = (int8_t)n;
+    pd.n_cta_bits = (int8_t)src;
+    return true;
 }
 
 // Local index of element h of the half-chunk whose bit lq equals bitval (global<->local qubit swap).

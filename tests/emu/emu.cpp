@@ -16,25 +16,39 @@
 
 using namespace dvd;
 
-static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits) {
+static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits, uint64_t zero_mask = 0) {
     PassDesc pd = pass.desc;
     pd.rank_bits = rank_bits;
     pd.tables = pass.tables.data();
     pd.tid_off = reinterpret_cast<const uint64_t*>(pass.tables.data() + pass.tid_off_slot);
-    const uint64_t ctas = 1ull << (pd.n_local - TILE_BITS);
+    // support tracking as the engine sets it up (engine.cu flush_impl): implied zeros are not read, tiles whose
+    // fixed bits hit the mask are not visited
+    uint64_t tile_mask = 0;
+    for (int k = 0; k < TILE_BITS; ++k) tile_mask |= 1ull << pd.tile_q[k];
+    pd.zero_mask = zero_mask;
+    int zregs = 0;
+    for (int k = 0; k < REG_BITS; ++k) if ((zero_mask >> pd.tile_q[IO_GROUP * REG_BITS + k]) & 1ull) zregs |= 1 << k;
+    pd.zero_regbits = (int8_t)zregs;
+    const bool sparse = (zero_mask & ~tile_mask) != 0 && fill_cta_runs_sparse(pd, zero_mask & ~tile_mask);
+    const uint64_t ctas = 1ull << pd.n_cta_bits;
+    if (!sparse && pd.n_cta_bits != pd.n_local - TILE_BITS) throw std::runtime_error("emu: n_cta_bits of the full grid");
     std::vector<cplx> tile(TILE_SLOTS);
     static cplx regs[NTHREADS][NREG];
     static ThreadCtx ctx[NTHREADS];
     for (uint64_t cta = 0; cta < ctas; ++cta) {
-        const uint64_t base = cta_base(pd, cta);
+        const uint64_t base = sparse ? cta_base_runs(pd, cta) : cta_base(pd, cta);
         if (cta_base_runs(pd, cta) != base) throw std::runtime_error("emu: run-compressed CTA base differs");
+        if (base & tile_mask) throw std::runtime_error("emu: CTA base overlaps the tile");
+        if (base & zero_mask) { if (sparse) throw std::runtime_error("emu: sparse grid visits an all-zero tile"); continue; }
         const uint64_t gbase = base | pd.rank_bits;
         if (pd.n_tab > MAX_TABLE_OPS || pd.n_ops >= MAX_OPS_PER_PASS || (size_t)pd.n_ops != pass.ops.size())
             throw std::runtime_error("emu: pass exceeds the kernel parameter limits");
         std::vector<cplx> wcs(pd.n_tab > 0 ? pd.n_tab : 1);     // kernel prologue: per-CTA table constants
         for (int ti = 0; ti < pd.n_tab; ++ti) wcs[ti] = table_cta_const(pd.tables, ti, gbase);
         for (int tid = 0; tid < NTHREADS; ++tid) {
-            for (int j = 0; j < NREG; ++j) regs[tid][j] = amp[base + tile_offset(pd, stage_idx(IO_GROUP, tid, j))];
+            const bool thread_zero = (tid_offset(pd, IO_GROUP, tid) & zero_mask) != 0;
+            for (int j = 0; j < NREG; ++j)
+                regs[tid][j] = (thread_zero || (j & pd.zero_regbits)) ? cplx{0.0, 0.0} : amp[base + tile_offset(pd, stage_idx(IO_GROUP, tid, j))];
             ctx[tid].pidx = gbase | tile_offset(pd, stage_idx(IO_GROUP, tid, 0));
             for (int g = 0; g < NGROUPS; ++g)
                 if (cta == 0 && tid_offset(pd, g, tid) != tile_offset(pd, stage_idx(g, tid, 0))) throw std::runtime_error("emu: thread offset table differs");
@@ -117,6 +131,18 @@ extern "C" {
 static std::string g_err;
 const char* emu_error() { return g_err.c_str(); }
 
+// emu_run_sparse: the same, replaying the engine's support tracking: `state` must hold |0..0> as the engine's
+// reset leaves it (amplitude 0 of every chunk stored, everything else arbitrary -- the tests fill it with NaN);
+// implied zeros are materialised at the end, before every global swap and before the one-gate path.
+static bool g_track_support = false;
+int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int fuse, double* state, int64_t* stats /*[4]*/);
+int emu_run_sparse(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int fuse, double* state, int64_t* stats) {
+    g_track_support = true;
+    const int rc = emu_run(n_qubits, world, gates, n_gates, fuse, state, stats);
+    g_track_support = false;
+    return rc;
+}
+
 int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int fuse, double* state, int64_t* stats /*[4]*/) {
     try {
         int g = 0; while ((1 << g) < world) ++g;
@@ -133,11 +159,20 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
         for (int q = 0; q < n_qubits; ++q) if (perm[q] != q) throw std::runtime_error("emu: layout not restored");
         int64_t n_pass = 0, n_swap = 0, n_switch = 0, n_ops = 0;
         PlanOptions opt;
+        // per-rank support masks (engine.cu: dvd_state::support); dense when tracking is off
+        const uint64_t local_mask = chunk - 1;
+        std::vector<uint64_t> support(world, (g_track_support && n_local >= TILE_BITS) ? ~local_mask : ~0ull);
+        auto materialize = [&](int r) {
+            const uint64_t zm = ~support[r] & local_mask;
+            if (zm) for (uint64_t i = 0; i < chunk; ++i) if (i & zm) amp[(uint64_t)r * chunk + i] = cplx{0.0, 0.0};
+            support[r] = ~0ull;
+        };
         for (auto& st : steps) {
             if (st.kind == DistStep::GLOBAL_SWAP) {
                 ++n_swap;
                 const int j = st.gq - n_local;
                 if (st.gq < n_local || st.gq >= n_qubits || st.lq < 0 || st.lq >= n_local) throw std::runtime_error("emu: bad swap");
+                for (int r = 0; r < world; ++r) materialize(r);
                 for (int r = 0; r < world; ++r) {
                     const int b = (r >> j) & 1, partner = r ^ (1 << j);
                     if (partner < r) continue;
@@ -154,13 +189,18 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
                 std::vector<Pass> passes = plan_local(st.gates, n_local, n_qubits, opt);
                 for (auto& p : passes) { ++n_pass; n_switch += p.n_switches; n_ops += (int64_t)p.ops.size(); }
                 for (int r = 0; r < world; ++r)
-                    for (auto& p : passes) run_pass(amp + (uint64_t)r * chunk, p, (uint64_t)r << n_local);
+                    for (auto& p : passes) {
+                        run_pass(amp + (uint64_t)r * chunk, p, (uint64_t)r << n_local, ~support[r] & local_mask);
+                        support[r] |= p.touch_mask;
+                    }
             } else {
+                for (int r = 0; r < world; ++r) materialize(r);
                 for (int r = 0; r < world; ++r)
                     for (auto& gte : st.gates) run_simple(amp + (uint64_t)r * chunk, n_local, (uint64_t)r << n_local, gte);
                 n_ops += (int64_t)st.gates.size();
             }
         }
+        for (int r = 0; r < world; ++r) materialize(r);
         if (stats) { stats[0] = n_pass; stats[1] = n_swap; stats[2] = n_switch; stats[3] = n_ops; }
         return 0;
     } catch (const std::exception& e) {

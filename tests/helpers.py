@@ -56,21 +56,35 @@ def emu():
         L.emu_run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(_lib.Gate), ctypes.c_int64, ctypes.c_int,
                               ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
         L.emu_run.restype = ctypes.c_int
+        L.emu_run_sparse.argtypes = L.emu_run.argtypes
+        L.emu_run_sparse.restype = ctypes.c_int
         L.emu_error.restype = ctypes.c_char_p
         L.emu_max_bank_conflict.restype = ctypes.c_int
         _emu = L
     return _emu
 
 
-def emu_run(oracle_circ: OracleCircuit, world: int = 1, state=None, fuse: bool = True):
-    """Run the recorded gates of `oracle_circ` through the CPU replay of the CUDA path."""
+def emu_run(oracle_circ: OracleCircuit, world: int = 1, state=None, fuse: bool = True, track_support: bool = False):
+    """Run the recorded gates of `oracle_circ` through the CPU replay of the CUDA path.
+    track_support: replay the engine's support tracking after a reset -- only amplitude 0 of every rank's chunk is
+    stored, the rest of the buffer is NaN (never-written memory) and must never be read."""
     n = oracle_circ.num_qubits
     arr, ng = gate_array(oracle_circ)
-    if state is None:
+    if track_support:
+        assert state is None
+        n_local = n - (world.bit_length() - 1)
+        # chunks below one tile are reset with a real memset (engine.cu set_zero_state)
+        state = np.full(2 << n, np.nan if n_local >= 12 else 0.0, dtype=np.float64)
+        chunk = (2 << n) // world
+        for r in range(world):
+            state[r * chunk:r * chunk + 2] = 0.0
+        state[0] = 1.0
+    elif state is None:
         state = np.zeros(2 << n, dtype=np.float64)
         state[0] = 1.0
     stats = (ctypes.c_int64 * 4)()
-    rc = emu().emu_run(n, world, arr, ng, int(fuse), state.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stats)
+    run = emu().emu_run_sparse if track_support else emu().emu_run
+    rc = run(n, world, arr, ng, int(fuse), state.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stats)
     if rc != 0:
         raise RuntimeError(emu().emu_error().decode())
     return state.view(np.complex128), dict(passes=stats[0], swaps=stats[1], switches=stats[2], ops=stats[3])

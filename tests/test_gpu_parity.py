@@ -348,3 +348,35 @@ def test_plan_cache_reuses_only_identical_gate_lists():
         c.set_parameters(params); c.reset_amplitudes(); c.forward()
     assert g.stats()["plan_cache_hits"] == 1               # new angles: planned again
     assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
+
+
+@pytest.mark.parametrize("n", [13, 20])
+def test_support_tracking_partial_circuits(n):
+    """After a reset only amplitude 0 is stored; passes launch only the tiles the touched qubits can populate and
+    the implied zeros appear at the first observation.  Circuits that leave most qubits in |0>, observed in the
+    middle and continued."""
+    def diag_only(c):
+        c.add_rotation_z_gate(3, 0.4); c.add_pauli_z_gate(n - 1, False)
+    def x_moves(c):
+        c.add_pauli_x_gate(n - 1, False); c.add_pauli_x_gate(0, False); c.add_cnot_gate(n - 1, 7); c.add_cnot_gate(3, 8)
+    def one_high(c):
+        c.add_hadamard_gate(n - 2); c.add_cnot_gate(n - 2, 2); c.add_cnot_gate(9, 5); c.add_rotation_y_gate(n - 3, 0.3)
+    def growing(c):
+        for q in np.random.default_rng(n).permutation(n)[:9]:
+            c.add_rotation_x_gate(int(q), 0.1 + 0.05 * q); c.add_rotation_z_gate(int(q), 0.2)
+            c.add_cnot_gate(int(q), int((q + 5) % n))
+    def ghz(c):
+        c.add_hadamard_gate(n - 1)
+        for q in range(n - 1, 0, -1):
+            c.add_cnot_gate(q, q - 1)
+    for build in (diag_only, x_moves, one_high, growing, ghz):
+        g, o = both(n, build)
+        assert g.norm() == pytest.approx(1.0, abs=1e-13)                 # observation in the middle
+        assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
+        for c in (g, o):                                                # continue on the (now dense) state
+            c.gates = []
+            c.add_hadamard_gate(1); c.add_cnot_gate(1, n - 1); c.add_rotation_x_gate(n // 2, 0.7)
+            c.forward()
+        assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
+        u = np.random.default_rng(3).random(64)
+        assert g.sample(64, uniforms=u) == o.sample(64, uniforms=u, mode="tree")

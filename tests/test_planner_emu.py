@@ -15,9 +15,12 @@ TOL = 1e-12
 def _check(circ: OracleCircuit, world=1):
     got, stats = emu_run(circ, world)                    # with the diagonal-run fusion pre-pass
     got_raw, stats_raw = emu_run(circ, world, fuse=False)  # gate by gate
+    got_sp, _ = emu_run(circ, world, track_support=True)   # from a reset: unwritten memory is NaN and never read
     circ.forward()
     assert rel_err(got, circ.amplitudes()) < TOL
     assert rel_err(got_raw, circ.amplitudes()) < TOL
+    assert not np.isnan(got_sp.view(np.float64)).any()
+    assert rel_err(got_sp, circ.amplitudes()) < TOL
     return stats
 
 
@@ -152,3 +155,28 @@ def test_distributed_list_scheduling_needs_few_swaps():
     c = OracleCircuit(n); circuits.hea(c, n, 5)
     s = _check(c, 8)
     assert s["swaps"] <= 9          # 3 rank-index qubits in, 3 back (+ slack); one swap per gate would be 15+
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_support_tracking_partial_circuits(world):
+    """Circuits that leave most qubits in |0>: the engine stores only what the touched qubits span, launches only
+    the tiles that can be populated and fills in the implied zeros at the first observation."""
+    n = 16
+    rng = np.random.default_rng(world)
+    cases = []
+    c = OracleCircuit(n); cases.append(c)                                   # nothing but diagonal gates
+    c.add_rotation_z_gate(3, 0.4); c.add_pauli_z_gate(15, False)
+    c = OracleCircuit(n); cases.append(c)                                   # X moves the single populated state around
+    c.add_pauli_x_gate(15, False); c.add_pauli_x_gate(0, False); c.add_cnot_gate(15, 7); c.add_cnot_gate(3, 8)
+    c = OracleCircuit(n); cases.append(c)                                   # one superposed high qubit, controls on it
+    c.add_hadamard_gate(14); c.add_cnot_gate(14, 2); c.add_cnot_gate(9, 5); c.add_rotation_y_gate(13, 0.3)
+    c = OracleCircuit(n); cases.append(c)                                   # support grows a few qubits at a time
+    for q in rng.permutation(n)[:9]:
+        c.add_rotation_x_gate(int(q), 0.1 + 0.05 * q); c.add_rotation_z_gate(int(q), 0.2)
+        c.add_cnot_gate(int(q), int((q + 5) % n))
+    c = OracleCircuit(n); cases.append(c)                                   # GHZ chain from the top qubit down
+    c.add_hadamard_gate(n - 1)
+    for q in range(n - 1, 0, -1):
+        c.add_cnot_gate(q, q - 1)
+    for c in cases:
+        _check(c, world)
