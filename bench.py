@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--no-scaling-point", action="store_true")
     ap.add_argument("--no-single-gate", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="one kernel per gate (no fusion) for comparison")
+    ap.add_argument("--jit", type=int, default=None, help="structure-specialised kernels: 0 off, 1 on (compiled during warm-up)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -258,8 +259,19 @@ def main():
         circ.reset_amplitudes()
         circ.forward_async()
 
+    # run-time specialised pass kernels: on for the single-GPU workloads (validated on B200, profiles/r1_*_v11*);
+    # the multi-GPU runs keep the interpreter kernels unless --jit 1 is given
+    jit = args.jit if args.jit is not None else int(os.environ.get("DVD_BENCH_JIT", "1" if args.gpus == 1 else "0"))
+    if jit:
+        circ.set_jit(1)
     for _ in range(args.warmup):
         one_step()
+    if jit:
+        # warm-up includes the run-time compilation of the pass kernels of this circuit's structure (sparse step and
+        # dense forward): wait for the background compiler, then run each once more so that the modules are loaded
+        circ.synchronize(); circ.jit_wait()
+        one_step(); circ.forward_async(); circ.synchronize(); circ.jit_wait()
+        one_step(); circ.forward_async(); circ.synchronize()
     barrier()
     circ.stats_reset()
     sampler = ClockSampler(device)
@@ -275,6 +287,8 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
     st = circ.stats()
+    # read while the circuit is alive (the scaling-point leg below closes it)
+    jit_cfg = dict(circ.jit_info(), launches_in_timed_region=int(st.get("jit_launches", 0))) if jit else False
     if args.gpus > 1:
         import torch
         import torch.distributed as dist
@@ -411,9 +425,14 @@ def main():
             sp_name = "random32"
             c2 = Circuit(workload_qubits(sp_name), "gpu")
             ng2 = build_workload(c2, sp_name)
+            if jit:
+                c2.set_jit(1)
             for _ in range(2):
                 c2.reset_amplitudes(); c2.forward_async()
             c2.synchronize()
+            if jit:
+                c2.jit_wait()
+                c2.reset_amplitudes(); c2.forward_async(); c2.synchronize()
             c2.timer_begin()
             for _ in range(2):
                 c2.reset_amplitudes(); c2.forward_async()
@@ -444,7 +463,8 @@ def main():
                                "tracks which qubits have left |0> and neither reads nor launches tiles that are zero by "
                                "construction -- see dense_state for the same circuit on a dense state)",
                        "l2": "state (>= 4 GiB per GPU) is far larger than the 126 MB L2; no flush needed",
-                       "fused": not args.unfused, "wall_s_timed_region": t_wall},
+                       "fused": not args.unfused, "wall_s_timed_region": t_wall,
+                       "jit": jit_cfg},
             "gpu_launches": int(st["kernel_launches"]),
             "passes_per_circuit": int(st["tile_passes"] // max(1, args.steps)),
             "global_swaps_per_circuit": int(st["global_swaps"] // max(1, args.steps)),

@@ -332,6 +332,23 @@ class Circuit:
     def stats_reset(self):
         _lib.check(self._lib.dvd_stats_reset(self._handle), "dvd_stats_reset")
 
+    def set_jit(self, mode: int):
+        """Structure-specialised pass kernels compiled at run time (csrc/jit.h): 0 off, 1 background, 2 on first use."""
+        _lib.check(self._lib.dvd_set_jit(self._handle, int(mode)), "dvd_set_jit")
+
+    def jit_wait(self):
+        """Block until every queued kernel compilation has finished."""
+        _lib.check(self._lib.dvd_jit_wait(self._handle), "dvd_jit_wait")
+
+    def jit_info(self) -> dict:
+        c, f, q = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        sec = ctypes.c_double()
+        msg = ctypes.create_string_buffer(4096)
+        _lib.check(self._lib.dvd_jit_info(self._handle, ctypes.byref(c), ctypes.byref(f), ctypes.byref(q), ctypes.byref(sec), msg, 4096),
+                   "dvd_jit_info")
+        return {"compiled": c.value, "failed": f.value, "pending": q.value, "compile_seconds": sec.value,
+                "message": msg.value.decode(errors="replace")}
+
     def set_unfused(self, flag: bool):
         _lib.check(self._lib.dvd_set_unfused(self._handle, int(bool(flag))), "dvd_set_unfused")
 

@@ -18,6 +18,8 @@
 #include "kernels.h"
 #include "nccl_dyn.h"
 #include "planner.h"
+#include "jit.h"
+#include "jit_rt.h"
 
 using namespace dvd;
 
@@ -88,6 +90,10 @@ struct dvd_state {
         bool valid = false;
     } cache;
     bool plan_cache = true;
+    // structure-specialised kernels (jit_rt.h): off / background compile / compile on first use
+    int jit_mode = JIT_OFF;
+    int jit_min_qubits = 20;
+    std::string jit_error;
     PlanOptions opt;
 };
 
@@ -196,6 +202,8 @@ static int create_common(int n_qubits, int device, int rank, int world, const vo
     if (const char* e = getenv("DVD_LAZY_ZERO")) s->lazy_zero = atoi(e) != 0;
     if (const char* e = getenv("DVD_BEST_GROUP")) s->opt.best_group = atoi(e) != 0;
     if (const char* e = getenv("DVD_PLAN_CACHE")) s->plan_cache = atoi(e) != 0;
+    if (const char* e = getenv("DVD_JIT")) s->jit_mode = std::string(e) == "sync" ? JIT_SYNC : std::max(0, std::min(2, atoi(e)));
+    if (const char* e = getenv("DVD_JIT_MIN_QUBITS")) s->jit_min_qubits = atoi(e);
     s->perm.resize(n_qubits);
     for (int q = 0; q < n_qubits; ++q) s->perm[q] = q;
     auto cleanup = [&](int code) { dvd_destroy(s); return code; };
@@ -527,7 +535,14 @@ static int flush_impl(dvd_state* s) {
                 pp.pd.tables = d_tabs + tat;
                 pp.pd.tid_off = reinterpret_cast<const uint64_t*>(d_tabs + tat + p.tid_off_slot);
                 std::memcpy(pp.ops, p.ops.data(), p.ops.size() * sizeof(DevOp));
-                CU(launch_tile_pass(s->amp, pp, s->stream));
+                bool launched = false;
+                if (s->jit_mode != JIT_OFF && s->n_local >= s->jit_min_qubits) {
+                    std::string jerr;
+                    launched = jit_launch(p, s->jit_mode, s->device, s->amp, pp, s->stream, &jerr);
+                    if (launched) s->stats.jit_launches++;
+                    else if (!jerr.empty()) s->jit_error = jerr;
+                }
+                if (!launched) CU(launch_tile_pass(s->amp, pp, s->stream));
                 tat += p.tables.size();
                 s->stats.kernel_launches++; s->stats.tile_passes++;
                 s->stats.stage_switches += p.n_switches;
@@ -795,6 +810,31 @@ int dvd_timer_end(dvd_state* s, double* ms) {
     *ms = f;
     return DVD_OK;
 }
+int dvd_set_jit(dvd_state* s, int mode) {
+    if (!s) return fail(DVD_ERR_ARG, "null state");
+    if (mode < 0 || mode > 2) return fail(DVD_ERR_ARG, "jit mode must be 0 (off), 1 (background) or 2 (on first use)");
+    s->jit_mode = mode;
+    return DVD_OK;
+}
+int dvd_jit_wait(dvd_state* s) {
+    (void)s;
+    jit_wait();
+    return DVD_OK;
+}
+int dvd_jit_info(dvd_state* s, int64_t* compiled, int64_t* failed, int64_t* pending, double* compile_seconds,
+                 char* last_error, int64_t cap) {
+    const JitStats st = jit_stats();
+    if (compiled) *compiled = st.compiled;
+    if (failed) *failed = st.failed;
+    if (pending) *pending = st.pending;
+    if (compile_seconds) *compile_seconds = st.compile_seconds;
+    if (last_error && cap > 0) {
+        std::string msg = s ? s->jit_error : std::string();
+        if (msg.empty()) msg = jit_available();
+        snprintf(last_error, (size_t)cap, "%s", msg.c_str());
+    }
+    return DVD_OK;
+}
 int dvd_set_unfused(dvd_state* s, int unfused) {
     if (!s) return fail(DVD_ERR_ARG, "null state");
     s->unfused = unfused != 0;
@@ -838,6 +878,32 @@ int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t 
         g_last_error = std::string("planner: ") + e.what();
         return INT64_MIN;
     }
+}
+
+// Generated source of the structure-specialised kernel of pass `pass_index` (development / tests).  Returns the
+// length written (without the terminator), -needed if cap is too small, INT64_MIN on a planner error.
+int64_t dvd_jit_debug_source(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates, int pass_index,
+                             char* out, int64_t cap) {
+    try {
+        PlanOptions opt;
+        std::vector<Pass> passes = plan_local(fuse_diagonal_runs(to_host_gates(gates, n_gates)), n_local, n_total, opt);
+        if (pass_index < 0 || pass_index >= (int)passes.size()) return 0;
+        const std::string src = generate_pass_source(passes[pass_index], "k_pass_static");
+        if ((int64_t)src.size() + 1 > cap) return -(int64_t)(src.size() + 1);
+        std::memcpy(out, src.c_str(), src.size() + 1);
+        return (int64_t)src.size();
+    } catch (const std::exception& e) {
+        g_last_error = std::string("planner: ") + e.what();
+        return INT64_MIN;
+    }
+}
+
+// NVRTC-compile a generated source (no GPU needed).  Returns the cubin size, or -1 with the log in dvd_last_error().
+int64_t dvd_jit_debug_compile(const char* source) {
+    std::vector<char> cubin;
+    const std::string log = jit_compile(source ? source : "", &cubin);
+    if (!log.empty()) { g_last_error = log; return -1; }
+    return (int64_t)cubin.size();
 }
 
 int64_t dvd_plan_distributed_debug(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates,

@@ -17,8 +17,20 @@
 // and emits it as byte-indexed phase tables (thread-level bits), per-register-bit factors and
 // register-pair factors, at the latest point the commutation rules allow.
 #pragma once
+#ifdef __CUDACC_RTC__
+// run-time compilation (jit_rt.cpp): no system headers; fixed-width types as on LP64 hosts (same sizes)
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <math.h>
 #include <stdint.h>
+#endif
 
 #ifdef __CUDACC__
 #define DVD_HD __host__ __device__ __forceinline__
@@ -225,6 +237,7 @@ DVD_HD uint64_t cta_base_runs(const PassDesc& pd, uint64_t cta) {
         b |= ((cta >> pd.run_src[r]) & ((1ull << pd.run_len[r]) - 1)) << pd.run_dst[r];
     return b;
 }
+#ifndef __CUDACC_RTC__
 // Host: fill PassDesc::run_* from sorted_q / n_local.
 inline void fill_cta_runs(PassDesc& pd) {
     int n = 0, src = 0, prev = 0;    // prev: first physical bit not yet covered
@@ -256,6 +269,7 @@ inline bool fill_cta_runs_sparse(PassDesc& pd, uint64_t skip) {
     pd.n_cta_bits = (int8_t)src;
     return true;
 }
+#endif  // !__CUDACC_RTC__
 
 // Local index of element h of the half-chunk whose bit lq equals bitval (global<->local qubit swap).
 DVD_HD uint64_t half_index(uint64_t h, int lq, int bitval) {
@@ -459,8 +473,7 @@ DVD_HD unsigned perm_index(const DevOp& op, unsigned v, unsigned idx) {
 
 // Twiddle on the registers with bit B (table_reg) followed by the Hadamard butterfly along B.
 template <int B>
-DVD_HD void twhad(cplx (&a)[NREG], const DevOp& op, const ThreadCtx& ctx, const cplx* tables, int n_tab, const cplx* wcs) {
-    const unsigned flags = op.flags;
+DVD_HD void twhad(cplx (&a)[NREG], const DevOp& op, unsigned flags, const ThreadCtx& ctx, const cplx* tables, int n_tab, const cplx* wcs) {
     table_reg<B>(a, op, flags, ctx, (flags & F_TABLE) ? table_tile(tables, n_tab, op.tab) : tables,
                  (flags & F_TABLE) ? wcs[op.tab] : cplx{1.0, 0.0});
     gate_all<B, K_HADAMARD>(a, op.m);
@@ -470,10 +483,11 @@ DVD_HD void twhad(cplx (&a)[NREG], const DevOp& op, const ThreadCtx& ctx, const 
 // tables / n_tab: the pass's table buffer; wcs: per-CTA constants of its table ops (kernel prologue).
 // Returns how many FOLLOWING ops the op consumed (macro-ops run opk[0..3] in one dispatch).
 // SET: the op classes this instantiation can execute (the others compile to nothing).
+// code / flags are opk[0].code / opk[0].flags: run-time values in the interpreter kernels, literals in the
+// structure-specialised kernels (jit.cpp), where the switch and the flag tests fold away.
 template <unsigned SET = C_ALL>
-DVD_HD int apply_op(cplx (&a)[NREG], const DevOp* opk, int code, ThreadCtx& ctx, const cplx* tables, int n_tab, const cplx* wcs) {
+DVD_HD int apply_op(cplx (&a)[NREG], const DevOp* opk, int code, unsigned flags, ThreadCtx& ctx, const cplx* tables, int n_tab, const cplx* wcs) {
     const DevOp& op = opk[0];
-    const unsigned flags = op.flags;
     if ((flags & F_TCTRL) && !parity64(ctx.pidx & op.cmask)) return 0;   // thread-level control
     const double* m = op.m;
     switch (code) {
@@ -514,7 +528,7 @@ DVD_HD int apply_op(cplx (&a)[NREG], const DevOp* opk, int code, ThreadCtx& ctx,
         } break;
         DVD_CASE4(C_TABLE, OC_TABLE_REG, (table_reg<B>(a, op, flags, ctx, (flags & F_TABLE) ? table_tile(tables, n_tab, op.tab) : tables,
                                               (flags & F_TABLE) ? wcs[op.tab] : cplx{1.0, 0.0})))
-        DVD_CASE4(C_TABLE, OC_TWHAD, (twhad<B>(a, op, ctx, tables, n_tab, wcs)))
+        DVD_CASE4(C_TABLE, OC_TWHAD, (twhad<B>(a, op, flags, ctx, tables, n_tab, wcs)))
         case OC_PAIR + 0: if constexpr ((SET & C_DIAG) != 0) scale_pair<0, 1>(a, m[0], m[1]); break;
         case OC_PAIR + 1: if constexpr ((SET & C_DIAG) != 0) scale_pair<0, 2>(a, m[0], m[1]); break;
         case OC_PAIR + 2: if constexpr ((SET & C_DIAG) != 0) scale_pair<0, 3>(a, m[0], m[1]); break;
@@ -527,8 +541,8 @@ DVD_HD int apply_op(cplx (&a)[NREG], const DevOp* opk, int code, ThreadCtx& ctx,
             return 3;
         } break;
         case OC_TWHAD4: if constexpr ((SET & C_MACRO_T) != 0) {
-            twhad<0>(a, opk[0], ctx, tables, n_tab, wcs); twhad<1>(a, opk[1], ctx, tables, n_tab, wcs);
-            twhad<2>(a, opk[2], ctx, tables, n_tab, wcs); twhad<3>(a, opk[3], ctx, tables, n_tab, wcs);
+            twhad<0>(a, opk[0], opk[0].flags, ctx, tables, n_tab, wcs); twhad<1>(a, opk[1], opk[1].flags, ctx, tables, n_tab, wcs);
+            twhad<2>(a, opk[2], opk[2].flags, ctx, tables, n_tab, wcs); twhad<3>(a, opk[3], opk[3].flags, ctx, tables, n_tab, wcs);
             return 3;
         } break;
         default: break;

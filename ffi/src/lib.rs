@@ -29,6 +29,7 @@ pub struct dvd_stats {
     pub pass_bytes: c_double,
     pub gate_algorithmic_bytes: c_double,
     pub plan_cache_hits: i64,
+    pub jit_launches: i64,
 }
 
 pub const DVD_NCCL_ID_BYTES: usize = 128;

@@ -126,6 +126,7 @@ typedef struct {
                                      the first pass after a reset, which does not read) */
     double gate_algorithmic_bytes;/* sum over gates of 32*2^n_local (16*2^n_local if controlled) */
     int64_t plan_cache_hits;      /* flushes that reused the previous plan (identical gate list) */
+    int64_t jit_launches;         /* tile passes that ran as a structure-specialised (run-time compiled) kernel */
 } dvd_stats;
 int dvd_get_stats(const dvd_state* s, dvd_stats* out);
 int dvd_stats_reset(dvd_state* s);
@@ -134,6 +135,13 @@ int dvd_timer_begin(dvd_state* s);
 int dvd_timer_end(dvd_state* s, double* elapsed_ms);
 /* 0 = fused tile passes (default), 1 = one kernel per gate (debug / baseline) */
 int dvd_set_unfused(dvd_state* s, int unfused);
+/* Structure-specialised pass kernels, compiled at run time with NVRTC (csrc/jit.h): 0 = off, 1 = compile in the
+ * background and switch over when ready, 2 = compile on first use.  Without libnvrtc / libcuda the interpreter
+ * kernels keep running.  dvd_jit_wait blocks until the background queue is empty. */
+int dvd_set_jit(dvd_state* s, int mode);
+int dvd_jit_wait(dvd_state* s);
+int dvd_jit_info(dvd_state* s, int64_t* compiled, int64_t* failed, int64_t* pending, double* compile_seconds,
+                 char* last_error, int64_t cap);
 
 /* ---- planner inspection (host only, no GPU needed) ----------------------------------------- */
 /* Runs the pass planner on a gate list for a state of n_total qubits with n_local local qubits
@@ -142,6 +150,12 @@ int dvd_set_unfused(dvd_state* s, int unfused);
  * Returns the number of int32 written, or -(needed) if cap is too small, or INT64_MIN on error. */
 int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates, int fuse,
                        int32_t* out, int64_t cap);
+/* CUDA source of the structure-specialised kernel the engine would compile for pass `pass_index` of the same plan
+ * (NUL-terminated text).  Returns its length, 0 if there is no such pass, -(needed) if cap is too small. */
+int64_t dvd_jit_debug_source(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates, int pass_index,
+                             char* out, int64_t cap);
+/* NVRTC-compiles such a source for sm_100a (no GPU needed): cubin size, or -1 with the log in dvd_last_error(). */
+int64_t dvd_jit_debug_compile(const char* source);
 /* Runs the distributed planner: perm_io[logical] = physical (in/out).  Output:
  *   [n_steps, then per step: kind (0 local gates, 1 swap), a, b, n_gates, then per gate: gate_idx, target, control]
  * For swaps a = global physical qubit, b = local physical qubit, n_gates = 0. */

@@ -86,7 +86,7 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits, uint64_t z
             if (is_table_op(op.code) && (op.flags & F_TABLE) && (op.tab < 0 || op.tab >= pd.n_tab)) throw std::runtime_error("emu: bad table index");
             int consumed = 0;
             if ((op.code == OC_REALPH4 || op.code == OC_TWHAD4) && oi + 3 >= pass.ops.size()) throw std::runtime_error("emu: truncated macro-op");
-            for (int tid = 0; tid < NTHREADS; ++tid) consumed = apply_op(regs[tid], &op, op.code, ctx[tid], pd.tables, pd.n_tab, wcs.data());
+            for (int tid = 0; tid < NTHREADS; ++tid) consumed = apply_op(regs[tid], &op, op.code, op.flags, ctx[tid], pd.tables, pd.n_tab, wcs.data());
             if ((op.code == OC_REALPH4 || op.code == OC_TWHAD4) && consumed != 3) throw std::runtime_error("emu: macro-op did not run");
             for (int e = 1; e <= consumed; ++e) if (pass.ops[oi + e].group != cur) throw std::runtime_error("emu: macro-op crosses a stage");
             oi += (size_t)consumed;

@@ -116,3 +116,30 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["vs_baseline"] is None and d["dtype"] == "f64"
+
+
+def test_jit_generator_and_nvrtc_compile():
+    """The generated source of a pass's structure-specialised kernel compiles with NVRTC for sm_100a on a host
+    without a GPU, and two passes with the same op structure (different angles) produce the same source."""
+    import ctypes
+    from damavand_b200 import _lib, circuits
+    from oracle.oracle import OracleCircuit
+    from tests.helpers import gate_array
+    L = _lib.load()
+    srcs = []
+    for seed_shift in (0.0, 0.37):
+        o = OracleCircuit.__new__(OracleCircuit); o.num_qubits = 14; o.gates = []; o.observables = []
+        circuits.hea(o, 14, 2)
+        for g in o.gates:
+            if g.parameter is not None:
+                g.parameter += seed_shift
+        arr, ng = gate_array(o)
+        buf = ctypes.create_string_buffer(1 << 20)
+        k = L.dvd_jit_debug_source(14, 14, arr, ng, 0, buf, 1 << 20)
+        assert k > 0, L.dvd_last_error()
+        srcs.append(buf.value)
+    assert srcs[0] == srcs[1]
+    assert b"apply_op<C_ALL>" in srcs[0] and b"tile_store<" in srcs[0]
+    size = L.dvd_jit_debug_compile(srcs[0])
+    assert size > 10000, L.dvd_last_error()
+    assert L.dvd_jit_debug_compile(b"this is not CUDA") == -1 and b"error" in L.dvd_last_error()

@@ -380,3 +380,42 @@ def test_support_tracking_partial_circuits(n):
         assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
         u = np.random.default_rng(3).random(64)
         assert g.sample(64, uniforms=u) == o.sample(64, uniforms=u, mode="tree")
+
+
+@pytest.mark.parametrize("kind,n", [("qft", 20), ("hea", 20), ("random", 21), ("partial", 20)])
+def test_jit_specialised_kernels_agree_with_oracle(env, kind, n):
+    """Structure-specialised pass kernels (NVRTC, compiled on first use here) against the oracle, and bit for bit
+    against the interpreter kernels they replace; a second parameter set reuses the compiled kernels."""
+    env(DVD_JIT_MIN_QUBITS=12)
+    def build(c):
+        if kind == "qft":
+            circuits.qft_like(c, n)
+        elif kind == "hea":
+            circuits.hea(c, n, 2)
+        elif kind == "random":
+            circuits.random_circuit(c, n, 80, 31)
+        else:
+            c.add_hadamard_gate(n - 1); c.add_rotation_y_gate(3, 0.4); c.add_cnot_gate(n - 1, 5); c.add_rotation_z_gate(5, 0.3)
+            c.add_rotation_x_gate(n - 2, 1.1); c.add_cnot_gate(3, n - 2)
+    rec = Recorder(); build(rec)
+    j = rec.replay(gpu_circuit(n)); i = rec.replay(gpu_circuit(n)); o = rec.replay(OracleCircuit(n))
+    j.set_jit(2)
+    info0 = j.jit_info()
+    j.forward(); i.forward(); o.forward()
+    st = j.stats()
+    assert st["jit_launches"] == st["tile_passes"] > 0, j.jit_info()
+    assert rel_err(j.state_numpy(), o.amplitudes()) < TOL
+    assert rel_err(j.state_numpy(), i.state_numpy()) < 1e-14
+    # dense input, same structure: no new compilation
+    compiled = j.jit_info()["compiled"]
+    assert compiled > info0["compiled"] or kind == "partial"
+    j.forward(); o.forward()
+    assert rel_err(j.state_numpy(), o.amplitudes()) < TOL
+    if kind == "hea":     # new angles, same structure
+        p = [0.05 * (k + 1) for k in range(2 * n * 2)]     # no zero angle: RY(0) is a different gate class
+        for c in (j, o):
+            c.set_parameters(p); c.reset_amplitudes(); c.forward()
+        assert j.jit_info()["compiled"] <= compiled + 1        # (an angle-dependent gate class may add one)
+        assert j.stats()["jit_launches"] == j.stats()["tile_passes"]
+        assert rel_err(j.state_numpy(), o.amplitudes()) < TOL
+    assert j.jit_info()["failed"] == 0
