@@ -5,8 +5,13 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <deque>
 #include <map>
 #include <memory>
@@ -146,7 +151,62 @@ Runtime& rt() {
 
 }  // namespace
 
+namespace {
+
+// Disk cache of compiled cubins, opt-in: the directory named by $DVD_JIT_CACHE_DIR (nothing is written anywhere
+// unless it is set).  File name = FNV-1a hash of the generated source and of both embedded headers, so a rebuilt
+// library with different device code never picks up a stale kernel.
+std::string cache_dir() {
+    const char* e = getenv("DVD_JIT_CACHE_DIR");
+    return e ? std::string(e) : std::string();
+}
+uint64_t fnv1a(uint64_t h, const char* p, size_t n) {
+    for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; }
+    return h;
+}
+std::string cache_path(const std::string& source) {
+    const std::string dir = cache_dir();
+    if (dir.empty()) return "";
+    uint64_t h = 1469598103934665603ull;
+    h = fnv1a(h, source.data(), source.size());
+    h = fnv1a(h, k_src_tile_core, sizeof k_src_tile_core);
+    h = fnv1a(h, k_src_tile_kernel, sizeof k_src_tile_kernel);
+    char name[64];
+    snprintf(name, sizeof name, "/%016llx.sm_100a.cubin", (unsigned long long)h);
+    return dir + name;
+}
+void mkdirs(const std::string& dir) {
+    for (size_t i = 1; i <= dir.size(); ++i)
+        if (i == dir.size() || dir[i] == '/') mkdir(dir.substr(0, i).c_str(), 0755);
+}
+bool cache_read(const std::string& path, std::vector<char>* out) {
+    if (path.empty()) return false;
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    bool ok = n > 64;
+    if (ok) { out->resize((size_t)n); ok = fread(out->data(), 1, (size_t)n, f) == (size_t)n; }
+    fclose(f);
+    return ok && (*out)[0] == 0x7f && (*out)[1] == 'E' && (*out)[2] == 'L' && (*out)[3] == 'F';   // a cubin is an ELF image
+}
+void cache_write(const std::string& path, const std::vector<char>& data) {
+    if (path.empty()) return;
+    mkdirs(path.substr(0, path.rfind('/')));
+    const std::string tmp = path + ".tmp." + std::to_string((long)getpid());
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    const bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+    fclose(f);
+    if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());   // rename: readers never see a partial file
+}
+
+}  // namespace
+
 std::string jit_compile(const std::string& source, std::vector<char>* cubin) {
+    const std::string cpath = cache_path(source);
+    if (cache_read(cpath, cubin)) return "";
     Api* api;
     {
         Runtime& r = rt();
@@ -178,6 +238,7 @@ std::string jit_compile(const std::string& source, std::vector<char>* cubin) {
         }
     }
     api->DestroyProgram(&prog);
+    if (log.empty()) cache_write(cpath, *cubin);
     return log;
 }
 

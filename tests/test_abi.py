@@ -143,3 +143,22 @@ def test_jit_generator_and_nvrtc_compile():
     size = L.dvd_jit_debug_compile(srcs[0])
     assert size > 10000, L.dvd_last_error()
     assert L.dvd_jit_debug_compile(b"this is not CUDA") == -1 and b"error" in L.dvd_last_error()
+
+
+def test_jit_disk_cache(tmp_path, monkeypatch):
+    """A compiled cubin is written to DVD_JIT_CACHE_DIR (atomically) and served from there the next time; a corrupt
+    file is ignored and overwritten."""
+    import time
+    from damavand_b200 import _lib
+    L = _lib.load()
+    monkeypatch.setenv("DVD_JIT_CACHE_DIR", str(tmp_path / "jit"))
+    src = b'extern "C" __global__ void dvd_pass_static(double* p) { p[threadIdx.x] *= 2.0; }\n// ' + str(time.time()).encode()
+    t0 = time.perf_counter(); a = L.dvd_jit_debug_compile(src); t_cold = time.perf_counter() - t0
+    files = list((tmp_path / "jit").glob("*.cubin"))
+    assert a > 0 and len(files) == 1 and files[0].stat().st_size == a
+    t0 = time.perf_counter(); b = L.dvd_jit_debug_compile(src); t_warm = time.perf_counter() - t0
+    assert b == a and t_warm < t_cold
+    files[0].write_bytes(b"garbage")
+    assert L.dvd_jit_debug_compile(src) == a and files[0].stat().st_size == a
+    monkeypatch.setenv("DVD_JIT_CACHE_DIR", "")
+    assert L.dvd_jit_debug_compile(src + b" ") == a and len(list((tmp_path / "jit").glob("*"))) == 1
