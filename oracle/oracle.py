@@ -313,6 +313,14 @@ class OracleCircuit:
     def add_cnot_gate(self, control, target):
         self.gates.append(_Gate("CNOT", target, control=control))
 
+    # gates.rs defines S (:617-641) and T (:675-703) but circuit.rs has no add_ method for them; the product offers
+    # add_s_gate / add_t_gate as extensions and the oracle mirrors that with the reference's matrices
+    def add_s_gate(self, q):
+        self.gates.append(_Gate("S", q))
+
+    def add_t_gate(self, q):
+        self.gates.append(_Gate("T", q))
+
     # -- forward -----------------------------------------------------------------------------
     def forward(self, max_gates: Optional[int] = None):  # circuit.rs:341-375 (no implicit reset)
         n = 1 << self.num_qubits

@@ -419,3 +419,34 @@ def test_jit_specialised_kernels_agree_with_oracle(env, kind, n):
         assert j.stats()["jit_launches"] == j.stats()["tile_passes"]
         assert rel_err(j.state_numpy(), o.amplitudes()) < TOL
     assert j.jit_info()["failed"] == 0
+
+
+def _golden():
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join("tests", "golden", "make_golden.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m
+
+
+def test_cuda_path_against_hand_derived_known_answers():
+    mg = _golden()
+    ka = np.load("tests/golden/known_answers.npz")
+    for name in ka.files:
+        g = mg.build_known(name, gpu_circuit)
+        g.forward()
+        assert np.abs(g.state_numpy() - ka[name]).max() < 1e-15, name
+
+
+@pytest.mark.parametrize("kind", ["layered", "hea", "qft", "random"])
+def test_cuda_path_against_committed_fixtures(kind):
+    """12 qubits = the smallest state the tiled kernel runs on: amplitudes within 1e-12, sampled indices and
+    expectation values bit-exact against tests/golden/oracle_regression.npz."""
+    mg = _golden()
+    fx = np.load("tests/golden/oracle_regression.npz")
+    g = mg.regression_case(kind, gpu_circuit)
+    g.forward()
+    assert g.stats()["tile_passes"] > 0
+    assert rel_err(g.state_numpy(), fx[f"{kind}_amplitudes"]) < TOL
+    s = g.sample(64, uniforms=fx[f"{kind}_uniforms"])
+    assert (np.asarray(s, dtype=np.uint64) == fx[f"{kind}_samples"]).all()
+    assert (np.asarray(g.extract_expectation_values(s)) == fx[f"{kind}_expectation"]).all()

@@ -151,3 +151,37 @@ def test_partner_rank_is_xor():
                 gap = per << j
                 for r in range(1 << world_bits):
                     assert L.orc_compute_partner_rank(r, per, gap) == r ^ (1 << j)
+
+
+# ---- committed fixtures (tests/golden/make_golden.py states where each one comes from) ----------------------------
+def _golden():
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join("tests", "golden", "make_golden.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("method", ["multithreading", "brute_force"])
+def test_hand_derived_known_answers(method):
+    mg = _golden()
+    ka = np.load("tests/golden/known_answers.npz")
+    assert set(ka.files) == set(mg.known_answers())
+    for name in ka.files:
+        c = mg.build_known(name, lambda n: OracleCircuit(n, method))
+        c.forward()
+        assert np.abs(c.amplitudes() - ka[name]).max() < 1e-15, name
+
+
+@pytest.mark.parametrize("kind", ["layered", "hea", "qft", "random"])
+def test_oracle_regression_fixtures(kind):
+    """The oracle reproduces its own frozen outputs bit for bit (amplitudes, samples, expectation values)."""
+    mg = _golden()
+    fx = np.load("tests/golden/oracle_regression.npz")
+    c = mg.regression_case(kind, OracleCircuit)
+    c.forward()
+    assert (c.amplitudes() == fx[f"{kind}_amplitudes"]).all()
+    s = c.sample(64, uniforms=fx[f"{kind}_uniforms"], mode="sequential")
+    assert (np.asarray(s, dtype=np.uint64) == fx[f"{kind}_samples"]).all()
+    assert s == c.sample(64, uniforms=fx[f"{kind}_uniforms"], mode="tree")
+    assert (np.asarray(c.extract_expectation_values(s)) == fx[f"{kind}_expectation"]).all()
+    assert abs(np.linalg.norm(fx[f"{kind}_amplitudes"]) - 1.0) < 1e-13

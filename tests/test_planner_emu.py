@@ -180,3 +180,16 @@ def test_support_tracking_partial_circuits(world):
         c.add_cnot_gate(q, q - 1)
     for c in cases:
         _check(c, world)
+
+
+@pytest.mark.parametrize("kind", ["layered", "hea", "qft", "random"])
+def test_replay_against_committed_fixtures(kind):
+    """Planner + kernel logic (CPU replay, dense and support-tracking forms) against tests/golden/oracle_regression.npz."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join("tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    fx = np.load("tests/golden/oracle_regression.npz")
+    c = mg.regression_case(kind, OracleCircuit)
+    for track in (False, True):
+        got, _ = emu_run(c, 1, track_support=track)
+        assert rel_err(got, fx[f"{kind}_amplitudes"]) < TOL
