@@ -883,12 +883,12 @@ int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t 
 // Generated source of the structure-specialised kernel of pass `pass_index` (development / tests).  Returns the
 // length written (without the terminator), -needed if cap is too small, INT64_MIN on a planner error.
 int64_t dvd_jit_debug_source(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates, int pass_index,
-                             char* out, int64_t cap) {
+                             int persistent, char* out, int64_t cap) {
     try {
         PlanOptions opt;
         std::vector<Pass> passes = plan_local(fuse_diagonal_runs(to_host_gates(gates, n_gates)), n_local, n_total, opt);
         if (pass_index < 0 || pass_index >= (int)passes.size()) return 0;
-        const std::string src = generate_pass_source(passes[pass_index], "k_pass_static");
+        const std::string src = generate_pass_source(passes[pass_index], "dvd_pass_static", persistent != 0);
         if ((int64_t)src.size() + 1 > cap) return -(int64_t)(src.size() + 1);
         std::memcpy(out, src.c_str(), src.size() + 1);
         return (int64_t)src.size();

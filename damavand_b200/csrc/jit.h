@@ -16,10 +16,12 @@
 namespace dvd {
 
 // Structure key of a pass: equal keys <=> identical generated source.
-std::vector<uint32_t> pass_structure_key(const Pass& p);
+std::vector<uint32_t> pass_structure_key(const Pass& p, bool persistent = false);
 
 // CUDA source of `extern "C" __global__ void <fn_name>(cplx*, const PassParams)`; expects tile_kernel.cuh to be
-// includable under that name.
-std::string generate_pass_source(const Pass& p, const std::string& fn_name);
+// includable under that name.  persistent: one CTA per resident slot loops over the tiles and fetches the next
+// tile with cp.async once the last transpose of the current one has been read back (the specialised form of
+// k_tile_pass_persist; dense states only).  Experimental: not yet measured on a GPU, off unless DVD_JIT_PERSIST=1.
+std::string generate_pass_source(const Pass& p, const std::string& fn_name, bool persistent = false);
 
 }  // namespace dvd

@@ -102,6 +102,7 @@ struct Runtime {
     std::map<std::vector<uint32_t>, std::shared_ptr<Entry>> entries;
     std::deque<std::pair<std::shared_ptr<Entry>, std::string>> queue;
     std::vector<std::thread> workers;
+    std::map<int, int> sm_count;     // per device
     int busy = 0;
     bool stop = false;
     JitStats stats;
@@ -252,14 +253,27 @@ bool jit_launch(const Pass& p, int mode, int device, cplx* amp, const PassParams
     if (mode == JIT_OFF) return false;
     Runtime& r = rt();
     CUfunction fn = nullptr;
+    // experimental persistent (cp.async prefetch) form: dense states only, off unless DVD_JIT_PERSIST=1
+    const char* pe = getenv("DVD_JIT_PERSIST");
+    bool persistent = pe && atoi(pe) != 0 && pp.pd.zero_mask == 0;
+    unsigned resident = 0;
     {
         std::unique_lock<std::mutex> lk(r.mu);
         if (!r.api.load(true).empty()) return false;
-        const std::vector<uint32_t> key = pass_structure_key(p);
+        if (persistent && r.sm_count.find(device) == r.sm_count.end()) {
+            int sms = 0;
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 0; }
+            r.sm_count[device] = sms;
+        }
+        if (persistent) {
+            resident = 2u * (unsigned)r.sm_count[device];      // __launch_bounds__(NTHREADS, 2): two CTAs per SM
+            if (resident == 0 || (1u << pp.pd.n_cta_bits) <= resident) persistent = false;
+        }
+        const std::vector<uint32_t> key = pass_structure_key(p, persistent);
         std::shared_ptr<Entry>& slot = r.entries[key];
         if (!slot) {
             slot = std::make_shared<Entry>();
-            r.queue.emplace_back(slot, generate_pass_source(p, "dvd_pass_static"));
+            r.queue.emplace_back(slot, generate_pass_source(p, "dvd_pass_static", persistent));
             ++r.stats.pending;
             r.start_workers();
             r.cv.notify_all();
@@ -287,7 +301,7 @@ bool jit_launch(const Pass& p, int mode, int device, cplx* amp, const PassParams
             fn = it->second;
         }
     }
-    const unsigned ctas = 1u << pp.pd.n_cta_bits;
+    const unsigned ctas = persistent ? resident : 1u << pp.pd.n_cta_bits;
     void* params[] = {(void*)&amp, (void*)&pp};
     const CUresult rc = r.api.LaunchKernel(fn, ctas, 1, 1, NTHREADS, 1, 1, TILE_SLOTS * (unsigned)sizeof(cplx), (CUstream)stream, params, nullptr);
     if (rc != CUDA_SUCCESS) {

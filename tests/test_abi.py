@@ -135,7 +135,7 @@ def test_jit_generator_and_nvrtc_compile():
                 g.parameter += seed_shift
         arr, ng = gate_array(o)
         buf = ctypes.create_string_buffer(1 << 20)
-        k = L.dvd_jit_debug_source(14, 14, arr, ng, 0, buf, 1 << 20)
+        k = L.dvd_jit_debug_source(14, 14, arr, ng, 0, 0, buf, 1 << 20)
         assert k > 0, L.dvd_last_error()
         srcs.append(buf.value)
     assert srcs[0] == srcs[1]
@@ -143,6 +143,10 @@ def test_jit_generator_and_nvrtc_compile():
     size = L.dvd_jit_debug_compile(srcs[0])
     assert size > 10000, L.dvd_last_error()
     assert L.dvd_jit_debug_compile(b"this is not CUDA") == -1 and b"error" in L.dvd_last_error()
+    # the experimental persistent (cp.async prefetch) form of the same pass compiles too and differs from the plain one
+    k = L.dvd_jit_debug_source(14, 14, arr, ng, 0, 1, buf, 1 << 20)
+    assert k > 0 and buf.value != srcs[0] and b"tile_prefetch<IO_GROUP>" in buf.value and b"cp_async_wait_all" in buf.value
+    assert L.dvd_jit_debug_compile(buf.value) > 10000, L.dvd_last_error()
 
 
 def test_jit_disk_cache(tmp_path, monkeypatch):
