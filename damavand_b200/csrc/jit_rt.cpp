@@ -29,7 +29,6 @@ struct Api {
     void* h_nvrtc = nullptr;
     void* h_cuda = nullptr;
     std::string why;      // non-empty: unusable
-    bool tried = false;
     // NVRTC
     nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
     nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
@@ -50,7 +49,7 @@ struct Api {
             if (void* h = dlopen(*n, RTLD_NOW | RTLD_GLOBAL)) return h;
         return nullptr;
     }
-    // compile == true: NVRTC only (the generator test runs where no driver exists)
+    // need_driver == false: NVRTC only (the generator test runs where no driver exists)
     const std::string& load(bool need_driver) {
         if (!h_nvrtc) {
             static const char* const names[] = {"libnvrtc.so.12", "libnvrtc.so", nullptr};
