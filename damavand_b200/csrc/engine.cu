@@ -201,6 +201,7 @@ static int create_common(int n_qubits, int device, int rank, int world, const vo
     if (const char* e = getenv("DVD_MACRO_OPS")) s->opt.macro_ops = atoi(e) != 0;
     if (const char* e = getenv("DVD_LAZY_ZERO")) s->lazy_zero = atoi(e) != 0;
     if (const char* e = getenv("DVD_BEST_GROUP")) s->opt.best_group = atoi(e) != 0;
+    if (const char* e = getenv("DVD_RELABEL")) s->opt.relabel = atoi(e) != 0;
     if (const char* e = getenv("DVD_PLAN_CACHE")) s->plan_cache = atoi(e) != 0;
     if (const char* e = getenv("DVD_JIT")) s->jit_mode = std::string(e) == "sync" ? JIT_SYNC : std::max(0, std::min(2, atoi(e)));
     if (const char* e = getenv("DVD_JIT_MIN_QUBITS")) s->jit_min_qubits = atoi(e);
@@ -859,6 +860,7 @@ int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t 
         PlanOptions opt;
         if (const char* e = getenv("DVD_BEST_GROUP")) opt.best_group = atoi(e) != 0;
         if (const char* e = getenv("DVD_PLAN_CANDIDATES")) opt.candidates = std::max(1, atoi(e));
+        if (const char* e = getenv("DVD_RELABEL")) opt.relabel = atoi(e) != 0;
         std::vector<Pass> passes = plan_local(fuse ? fuse_diagonal_runs(to_host_gates(gates, n_gates)) : to_host_gates(gates, n_gates), n_local, n_total, opt);
         std::vector<int32_t> v;
         v.push_back((int32_t)passes.size());

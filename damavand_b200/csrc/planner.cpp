@@ -2,6 +2,7 @@
 #include "planner.h"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <complex>
 #include <cstring>
@@ -651,8 +652,9 @@ struct StageEmitter {
 
 }  // namespace
 
-std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, int n_total,
+std::vector<Pass> plan_local(const std::vector<HostGate>& gates_in, int n_local, int n_total,
                              const PlanOptions& opt) {
+    std::vector<HostGate> gates = gates_in;   // relabelling appends swap gates and renames qubits of the gates still to run
     if (n_local < TILE_BITS) throw std::runtime_error("plan_local: n_local < TILE_BITS");
     if (n_total > 62) throw std::runtime_error("plan_local: too many qubits");
     std::vector<Pass> passes;
@@ -677,8 +679,21 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
     // one of its qubits (or when the gate list ends), so a controlled phase between a qubit of this pass's
     // tile and one of a later pass's tile costs nothing here and folds into a per-CTA constant there.
     DiagAcc acc;
+    // relabelling state: partner[s] = physical qubit whose logical content currently sits in pinned slot s (and whose
+    // own position holds logical s); partner[s] == s: identity.  Always a product of disjoint transpositions.
+    int partner[8];
+    for (int sl = 0; sl < 8; ++sl) partner[sl] = sl;
+    static const double kX[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+    auto swap_bits = [](uint64_t m, int x, int y) {
+        const uint64_t bx = (m >> x) & 1ull, by = (m >> y) & 1ull;
+        return bx == by ? m : m ^ ((1ull << x) | (1ull << y));
+    };
     while (!pending.empty()) {
         const DiagAcc acc_start = acc;
+        const size_t gates_start = gates.size();
+        std::vector<std::pair<int, int>> swaps;      // physical-qubit transpositions appended to this pass, in order
+        int trial[8];                                // partner[] if this pass is accepted
+        for (int sl = 0; sl < 8; ++sl) trial[sl] = partner[sl];
         // ---- pass level: grow the tile greedily, take everything that commutes to the front ----
         // Candidate c hands the free tile positions to the qubits in first-come order but refuses the
         // first c newcomers: on layered circuits (entangler chains) that slides the window along the
@@ -725,6 +740,50 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
         // pad the tile with the lowest unused local qubits (keeps segments long)
         for (int q = 0; q < n_local && tile_n < TILE_BITS; ++q)
             if (!((tile >> q) & 1)) { tile |= 1ull << q; ++tile_n; }
+
+        if (opt.relabel) {
+            // next_use[q]: how soon physical qubit q is the target of a non-diagonal gate among the gates left after this
+            // pass (labels are physical, so next_use[slot] is the need of whatever the slot currently holds)
+            std::vector<int> next_use(n_total, INT_MAX);
+            {
+                int k = 0;
+                for (int gi : rest) {
+                    const HostGate& g = gates[gi];
+                    if (!g.diag && next_use[g.target()] == INT_MAX) next_use[g.target()] = k;
+                    if (++k > opt.window) break;
+                }
+            }
+            // SWAP(x, y) = CNOT(x,y) CNOT(y,x) CNOT(x,y), both inside the tile: joins the pass's last permuting transpose
+            auto append_swap = [&](int x, int y) {
+                const int pairs[3][2] = {{x, y}, {y, x}, {x, y}};
+                for (auto& pr : pairs) { gates.push_back(make_gate(pr[1], pr[0], kX, -1)); taken.push_back((int)gates.size() - 1); }
+                swaps.push_back({x, y});
+                std::swap(next_use[x], next_use[y]);     // the gates written for x now find their data at y and vice versa
+            };
+            for (int sl = 0; sl < min_low; ++sl) trial[sl] = partner[sl];
+            if (rest.empty()) {
+                // last pass of this call: send every displaced qubit home that this tile can reach
+                for (int sl = 0; sl < min_low; ++sl)
+                    if (trial[sl] != sl && ((tile >> trial[sl]) & 1)) { append_swap(sl, trial[sl]); trial[sl] = sl; }
+            } else {
+                for (int sl = 0; sl < min_low; ++sl) {
+                    const int cur = trial[sl];
+                    if (cur != sl && !((tile >> cur) & 1)) continue;     // the resident's home is not in this tile
+                    int best = -1;
+                    for (int q = min_low; q < n_local; ++q) {
+                        if (!((tile >> q) & 1) || q == cur) continue;
+                        bool is_partner = false;
+                        for (int s2 = 0; s2 < min_low; ++s2) if (trial[s2] == q) is_partner = true;
+                        if (is_partner) continue;
+                        if (next_use[q] < next_use[sl] && (best < 0 || next_use[q] < next_use[best])) best = q;
+                    }
+                    if (best < 0) continue;
+                    if (cur != sl) append_swap(sl, cur);                 // the old resident goes home first (keeps the
+                    append_swap(sl, best);                               //   layout a product of disjoint transpositions)
+                    trial[sl] = best;
+                }
+            }
+        }
 
         // ---- tile positions: pinned low run, then by first non-permutation target use -----------
         // Two hand-out orders of the free tile positions are planned and the one with fewer stage switches
@@ -862,14 +921,32 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
         for (int gi : taken) if (!gates[gi].diag) pass.touch_mask |= gates[gi].tmask;
         if (pass.desc.n_ops >= MAX_OPS_PER_PASS || pass.desc.n_tab > MAX_TABLE_OPS) {
             // the op list is a kernel parameter of bounded size: take fewer gates and plan this pass again
-            if (taken.size() <= 1) throw std::runtime_error("plan_local: one gate does not fit a pass");
-            gate_budget = (int)taken.size() / 2;
+            if (taken.size() - 3 * swaps.size() <= 1) throw std::runtime_error("plan_local: one gate does not fit a pass");
+            gate_budget = (int)(taken.size() - 3 * swaps.size()) / 2;
             acc = acc_start;
+            gates.resize(gates_start);     // drop the swap gates of the rejected attempt
             continue;
         }
         gate_budget = opt.max_ops_per_pass;
         pass.finish_tables();
         passes.push_back(std::move(pass));
+        // the pass is accepted: its swaps are now part of the state, rename the qubits of every gate still to run
+        for (auto& sw : swaps)
+            for (int gi : rest) {
+                gates[gi].tmask = swap_bits(gates[gi].tmask, sw.first, sw.second);
+                gates[gi].cmask = swap_bits(gates[gi].cmask, sw.first, sw.second);
+            }
+        for (int sl = 0; sl < min_low; ++sl) partner[sl] = trial[sl];
+        if (rest.empty()) {
+            // qubits still away from home (their partner was outside the last tile): one more pass of swaps only
+            for (int sl = 0; sl < min_low; ++sl)
+                if (partner[sl] != sl) {
+                    const int x = sl, y = partner[sl];
+                    const int pairs[3][2] = {{x, y}, {y, x}, {x, y}};
+                    for (auto& pr : pairs) { gates.push_back(make_gate(pr[1], pr[0], kX, -1)); rest.push_back((int)gates.size() - 1); }
+                    partner[sl] = sl;
+                }
+        }
         pending.swap(rest);
     }
     return passes;

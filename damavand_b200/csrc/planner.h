@@ -56,6 +56,12 @@ struct PlanOptions {
     int max_ops_per_pass = 1024;   // gates taken into one pass (halved and retried while the op stream exceeds MAX_OPS_PER_PASS)
     bool macro_ops = true;     // fuse 4-op runs on the four register bits into one dispatch (OC_REALPH4, OC_TWHAD4)
     bool best_group = false;   // stage order: group with the most runnable work (true) or group of the first waiting gate
+    bool relabel = false;      // tile relabelling (experimental, replay-tested only): the pinned low tile positions are
+                               //   physical qubits [0, min_low), present in every tile; at the end of a pass the logical
+                               //   qubit held there may trade places with one of the tile's other qubits that the
+                               //   following gates need sooner (three CNOTs = one more column swap of the permuting
+                               //   transpose, no HBM traffic), so the next pass has 12 useful positions instead of 9.
+                               //   The layout is back to identity when plan_local returns.
 };
 
 // Classify a 2x2 by exact zero / one tests on its entries.

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstring>
 #include <stdexcept>
+#include <cstdlib>
 #include <vector>
 
 #include "../../damavand_b200/csrc/planner.cpp"
@@ -159,6 +160,7 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
         for (int q = 0; q < n_qubits; ++q) if (perm[q] != q) throw std::runtime_error("emu: layout not restored");
         int64_t n_pass = 0, n_swap = 0, n_switch = 0, n_ops = 0;
         PlanOptions opt;
+        if (const char* e = getenv("DVD_RELABEL")) opt.relabel = atoi(e) != 0;   // experimental tile relabelling
         // per-rank support masks (engine.cu: dvd_state::support); dense when tracking is off
         const uint64_t local_mask = chunk - 1;
         std::vector<uint64_t> support(world, (g_track_support && n_local >= TILE_BITS) ? ~local_mask : ~0ull);

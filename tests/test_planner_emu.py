@@ -193,3 +193,28 @@ def test_replay_against_committed_fixtures(kind):
     for track in (False, True):
         got, _ = emu_run(c, 1, track_support=track)
         assert rel_err(got, fx[f"{kind}_amplitudes"]) < TOL
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_tile_relabelling_option(monkeypatch, world):
+    """PlanOptions::relabel (experimental, off by default): the qubit held in the pinned low tile positions trades
+    places with hotter tile qubits at the end of a pass.  Fewer passes on chain-like circuits, same amplitudes, and
+    the layout is back to identity at the end (the replay compares in the reference's index order)."""
+    n = 18
+    def build():
+        c = OracleCircuit(n)
+        circuits.hea(c, n, 6)
+        c.add_hadamard_gate(0); c.add_cnot_gate(0, n - 1); c.add_rotation_x_gate(1, 0.3)
+        return c
+    monkeypatch.setenv("DVD_RELABEL", "0")
+    base, st0 = emu_run(build(), world)
+    monkeypatch.setenv("DVD_RELABEL", "1")
+    got, st1 = emu_run(build(), world)
+    got_sp, _ = emu_run(build(), world, track_support=True)
+    ref = build(); ref.forward()
+    assert rel_err(base, ref.amplitudes()) < TOL
+    assert rel_err(got, ref.amplitudes()) < TOL
+    assert rel_err(got_sp, ref.amplitudes()) < TOL
+    assert st1["passes"] <= st0["passes"], (st0, st1)
+    if world == 1:
+        assert st1["passes"] < st0["passes"], (st0, st1)
