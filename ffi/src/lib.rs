@@ -87,4 +87,11 @@ extern "C" {
     pub fn dvd_timer_begin(s: *mut dvd_state) -> c_int;
     pub fn dvd_timer_end(s: *mut dvd_state, elapsed_ms: *mut c_double) -> c_int;
     pub fn dvd_set_unfused(s: *mut dvd_state, unfused: c_int) -> c_int;
+    // run-time specialised pass kernels (NVRTC): 0 off, 1 background compile, 2 compile on first use
+    pub fn dvd_set_jit(s: *mut dvd_state, mode: c_int) -> c_int;
+    pub fn dvd_jit_wait(s: *mut dvd_state) -> c_int;
+    pub fn dvd_jit_info(
+        s: *mut dvd_state, compiled: *mut i64, failed: *mut i64, pending: *mut i64,
+        compile_seconds: *mut c_double, last_error: *mut c_char, cap: i64,
+    ) -> c_int;
 }
