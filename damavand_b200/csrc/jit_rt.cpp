@@ -57,7 +57,7 @@ struct Api {
             if (!h_nvrtc) { why = std::string("dlopen(libnvrtc.so.12) failed: ") + dlerror(); return why; }
 #define DVD_SYM(h, field, name)                                                  \
     field = reinterpret_cast<decltype(field)>(dlsym(h, name));                   \
-    if (!field) { why = std::string("symbol missing: ") + name; return why; }
+    if (!field) { why = std::string("symbol missing: ") + name; h = nullptr; return why; }   /* retried next call */
             DVD_SYM(h_nvrtc, CreateProgram, "nvrtcCreateProgram")
             DVD_SYM(h_nvrtc, CompileProgram, "nvrtcCompileProgram")
             DVD_SYM(h_nvrtc, GetCUBINSize, "nvrtcGetCUBINSize")
