@@ -430,21 +430,17 @@ def main():
             sp_name = "random32"
             c2 = Circuit(workload_qubits(sp_name), "gpu")
             ng2 = build_workload(c2, sp_name)
-            if jit:
-                c2.set_jit(1)
-            for _ in range(2):
-                c2.reset_amplitudes(); c2.forward_async()
-            c2.synchronize()
-            if jit:
-                c2.jit_wait()
-                c2.reset_amplitudes(); c2.forward_async(); c2.synchronize()
+            # same step definition and the same (interpreter) kernels as the N > 1 runs use by default
+            c2.reset_amplitudes(); c2.forward_async()
+            c2.forward_async(); c2.synchronize()
             c2.timer_begin()
             for _ in range(2):
-                c2.reset_amplitudes(); c2.forward_async()
+                c2.forward_async()
             ms2 = c2.timer_end()
             scaling_point = {"workload": f"{sp_name}: {workload_desc(sp_name)}", "n_gpus": 1, "value": 2 * ng2 / (ms2 / 1e3),
-                             "unit": "gates/s", "ms_per_step": ms2 / 2, "steps": 2, "warmup": 2,
-                             "note": "same step definition as `value`; divide the N-GPU lines' value by N x this for strong-scaling efficiency"}
+                             "unit": "gates/s", "ms_per_step": ms2 / 2, "steps": 2, "warmup": 2, "jit": False,
+                             "note": "same step definition as `value` (forward on a dense state), interpreter kernels as in "
+                                     "the default N > 1 runs; divide an N-GPU line's value by N x this for strong-scaling efficiency"}
             c2.close()
         except Exception as e:
             scaling_point = {"workload": "random32", "value": None, "note": f"failed: {e}"}
