@@ -52,10 +52,16 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
+
+    nvidia-smi needs about a second before its first sample, so it is started before the warm-up; stop(t0, t1) keeps
+    the samples whose timestamp lies inside the timed region [t0, t1] (datetime, host clock).  When the region is shorter
+    than the 100 ms sampling period, the samples taken under load during the warm-up right before it stand in
+    (`window` says which)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, device: int):
         self.device = device
@@ -72,35 +78,67 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+    @classmethod
+    def summarise(cls, lines, t0=None, t1=None):
+        """lines: nvidia-smi csv rows (strings).  Returns the clocks dict of the bench contract."""
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": None}
+        rows = []
+        for line in lines:
+            r = [x.strip() for x in line.strip().split(",")]
+            if len(r) < 10:
+                continue
+            ts = None
+            for fmt in ("%Y/%m/%d %H:%M:%S.%f", "%Y/%m/%d %H:%M:%S", "%Y-%m-%d %H:%M:%S.%f"):
+                try:
+                    ts = datetime.datetime.strptime(r[0], fmt)
+                    break
+                except ValueError:
+                    pass
+            try:
+                power = float(r[4])
+            except ValueError:
+                power = 0.0
+            try:
+                # an unparsable timestamp keeps the row (as "before the region"): clocks are still worth reporting
+                rows.append((ts or datetime.datetime.min, float(r[2]), float(r[3]), power, r[6:10]))
+            except ValueError:
+                continue
+        if not rows:
             return out
+        inside = [x for x in rows if t0 is not None and t1 is not None and t0 <= x[0] <= t1]
+        if inside:
+            use, window = inside, "timed region"
+        else:
+            # region shorter than the sampling period: fall back to the samples under load (power within 70 % of the
+            # highest seen) taken before its end, i.e. during the warm-up of the same workload
+            before = [x for x in rows if t1 is None or x[0] <= t1] or rows
+            pmax = max(x[3] for x in before)
+            use = [x for x in before if x[3] >= 0.7 * pmax] or before
+            window = "under load before the end of the timed region (region shorter than the sampling period)"
+        reasons = set()
+        for x in use:
+            for k, name in enumerate(cls.NAMES):
+                if x[4][k].lower().startswith("active"):
+                    reasons.add(name)
+        out.update(sm_mhz=float(np.median([x[1] for x in use])), sm_max_mhz=float(max(x[2] for x in use)),
+                   reasons=sorted(reasons), samples=len(use), window=window)
+        return out
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return self.summarise([])
         try:
             self.proc.terminate()
             self.proc.wait(timeout=5)
         except Exception:
             pass
         try:
-            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            lines = open(self.path).read().splitlines()
             os.unlink(self.path)
         except Exception:
-            return out
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            if len(r) < 9:
-                continue
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except ValueError:
-                continue
-            for k, name in enumerate(names):
-                if r[5 + k].strip().lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
-        return out
+            return self.summarise([])
+        return self.summarise(lines, t0, t1)
 
 
 def build_workload(circ, name):
@@ -266,6 +304,9 @@ def main():
     jit = args.jit if args.jit is not None else int(os.environ.get("DVD_BENCH_JIT", "1" if args.gpus == 1 else "0"))
     if jit:
         circ.set_jit(1)
+    sampler = ClockSampler(device)     # started before the warm-up: nvidia-smi needs ~1 s before its first sample
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         one_step()
     if jit:
@@ -276,9 +317,6 @@ def main():
         one_step(); circ.forward_async(); circ.synchronize()
     barrier()
     circ.stats_reset()
-    sampler = ClockSampler(device)
-    if rank == 0:
-        sampler.start()
     barrier()
     t_wall0 = time.perf_counter()
     circ.timer_begin()
@@ -307,6 +345,8 @@ def main():
     circ.stats_reset()
     barrier()
     dense_reps = max(1, args.steps)                    # the headline region: EXACTLY --steps forwards
+    import datetime
+    t_region0 = datetime.datetime.now()
     t_wall0 = time.perf_counter()
     circ.timer_begin()
     for _ in range(dense_reps):
@@ -314,7 +354,7 @@ def main():
     fwd_ms = circ.timer_end() / dense_reps
     barrier()
     t_wall_dense = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, datetime.datetime.now()) if rank == 0 else None
     if args.gpus > 1:
         import torch
         import torch.distributed as dist

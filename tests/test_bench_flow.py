@@ -111,3 +111,19 @@ def test_gpu_arm_flow_with_stub_engine(monkeypatch, argv):
         assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 8
     assert ("scaling_point" in d) == (argv == [])
     assert (d["config"]["jit"] is False) == ("--jit" in argv)
+
+
+def test_clock_sampler_windowing():
+    """nvidia-smi rows are filtered to the timed region by timestamp; a region shorter than the sampling period falls
+    back to the samples under load before its end; throttle reasons are collected from the rows used."""
+    import datetime
+    import bench
+    row = lambda t, sm, p, cap="Not Active": f"2026/10/17 13:56:{t:06.3f}, 0, {sm}, 1965, {p}, 0x0, Not Active, Not Active, Not Active, {cap}"
+    lines = [row(1.0, 345, 180.0), row(1.1, 1965, 700.0), row(1.2, 1950, 720.0, "Active"), row(1.3, 1965, 710.0), row(1.4, 600, 200.0), "garbage"]
+    T = lambda sec: datetime.datetime(2026, 10, 17, 13, 56, int(sec), int(round((sec % 1) * 1e6)))
+    c = bench.ClockSampler.summarise(lines, T(1.15), T(1.35))
+    assert c["samples"] == 2 and c["sm_mhz"] == 1957.5 and c["sm_max_mhz"] == 1965 and c["reasons"] == ["sw_power_cap"]
+    assert c["window"] == "timed region"
+    c = bench.ClockSampler.summarise(lines, T(1.31), T(1.33))          # no sample inside: samples under load before 1.33
+    assert c["samples"] == 3 and c["sm_mhz"] == 1965 and "shorter" in c["window"]
+    assert bench.ClockSampler.summarise([])["samples"] == 0
