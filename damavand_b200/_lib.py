@@ -87,6 +87,7 @@ SIGNATURES = {
     "dvd_set_jit": (ctypes.c_int, [_VP, ctypes.c_int]),
     "dvd_jit_wait": (ctypes.c_int, [_VP]),
     "dvd_jit_info": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), _DP, ctypes.c_char_p, ctypes.c_int64]),
+    "dvd_jit_forms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int64)]),
     "dvd_jit_debug_compile": (ctypes.c_int64, [ctypes.c_char_p]),
     "dvd_jit_debug_source": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(Gate), ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int64]),
     "dvd_plan_distributed_debug": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(Gate), ctypes.c_int64, _I32P, ctypes.c_int, _I32P, ctypes.c_int64]),

@@ -346,8 +346,13 @@ class Circuit:
         msg = ctypes.create_string_buffer(4096)
         _lib.check(self._lib.dvd_jit_info(self._handle, ctypes.byref(c), ctypes.byref(f), ctypes.byref(q), ctypes.byref(sec), msg, 4096),
                    "dvd_jit_info")
+        forms = (ctypes.c_int64 * 7)()
+        _lib.check(self._lib.dvd_jit_forms(forms), "dvd_jit_forms")
+        names = ("classic2", "classic3", "ring")
         return {"compiled": c.value, "failed": f.value, "pending": q.value, "compile_seconds": sec.value,
-                "message": msg.value.decode(errors="replace")}
+                "message": msg.value.decode(errors="replace"), "tuning": int(forms[0]),
+                "chosen": {n: int(forms[1 + i]) for i, n in enumerate(names)},
+                "launches": {n: int(forms[4 + i]) for i, n in enumerate(names)}}
 
     def set_unfused(self, flag: bool):
         _lib.check(self._lib.dvd_set_unfused(self._handle, int(bool(flag))), "dvd_set_unfused")

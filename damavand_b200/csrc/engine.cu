@@ -836,6 +836,13 @@ int dvd_jit_info(dvd_state* s, int64_t* compiled, int64_t* failed, int64_t* pend
     }
     return DVD_OK;
 }
+int dvd_jit_forms(int64_t out[7]) {
+    if (!out) return fail(DVD_ERR_ARG, "null argument");
+    const JitStats st = jit_stats();
+    out[0] = st.tuning;
+    for (int f = 0; f < 3; ++f) { out[1 + f] = st.chosen[f]; out[4 + f] = st.launches[f]; }
+    return DVD_OK;
+}
 int dvd_set_unfused(dvd_state* s, int unfused) {
     if (!s) return fail(DVD_ERR_ARG, "null state");
     s->unfused = unfused != 0;
@@ -885,12 +892,12 @@ int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t 
 // Generated source of the structure-specialised kernel of pass `pass_index` (development / tests).  Returns the
 // length written (without the terminator), -needed if cap is too small, INT64_MIN on a planner error.
 int64_t dvd_jit_debug_source(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates, int pass_index,
-                             int persistent, char* out, int64_t cap) {
+                             int form, char* out, int64_t cap) {
     try {
         PlanOptions opt;
         std::vector<Pass> passes = plan_local(fuse_diagonal_runs(to_host_gates(gates, n_gates)), n_local, n_total, opt);
         if (pass_index < 0 || pass_index >= (int)passes.size()) return 0;
-        const std::string src = generate_pass_source(passes[pass_index], "dvd_pass_static", persistent != 0);
+        const std::string src = generate_pass_source(passes[pass_index], "dvd_pass_static", form < 0 || form >= FORM_COUNT ? FORM_CLASSIC2 : form);
         if ((int64_t)src.size() + 1 > cap) return -(int64_t)(src.size() + 1);
         std::memcpy(out, src.c_str(), src.size() + 1);
         return (int64_t)src.size();

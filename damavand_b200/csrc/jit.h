@@ -15,13 +15,19 @@
 
 namespace dvd {
 
+// Kernel forms a pass structure can be compiled into (jit_rt picks per structure, by measurement):
+//   FORM_CLASSIC2  one tile per CTA, 256 threads, two CTAs per SM (<= 128 registers);
+//   FORM_CLASSIC3  the same with __launch_bounds__(256, 3): three CTAs = 24 warps per SM if it fits 80 registers
+//                  (kept only where ptxas needed no or next to no local memory);
+//   FORM_RING      persistent, one CTA of 2 x 256 threads per SM, three shared-memory tile buffers filled by cp.async a
+//                  full tile period ahead (tile_kernel.cuh, "two-group persistent form"); dense states only.
+enum JitForm : int { FORM_CLASSIC2 = 0, FORM_CLASSIC3 = 1, FORM_RING = 2, FORM_COUNT = 3 };
+
 // Structure key of a pass: equal keys <=> identical generated source.
-std::vector<uint32_t> pass_structure_key(const Pass& p, bool persistent = false);
+std::vector<uint32_t> pass_structure_key(const Pass& p, int form = FORM_CLASSIC2);
 
 // CUDA source of `extern "C" __global__ void <fn_name>(cplx*, const PassParams)`; expects tile_kernel.cuh to be
-// includable under that name.  persistent: one CTA per resident slot loops over the tiles and fetches the next
-// tile with cp.async once the last transpose of the current one has been read back (the specialised form of
-// k_tile_pass_persist; dense states only).  Experimental: not yet measured on a GPU, off unless DVD_JIT_PERSIST=1.
-std::string generate_pass_source(const Pass& p, const std::string& fn_name, bool persistent = false);
+// includable under that name.
+std::string generate_pass_source(const Pass& p, const std::string& fn_name, int form = FORM_CLASSIC2);
 
 }  // namespace dvd

@@ -41,6 +41,7 @@ struct Api {
     CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
     CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
     CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
 
@@ -73,6 +74,7 @@ struct Api {
             DVD_SYM(h_cuda, ModuleLoadData, "cuModuleLoadData")
             DVD_SYM(h_cuda, ModuleGetFunction, "cuModuleGetFunction")
             DVD_SYM(h_cuda, FuncSetAttribute, "cuFuncSetAttribute")
+            DVD_SYM(h_cuda, FuncGetAttribute, "cuFuncGetAttribute")
             DVD_SYM(h_cuda, LaunchKernel, "cuLaunchKernel")
             DVD_SYM(h_cuda, GetErrorString, "cuGetErrorString")
 #undef DVD_SYM
@@ -89,16 +91,36 @@ struct Api {
 
 struct Entry {
     enum State { QUEUED, COMPILED, FAILED } state = QUEUED;
+    int form = FORM_CLASSIC2;
     std::vector<char> cubin;
     std::string log;
-    std::map<int, CUfunction> fn;    // per device (module loaded in that device's primary context)
+    struct Loaded { CUfunction fn = nullptr; int local_bytes = 0; int regs = 0; };
+    std::map<int, Loaded> fn;    // per device (module loaded in that device's primary context)
+};
+
+// One pass structure: its kernel forms and the choice between them.  The choice is MEASURED: once every candidate
+// has been compiled, dense full-grid launches of the structure rotate through the candidates bracketed by CUDA
+// events until each has TUNE_SAMPLES timings of the same grid; the fastest is kept (per device).
+constexpr int TUNE_SAMPLES = 2;
+struct Tuner {
+    std::shared_ptr<Entry> e[FORM_COUNT];
+    struct Sample { cudaEvent_t t0 = nullptr, t1 = nullptr; int form = 0; };
+    struct PerDevice {
+        int best_dense = -1;          // decided form for dense launches (-1: still measuring)
+        int best_classic = -1;        // decided classic form (launches with a support mask, or too few tiles for the ring)
+        int sig = -1;                 // n_cta_bits of the launches being compared
+        std::vector<float> ms[FORM_COUNT];
+        std::vector<Sample> pending;
+        bool dropped[FORM_COUNT] = {false, false, false};   // form failed to load / needs too much local memory
+    };
+    std::map<int, PerDevice> dev;
 };
 
 struct Runtime {
     std::mutex mu;
     std::condition_variable cv;
     Api api;
-    std::map<std::vector<uint32_t>, std::shared_ptr<Entry>> entries;
+    std::map<std::vector<uint32_t>, std::shared_ptr<Tuner>> tuners;   // key: pass_structure_key(p, FORM_CLASSIC2)
     std::deque<std::pair<std::shared_ptr<Entry>, std::string>> queue;
     std::vector<std::thread> workers;
     std::map<int, int> sm_count;     // per device
@@ -118,7 +140,7 @@ struct Runtime {
     void start_workers() {   // mu held
         if (!workers.empty()) return;
         unsigned n = std::thread::hardware_concurrency();
-        n = n == 0 ? 2 : (n > 4 ? 4 : n);
+        n = n == 0 ? 2 : (n > 12 ? 12 : n);
         for (unsigned i = 0; i < n; ++i) workers.emplace_back([this] { work(); });
     }
     void work() {
@@ -248,64 +270,192 @@ std::string jit_available() {
     return r.api.load(true);
 }
 
+namespace {
+
+// DVD_JIT_FORM: classic2 | classic3 | ring force one kernel form (development, parity tests); anything else = measure.
+int forced_form() {
+    const char* e = getenv("DVD_JIT_FORM");
+    if (!e) return -1;
+    const std::string v(e);
+    if (v == "classic2") return FORM_CLASSIC2;
+    if (v == "classic3") return FORM_CLASSIC3;
+    if (v == "ring") return FORM_RING;
+    return -1;
+}
+// a classic3 kernel that had to spill more than this is not worth measuring
+constexpr int CLASSIC3_MAX_LOCAL_BYTES = 256;
+
+// Load `e` on `device` if it has not been yet.  mu held.  Returns nullptr when the kernel cannot be used.
+const Entry::Loaded* loaded_fn(Runtime& r, Entry& e, int device, std::string* err) {
+    if (e.state != Entry::COMPILED) return nullptr;
+    auto it = e.fn.find(device);
+    if (it != e.fn.end()) return &it->second;
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+    CUresult rc = r.api.ModuleLoadData(&mod, e.cubin.data());
+    if (rc == CUDA_SUCCESS) rc = r.api.ModuleGetFunction(&fn, mod, "dvd_pass_static");
+    const int smem = e.form == FORM_RING ? RING_SMEM_BYTES : TILE_SLOTS * (int)sizeof(cplx);
+    if (rc == CUDA_SUCCESS) rc = r.api.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
+    if (rc != CUDA_SUCCESS) {
+        if (err) *err = "jit module load: " + r.api.cu_error(rc);
+        e.state = Entry::FAILED;
+        return nullptr;
+    }
+    Entry::Loaded l;
+    l.fn = fn;
+    r.api.FuncGetAttribute(&l.local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, fn);
+    r.api.FuncGetAttribute(&l.regs, CU_FUNC_ATTRIBUTE_NUM_REGS, fn);
+    return &(e.fn[device] = l);
+}
+
+// Collect the tuning launches whose events have completed.  mu held.
+void harvest(Tuner::PerDevice& d) {
+    for (size_t i = 0; i < d.pending.size();) {
+        Tuner::Sample& sm = d.pending[i];
+        if (cudaEventQuery(sm.t1) != cudaSuccess) { cudaGetLastError(); ++i; continue; }
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sm.t0, sm.t1) == cudaSuccess) d.ms[sm.form].push_back(ms); else cudaGetLastError();
+        cudaEventDestroy(sm.t0); cudaEventDestroy(sm.t1);
+        d.pending.erase(d.pending.begin() + (long)i);
+    }
+}
+
+}  // namespace
+
 bool jit_launch(const Pass& p, int mode, int device, cplx* amp, const PassParams& pp, cudaStream_t stream, std::string* err) {
     if (mode == JIT_OFF) return false;
     Runtime& r = rt();
     CUfunction fn = nullptr;
-    // experimental persistent (cp.async prefetch) form: dense states only, off unless DVD_JIT_PERSIST=1
-    const char* pe = getenv("DVD_JIT_PERSIST");
-    bool persistent = pe && atoi(pe) != 0 && pp.pd.zero_mask == 0;
-    unsigned resident = 0;
+    int form = FORM_CLASSIC2;
+    unsigned sms = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::shared_ptr<Tuner> tuner;
     {
         std::unique_lock<std::mutex> lk(r.mu);
         if (!r.api.load(true).empty()) return false;
-        if (persistent && r.sm_count.find(device) == r.sm_count.end()) {
-            int sms = 0;
-            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 0; }
-            r.sm_count[device] = sms;
+        if (r.sm_count.find(device) == r.sm_count.end()) {
+            int n = 0;
+            if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 0; }
+            r.sm_count[device] = n;
         }
-        if (persistent) {
-            resident = 2u * (unsigned)r.sm_count[device];      // __launch_bounds__(NTHREADS, 2): two CTAs per SM
-            if (resident == 0 || (1u << pp.pd.n_cta_bits) <= resident) persistent = false;
-        }
-        const std::vector<uint32_t> key = pass_structure_key(p, persistent);
-        std::shared_ptr<Entry>& slot = r.entries[key];
+        sms = (unsigned)r.sm_count[device];
+        std::shared_ptr<Tuner>& slot = r.tuners[pass_structure_key(p, FORM_CLASSIC2)];
         if (!slot) {
-            slot = std::make_shared<Entry>();
-            r.queue.emplace_back(slot, generate_pass_source(p, "dvd_pass_static", persistent));
-            ++r.stats.pending;
+            slot = std::make_shared<Tuner>();
+            const int forced = forced_form();
+            for (int f = 0; f < FORM_COUNT; ++f) {
+                if (forced >= 0 && f != forced && f != FORM_CLASSIC2) continue;   // classic2 always exists: it runs every launch
+                slot->e[f] = std::make_shared<Entry>();
+                slot->e[f]->form = f;
+                r.queue.emplace_back(slot->e[f], generate_pass_source(p, "dvd_pass_static", f));
+                ++r.stats.pending;
+            }
             r.start_workers();
             r.cv.notify_all();
         }
-        std::shared_ptr<Entry> e = slot;
-        if (mode == JIT_SYNC) r.cv.wait(lk, [&] { return e->state != Entry::QUEUED; });
-        if (e->state != Entry::COMPILED) {
-            if (e->state == Entry::FAILED && err && !e->log.empty()) { *err = "jit compile: " + e->log; e->log.clear(); }
-            return false;
-        }
-        auto it = e->fn.find(device);
-        if (it == e->fn.end()) {
-            CUmodule mod = nullptr;
-            CUresult rc = r.api.ModuleLoadData(&mod, e->cubin.data());
-            if (rc == CUDA_SUCCESS) rc = r.api.ModuleGetFunction(&fn, mod, "dvd_pass_static");
-            if (rc == CUDA_SUCCESS)
-                rc = r.api.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, TILE_SLOTS * (int)sizeof(cplx));
-            if (rc != CUDA_SUCCESS) {
-                if (err) *err = "jit module load: " + r.api.cu_error(rc);
-                e->state = Entry::FAILED;
-                return false;
+        tuner = slot;
+        Tuner& t = *tuner;
+        auto all_done = [&] {
+            for (auto& e : t.e) if (e && e->state == Entry::QUEUED) return false;
+            return true;
+        };
+        if (mode == JIT_SYNC) r.cv.wait(lk, all_done);
+        // the ring form needs a dense state and enough tiles to keep every SM's ring turning
+        const unsigned n_tiles = 1u << pp.pd.n_cta_bits;
+        const char* mt = getenv("DVD_RING_MIN_TILES");
+        const bool ring_ok = pp.pd.zero_mask == 0 && sms > 0 && (long)n_tiles >= (mt ? atol(mt) : 8l * (long)sms);
+        Tuner::PerDevice& d = t.dev[device];
+        auto usable = [&](int f) -> const Entry::Loaded* {
+            if (!t.e[f] || d.dropped[f]) return nullptr;
+            std::string lerr;
+            const Entry::Loaded* l = loaded_fn(r, *t.e[f], device, &lerr);
+            if (!l) {
+                if (t.e[f]->state == Entry::FAILED) {
+                    d.dropped[f] = true;
+                    if (err && !t.e[f]->log.empty()) { *err = "jit compile: " + t.e[f]->log; t.e[f]->log.clear(); }
+                    else if (err && !lerr.empty()) *err = lerr;
+                }
+                return nullptr;
             }
-            e->fn[device] = fn;
+            if (f == FORM_CLASSIC3 && l->local_bytes > CLASSIC3_MAX_LOCAL_BYTES) { d.dropped[f] = true; return nullptr; }
+            return l;
+        };
+        const int forced = forced_form();
+        const Entry::Loaded* pick = nullptr;
+        if (forced >= 0) {
+            form = (forced == FORM_RING && !ring_ok) ? FORM_CLASSIC2 : forced;
+            pick = usable(form);
+            if (!pick && form != FORM_CLASSIC2) { form = FORM_CLASSIC2; pick = usable(form); }
+        } else if (!all_done()) {
+            form = FORM_CLASSIC2;          // the other candidates are still compiling
+            pick = usable(form);
         } else {
-            fn = it->second;
+            harvest(d);
+            const bool dense_full = ring_ok;
+            if (dense_full && d.best_dense < 0 && (d.sig < 0 || d.sig == pp.pd.n_cta_bits)) {
+                // measuring: the usable candidate with the fewest timings (finished or in flight) runs next
+                int n_have[FORM_COUNT];
+                for (int f = 0; f < FORM_COUNT; ++f) n_have[f] = (int)d.ms[f].size();
+                for (auto& sm : d.pending) ++n_have[sm.form];
+                int cand = -1;
+                bool complete = true;
+                for (int f = 0; f < FORM_COUNT; ++f) {
+                    if (!usable(f)) continue;
+                    if ((int)d.ms[f].size() < TUNE_SAMPLES) complete = false;
+                    if (n_have[f] < TUNE_SAMPLES && (cand < 0 || n_have[f] < n_have[cand])) cand = f;
+                }
+                if (complete) {
+                    float best = 0.f, best_c = 0.f;
+                    for (int f = 0; f < FORM_COUNT; ++f) {
+                        if (!usable(f)) continue;
+                        float m = d.ms[f][0];
+                        for (float v : d.ms[f]) m = v < m ? v : m;
+                        if (d.best_dense < 0 || m < best) { d.best_dense = f; best = m; }
+                        if (f != FORM_RING && (d.best_classic < 0 || m < best_c)) { d.best_classic = f; best_c = m; }
+                    }
+                } else if (cand >= 0) {
+                    form = cand;
+                    pick = usable(form);
+                    d.sig = pp.pd.n_cta_bits;
+                    if (pick && (cudaEventCreate(&ev0) != cudaSuccess || cudaEventCreate(&ev1) != cudaSuccess)) {
+                        cudaGetLastError();
+                        if (ev0) cudaEventDestroy(ev0);
+                        ev0 = ev1 = nullptr;
+                    }
+                }
+            }
+            if (!pick) {
+                form = dense_full ? (d.best_dense >= 0 ? d.best_dense : FORM_CLASSIC2)
+                                  : (d.best_classic >= 0 ? d.best_classic : FORM_CLASSIC2);
+                pick = usable(form);
+                if (!pick && form != FORM_CLASSIC2) { form = FORM_CLASSIC2; pick = usable(form); }
+            }
         }
+        if (!pick) return false;
+        fn = pick->fn;
     }
-    const unsigned ctas = persistent ? resident : 1u << pp.pd.n_cta_bits;
+    const bool ring = form == FORM_RING;
+    const unsigned ctas = ring ? sms : 1u << pp.pd.n_cta_bits;
+    const unsigned threads = ring ? RING_GROUPS * NTHREADS : NTHREADS;
+    const unsigned smem = ring ? (unsigned)RING_SMEM_BYTES : TILE_SLOTS * (unsigned)sizeof(cplx);
     void* params[] = {(void*)&amp, (void*)&pp};
-    const CUresult rc = r.api.LaunchKernel(fn, ctas, 1, 1, NTHREADS, 1, 1, TILE_SLOTS * (unsigned)sizeof(cplx), (CUstream)stream, params, nullptr);
+    if (ev0) cudaEventRecord(ev0, stream);
+    const CUresult rc = r.api.LaunchKernel(fn, ctas, 1, 1, threads, 1, 1, smem, (CUstream)stream, params, nullptr);
+    if (ev0) {
+        cudaEventRecord(ev1, stream);
+        std::lock_guard<std::mutex> lk(r.mu);
+        Tuner::Sample sm; sm.t0 = ev0; sm.t1 = ev1; sm.form = form;
+        tuner->dev[device].pending.push_back(sm);
+    }
     if (rc != CUDA_SUCCESS) {
         if (err) *err = "jit launch: " + r.api.cu_error(rc);
+        std::lock_guard<std::mutex> lk(r.mu);
+        tuner->dev[device].dropped[form] = true;
         return false;
+    }
+    {
+        std::lock_guard<std::mutex> lk(r.mu);
+        ++r.stats.launches[form];
     }
     return true;
 }
@@ -321,6 +471,13 @@ JitStats jit_stats() {
     std::lock_guard<std::mutex> lk(r.mu);
     JitStats s = r.stats;
     s.pending = (long)r.queue.size() + r.busy;
+    s.tuning = 0;
+    for (int f = 0; f < FORM_COUNT; ++f) s.chosen[f] = 0;
+    for (auto& kv : r.tuners)
+        for (auto& dv : kv.second->dev) {
+            if (dv.second.sig >= 0 && dv.second.best_dense < 0) ++s.tuning;
+            if (dv.second.best_dense >= 0) ++s.chosen[dv.second.best_dense];
+        }
     return s;
 }
 

@@ -32,7 +32,13 @@ bool jit_launch(const Pass& p, int mode, int device, cplx* amp, const PassParams
 // Block until every queued compilation has finished.
 void jit_wait();
 
-struct JitStats { long compiled = 0, failed = 0, pending = 0; double compile_seconds = 0.0; };
+struct JitStats {
+    long compiled = 0, failed = 0, pending = 0;
+    double compile_seconds = 0.0;
+    long tuning = 0;          // pass structures whose kernel form is still being measured
+    long chosen[3] = {0, 0, 0};    // structures per chosen form (jit.h: JitForm)
+    long launches[3] = {0, 0, 0};  // launches per form
+};
 JitStats jit_stats();
 
 // Compile a source with NVRTC to a cubin (used by jit_launch and by the CPU-side test of the generator).

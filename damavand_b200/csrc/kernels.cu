@@ -35,9 +35,9 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     if (tid < n_tab) s_wc[tid] = table_cta_const(tables, tid, gbase);
     // a tile whose fixed bits hit the support mask is all zero on input, hence on output: nothing to do (the engine
     // normally does not even launch those)
-    if (cbase & pd.zero_mask) return;
+    if (cbase & pd.zero_mask & ~pd.remap_lmask) return;
     cplx a[NREG];
-    tile_load<IO_GROUP>(amp, pd, a, cbase, tid);
+    tile_load<IO_GROUP>(amp, pd, a, cbase, tid);   // with a fused remap (pd.remap_n > 0) the input is pd.remap_src[..], out of place
 
     if (n_tab > 0) __syncthreads();
     ThreadCtx ctx;
@@ -74,47 +74,49 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     else tile_store<1>(amp, pd, a, gbase - pd.rank_bits);
 }
 
-// Persistent form of the same pass: one CTA per resident slot loops over tiles t = blockIdx.x, + gridDim.x, ...
-// As soon as the last transpose of tile t has been read back, the shared-memory tile is free, so the
-// amplitudes of tile t + gridDim.x are fetched into it with cp.async (no registers involved) while the last
-// group's gates and the write-back of tile t run; the per-CTA table constants of the next tile are
-// computed in the same shadow.  The load latency, which the one-tile-per-CTA form exposes once per
-// tile (its stalls are ~20 % of the warp time in profiles/r1_ncu_full_tile_qft30_v8.csv), is hidden.
+// Two-group persistent form of the same pass (tile_kernel.cuh, "ring"): one CTA of 2 x 256 threads per SM, three
+// shared-memory tile buffers; slot s is computed by group s % 2 in buffer s % 3, and as soon as its last transpose
+// has been read back the same threads fetch slot s + 3 into the buffer with cp.async -- a full tile period ahead of
+// its use by the other group.  No thread waits on a global load it issued itself; HBM reads, fp64 work and
+// shared-memory transposes of three different tiles overlap inside one SM.  Dense states only (zero_mask == 0).
 template <unsigned SET>
-__global__ void __launch_bounds__(NTHREADS, 2)
-k_tile_pass_persist(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
+__global__ void __launch_bounds__(RING_GROUPS * NTHREADS, 1)
+k_tile_pass_ring(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx* tile = reinterpret_cast<cplx*>(smem_raw);
-    __shared__ cplx s_wc[2][MAX_TABLE_OPS];
     const PassDesc& pd = pp.pd;
-    const int tid = threadIdx.x;
-    const unsigned n_tiles = 1u << pd.n_cta_bits;   // launched for dense states only (zero_mask == 0)
     const cplx* __restrict__ tables = pd.tables;
     const int n_tab = pd.n_tab;
+    const cplx* amp_in = amp;
+    const Ring ring = ring_setup(smem_raw);
+    const int grp = threadIdx.x / NTHREADS, tid = threadIdx.x % NTHREADS;
+    const unsigned n_tiles = 1u << pd.n_cta_bits, stride = gridDim.x;
     const int n_ops = pd.n_ops;
     const int last_switch = pd.last_switch;
-    unsigned t = blockIdx.x;
-    if (t >= n_tiles) return;
-    {
-        const uint64_t cb = cta_base_runs(pd, (uint64_t)t);
-        tile_prefetch<IO_GROUP>(tile, amp, pd, cb, tid);
-        if (tid < n_tab) s_wc[0][tid] = table_cta_const(tables, tid, cb | pd.rank_bits);
+    {   // prologue: slots 0 and 2 are fetched by group 0, slot 1 by group 1
+        const unsigned t0 = blockIdx.x + grp * stride;
+        if (t0 < n_tiles) ring_fetch(ring, grp, amp_in, pd, t0, tid);
+        if (grp == 0 && blockIdx.x + 2 * stride < n_tiles) ring_fetch(ring, 2, amp_in, pd, blockIdx.x + 2 * stride, tid);
+        if (tid < n_tab && t0 < n_tiles) ring.wcs(grp, 0)[tid] = table_cta_const(tables, tid, cta_base_runs(pd, t0) | pd.rank_bits);
     }
-    int buf = 0;
-    for (; t < n_tiles; t += gridDim.x, buf ^= 1) {
+    unsigned kslot = 0;
+    for (unsigned slot = grp; ; slot += RING_GROUPS, ++kslot) {
+        const unsigned t = blockIdx.x + slot * stride;
+        if (t >= n_tiles) break;
+        cplx* tile = ring.tile(slot);
+        const cplx* wcs = ring.wcs(grp, kslot);
+        const uint64_t gbase = cta_base_runs(pd, t) | pd.rank_bits;
+        ring_wait(ring, slot);
+        group_sync(grp);   // this group's previous slot is over everywhere; its table constants are visible
         cplx a[NREG];
-        cp_async_wait_all();
-        __syncthreads();               // s_wc[buf] is visible; nobody still reads the previous tile's transposes
         stage_load<IO_GROUP>(tile, a, tid);
-        const unsigned tn = t + gridDim.x;
-        const uint64_t gbase = cta_base_runs(pd, (uint64_t)t) | pd.rank_bits;
-        const cplx* wcs = s_wc[buf];
-        if (last_switch < 0 && tn < n_tiles) {   // no transpose in this pass: the tile buffer is free right away
-            __syncthreads();
-            const uint64_t cb = cta_base_runs(pd, (uint64_t)tn);
-            tile_prefetch<IO_GROUP>(tile, amp, pd, cb, tid);
-            if (tid < n_tab) s_wc[buf ^ 1][tid] = table_cta_const(tables, tid, cb | pd.rank_bits);
-        }
+        // the slot's buffer is free once its last transpose has been read back: fetch slot + 3 into it
+        auto release_buffer = [&]() {
+            group_sync(grp);
+            if (t + 3 * stride < n_tiles) ring_fetch(ring, slot + 3, amp_in, pd, t + 3 * stride, tid);
+            if (tid < n_tab && t + 2 * stride < n_tiles)
+                ring.wcs(grp, kslot + 1)[tid] = table_cta_const(tables, tid, cta_base_runs(pd, t + 2 * stride) | pd.rank_bits);
+        };
+        if (last_switch < 0) release_buffer();
         ThreadCtx ctx;
         ctx.pidx = gbase | tid_offset(pd, IO_GROUP, tid);
         ctx.ph = cplx{1.0, 0.0};
@@ -126,21 +128,16 @@ k_tile_pass_persist(cplx* __restrict__ amp, const __grid_constant__ PassParams p
             if (code >= OC_SWITCH) {
                 const int from = (code - OC_SWITCH) / NGROUPS, to = (code - OC_SWITCH) % NGROUPS;
                 flush_phase(a, ctx);
-                __syncthreads();
+                group_sync(grp);
                 if (from == 0) switch_store<0>(tile, a, tid, op, op.flags, gbase);
                 else if (from == 1) switch_store<1>(tile, a, tid, op, op.flags, gbase);
                 else switch_store<2>(tile, a, tid, op, op.flags, gbase);
-                __syncthreads();
+                group_sync(grp);
                 if (to == 0) stage_load<0>(tile, a, tid);
                 else if (to == 1) stage_load<1>(tile, a, tid);
                 else stage_load<2>(tile, a, tid);
                 ctx.pidx = gbase | tid_offset(pd, to, tid);
-                if (k == last_switch && tn < n_tiles) {
-                    __syncthreads();   // every thread has read its registers back: the tile buffer is free
-                    const uint64_t cb = cta_base_runs(pd, (uint64_t)tn);
-                    tile_prefetch<IO_GROUP>(tile, amp, pd, cb, tid);
-                    if (tid < n_tab) s_wc[buf ^ 1][tid] = table_cta_const(tables, tid, cb | pd.rank_bits);
-                }
+                if (k == last_switch) release_buffer();
                 continue;
             }
             k += apply_op<SET>(a, &op, code, op.flags, ctx, tables, n_tab, wcs);
@@ -479,33 +476,35 @@ constexpr unsigned V_FOURIER = C_HAD | C_DIAG | C_TABLE | C_MACRO_T;            
 constexpr unsigned V_COMMON = C_GENERAL | C_REAL | C_RX | C_HAD | C_DIAG | C_TABLE;  // everything but rare ops / macros
 constexpr unsigned VARIANTS[] = {V_LAYERED, V_FOURIER, V_COMMON, C_ALL};
 typedef void (*TileKernel)(cplx*, const PassParams);
-static TileKernel tile_kernel(int v, bool persist) {
+static TileKernel tile_kernel(int v, bool ring) {
     switch (v) {
-        case 0: return persist ? k_tile_pass_persist<V_LAYERED> : k_tile_pass<V_LAYERED>;
-        case 1: return persist ? k_tile_pass_persist<V_FOURIER> : k_tile_pass<V_FOURIER>;
-        case 2: return persist ? k_tile_pass_persist<V_COMMON> : k_tile_pass<V_COMMON>;
-        default: return persist ? k_tile_pass_persist<C_ALL> : k_tile_pass<C_ALL>;
+        case 0: return ring ? k_tile_pass_ring<V_LAYERED> : k_tile_pass<V_LAYERED>;
+        case 1: return ring ? k_tile_pass_ring<V_FOURIER> : k_tile_pass<V_FOURIER>;
+        case 2: return ring ? k_tile_pass_ring<V_COMMON> : k_tile_pass<V_COMMON>;
+        default: return ring ? k_tile_pass_ring<C_ALL> : k_tile_pass<C_ALL>;
     }
 }
 
 static int g_sm_count = 148;
-static int g_persist = 0;     // DVD_PERSIST: 0 = one tile per CTA, 1 = persistent CTAs with cp.async prefetch
-static int g_persist_ctas_per_sm = 2;
+static long g_ring_min_tiles = -1;   // DVD_RING_MIN_TILES: fewest tiles a pass needs for the ring form (default 8 per SM)
+static int g_ring = 0;        // DVD_RING: 1 = dense passes with enough tiles run the two-group persistent form, 0 = one tile per CTA
+
+long ring_min_tiles(int sm_count) { return g_ring_min_tiles >= 0 ? g_ring_min_tiles : 8l * sm_count; }
 
 cudaError_t kernels_init() {
     for (int p = 0; p < 2; ++p)
         for (int v = 0; v < 4; ++v) {
             cudaError_t e = cudaFuncSetAttribute(tile_kernel(v, p != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 TILE_SLOTS * (int)sizeof(cplx));
+                                                 p ? RING_SMEM_BYTES : TILE_SLOTS * (int)sizeof(cplx));
             if (e != cudaSuccess) return e;
         }
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
         g_sm_count = sms;
-    const char* e = getenv("DVD_PERSIST");        // re-read at every dvd_create: absent means the default again
-    g_persist = e ? atoi(e) != 0 : 0;
-    e = getenv("DVD_PERSIST_CTAS");
-    g_persist_ctas_per_sm = (e && atoi(e) > 0) ? atoi(e) : 2;
+    const char* e = getenv("DVD_RING");           // re-read at every dvd_create: absent means the default again
+    g_ring = e ? atoi(e) != 0 : 0;
+    e = getenv("DVD_RING_MIN_TILES");
+    g_ring_min_tiles = e ? atol(e) : -1;
     return cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 SAMPLE_WARPS * (2 << BLK_BITS) * (int)sizeof(double));
 }
@@ -522,9 +521,8 @@ cudaError_t launch_tile_pass(cplx* amp, PassParams& pp, cudaStream_t s) {
     int v = 0;
     while (v < 3 && (need & ~VARIANTS[v])) ++v;
     if (const char* e = getenv("DVD_KERNEL_VARIANT")) v = atoi(e) & 3;   // development: force a variant (3 = all ops)
-    const uint64_t resident = (uint64_t)g_sm_count * g_persist_ctas_per_sm;
-    if (g_persist && pp.pd.zero_mask == 0 && ctas > resident)
-        tile_kernel(v, true)<<<(unsigned)resident, NTHREADS, TILE_SLOTS * sizeof(cplx), s>>>(amp, pp);
+    if (g_ring && pp.pd.zero_mask == 0 && ctas >= (uint64_t)ring_min_tiles(g_sm_count))
+        tile_kernel(v, true)<<<(unsigned)g_sm_count, RING_GROUPS * NTHREADS, RING_SMEM_BYTES, s>>>(amp, pp);
     else
         tile_kernel(v, false)<<<(unsigned)ctas, NTHREADS, TILE_SLOTS * sizeof(cplx), s>>>(amp, pp);
     return cudaGetLastError();

@@ -10,6 +10,7 @@ namespace dvd {
 constexpr int BLK_BITS = 10;  // sampler / reduction leaf block: 2^10 amplitudes
 
 cudaError_t kernels_init();   // one-time function attributes (dynamic shared memory opt-in)
+long ring_min_tiles(int sm_count);   // fewest tiles of a dense pass for the two-group persistent form (DVD_RING_MIN_TILES)
 
 // Tiled multi-gate pass (n_local >= TILE_BITS).  pp (description + op list) travels as the kernel parameter.
 cudaError_t launch_tile_pass(cplx* amp, PassParams& pp, cudaStream_t s);   // fills pp.pd.last_switch

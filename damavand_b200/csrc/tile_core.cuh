@@ -188,7 +188,21 @@ struct PassDesc {
     uint64_t zero_mask;           // local qubits that are still |0> in every populated basis state (support tracking after
                                   //   a reset): amplitudes with one of these bits set are zero by construction, are never
                                   //   read, and tiles whose fixed bits hit the mask are not launched at all.  0 = dense state
+                                  //   (with a fused remap: a mask over the SOURCE index, i.e. the layout before the swap)
+    // Fused global<->local qubit remap (distributed_gpu, set by the engine): up to MAX_REMAP disjoint swaps of a
+    // rank-index qubit with a local qubit are executed by this pass's LOAD instead of by an exchange of their own.
+    // The pass then runs out of place: the amplitude at (new) local index i is read from
+    //     remap_src[sel(i)] + ((i & ~remap_lmask) | remap_const),   sel(i) = sum_k bit(remap_lq[k] of i) << k,
+    // where remap_src[sel] is this rank's own input buffer or a partner rank's (peer memory over NVLink, mapped with
+    // CUDA IPC) and remap_const holds this rank's bits of the swapped rank-index qubits, deposited at remap_lq[k].
+    // remap_n == 0: plain in-place pass.  Replaces exchange_amplitudes_between_gpus + the distributed gate kernel
+    // (rust_communication.cu:106-141, kernels.cu:174-230): the exchange IS the next pass's read.
+    int8_t remap_n;
+    int8_t remap_lq[3];
+    uint64_t remap_lmask, remap_const;
+    const cplx* remap_src[8];
 };
+constexpr int MAX_REMAP = 3;
 // Kernel parameter block: the pass description and its whole op list (<= 32764 B of parameters).
 constexpr int MAX_OPS_PER_PASS = 336;
 struct PassParams {
@@ -211,6 +225,13 @@ DVD_HD int stage_idx(int g, int tid, int j) {
 // address is an immediate offset from one per-thread base.
 constexpr int TILE_SLOTS = TILE_AMPS + TILE_AMPS / 16;
 DVD_HD int smem_slot(int idx) { return idx + (idx >> 4); }
+
+// Two-group persistent form (tile_kernel.cuh): dynamic shared memory =
+// [RING_BUFFERS tiles][per-group, double-buffered table constants][mbarriers]
+constexpr int RING_BUFFERS = 3;
+constexpr int RING_GROUPS = 2;
+constexpr int RING_WC_BYTES = RING_GROUPS * 2 * MAX_TABLE_OPS * (int)sizeof(cplx);
+constexpr int RING_SMEM_BYTES = RING_BUFFERS * TILE_SLOTS * (int)sizeof(cplx) + RING_WC_BYTES + 64;
 
 // Physical offset (in amplitudes) of tile index idx.
 DVD_HD uint64_t tile_offset(const PassDesc& pd, int idx) {
@@ -270,6 +291,16 @@ inline bool fill_cta_runs_sparse(PassDesc& pd, uint64_t skip) {
     return true;
 }
 #endif  // !__CUDACC_RTC__
+
+// Source of the amplitude at (new) local index i under a fused remap (PassDesc::remap_*): buffer and local index.
+DVD_HD unsigned remap_sel(const PassDesc& pd, uint64_t i) {
+    unsigned sel = 0;
+#pragma unroll
+    for (int k = 0; k < MAX_REMAP; ++k)
+        if (k < pd.remap_n) sel |= (unsigned)((i >> pd.remap_lq[k]) & 1ull) << k;
+    return sel;
+}
+DVD_HD uint64_t remap_index(const PassDesc& pd, uint64_t i) { return (i & ~pd.remap_lmask) | pd.remap_const; }
 
 // Local index of element h of the half-chunk whose bit lq equals bitval (global<->local qubit swap).
 DVD_HD uint64_t half_index(uint64_t h, int lq, int bitval) {

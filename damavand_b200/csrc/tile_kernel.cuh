@@ -42,8 +42,14 @@ __device__ __forceinline__ void stage_store_perm(cplx* tile, const cplx (&a)[NRE
 // Global <-> register layout = IO_GROUP stage: lanes run over tile positions 0..4, i.e. over
 // >= 128 contiguous bytes (tile positions 0..2 are always physical qubits 0..2).  The addressing is
 // recomputed for the write-back (opaque re-read of %tid / %ctaid) so that it does not occupy
-// registers while the gates run.
-struct IoAddr { cplx* p0; uint64_t hs[REG_BITS]; };
+// registers while the gates run.  The two-group persistent form runs 2 x NTHREADS threads per CTA: the thread's
+// index inside its group is %tid.x & (NTHREADS - 1) in every form.
+struct IoAddr { uint64_t i0; uint64_t hs[REG_BITS]; };
+__device__ __forceinline__ int group_tid() {
+    unsigned tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    return (int)(tid & (NTHREADS - 1));
+}
 // Every amplitude is touched exactly once per pass: stream it past L1 so that the phase tables stay there.
 __device__ __forceinline__ cplx ld_stream(const cplx* p) {
     const double2 v = __ldcs(reinterpret_cast<const double2*>(p));
@@ -52,40 +58,48 @@ __device__ __forceinline__ cplx ld_stream(const cplx* p) {
 __device__ __forceinline__ void st_stream(cplx* p, cplx v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
 // `cbase` = cta_base_runs(tile index): the tile's physical base, computed once per tile by the caller.
 template <int G>
-__device__ __forceinline__ IoAddr io_addr(cplx* amp, const PassDesc& pd, uint64_t cbase) {
-    unsigned tid;
-    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+__device__ __forceinline__ IoAddr io_addr(const PassDesc& pd, uint64_t cbase) {
     IoAddr io;
-    io.p0 = amp + cbase + tid_offset(pd, G, (int)tid);
+    io.i0 = cbase + tid_offset(pd, G, group_tid());
 #pragma unroll
     for (int k = 0; k < REG_BITS; ++k) io.hs[k] = 1ull << pd.tile_q[G * REG_BITS + k];
     return io;
 }
+__device__ __forceinline__ uint64_t io_reg_offset(const IoAddr& io, int j) {
+    uint64_t off = 0;
+#pragma unroll
+    for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += io.hs[k];
+    return off;
+}
 template <int G>
 __device__ __forceinline__ void tile_store(cplx* amp, const PassDesc& pd, const cplx (&a)[NREG], uint64_t cbase) {
-    const IoAddr io = io_addr<G>(amp, pd, cbase);
+    const IoAddr io = io_addr<G>(pd, cbase);
+    cplx* p0 = amp + io.i0;
 #pragma unroll
-    for (int j = 0; j < NREG; ++j) {
-        uint64_t off = 0;
-#pragma unroll
-        for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += io.hs[k];
-        st_stream(io.p0 + off, a[j]);
-    }
+    for (int j = 0; j < NREG; ++j) st_stream(p0 + io_reg_offset(io, j), a[j]);
 }
 // Load the tile in the group-G layout.  Support tracking (PassDesc::zero_mask): amplitudes with a bit of zero_mask set
 // are zero by construction and their memory is never read (after a reset it has not even been written).
+// With a fused remap (PassDesc::remap_n > 0) every amplitude comes from the buffer -- this rank's input or a partner
+// rank's, over NVLink -- that held it before the global<->local qubit swap(s); zero_mask then applies to the source index.
 template <int G>
-__device__ __forceinline__ void tile_load(cplx* amp, const PassDesc& pd, cplx (&a)[NREG], uint64_t cbase, int tid) {
-    const IoAddr io = io_addr<G>(amp, pd, cbase);
+__device__ __forceinline__ void tile_load(const cplx* amp, const PassDesc& pd, cplx (&a)[NREG], uint64_t cbase, int tid) {
+    const IoAddr io = io_addr<G>(pd, cbase);
     const uint64_t zmask = pd.zero_mask;
-    const bool thread_zero = (tid_offset(pd, G, tid) & zmask) != 0;
-    const int zregs = pd.zero_regbits;
+    if (pd.remap_n == 0) {
+        const cplx* p0 = amp + io.i0;
+        const bool thread_zero = (tid_offset(pd, G, tid) & zmask) != 0;
+        const int zregs = pd.zero_regbits;
 #pragma unroll
-    for (int j = 0; j < NREG; ++j) {
-        uint64_t off = 0;
+        for (int j = 0; j < NREG; ++j)
+            a[j] = (thread_zero || (j & zregs)) ? cplx{0.0, 0.0} : ld_stream(p0 + io_reg_offset(io, j));
+    } else {
 #pragma unroll
-        for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += io.hs[k];
-        a[j] = (thread_zero || (j & zregs)) ? cplx{0.0, 0.0} : ld_stream(io.p0 + off);
+        for (int j = 0; j < NREG; ++j) {
+            const uint64_t i = io.i0 + io_reg_offset(io, j);
+            const uint64_t src = remap_index(pd, i);
+            a[j] = (src & zmask) ? cplx{0.0, 0.0} : ld_stream(pd.remap_src[remap_sel(pd, i)] + src);
+        }
     }
 }
 
@@ -97,18 +111,26 @@ __device__ __forceinline__ void cp_async16(cplx* smem_dst, const cplx* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // Every thread fetches exactly the 16 amplitudes it will hold in the group-G layout, into the slots
-// stage_load<G> reads them back from: the staging needs no barrier of its own.
+// stage_load<G> reads them back from (dense states only: no zero_mask handling).  Fused remaps are honoured.
 template <int G>
-__device__ __forceinline__ void tile_prefetch(cplx* tile, cplx* amp, const PassDesc& pd, uint64_t cbase, int tid) {
-    const IoAddr io = io_addr<G>(amp, pd, cbase);
+__device__ __forceinline__ void tile_prefetch_issue(cplx* tile, const cplx* amp, const PassDesc& pd, uint64_t cbase, int tid) {
+    const IoAddr io = io_addr<G>(pd, cbase);
     cplx* sp = tile + smem_slot(stage_idx(G, tid, 0));
+    if (pd.remap_n == 0) {
+        const cplx* p0 = amp + io.i0;
 #pragma unroll
-    for (int j = 0; j < NREG; ++j) {
-        uint64_t off = 0;
+        for (int j = 0; j < NREG; ++j) cp_async16(sp + smem_slot(j << (REG_BITS * G)), p0 + io_reg_offset(io, j));
+    } else {
 #pragma unroll
-        for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += io.hs[k];
-        cp_async16(sp + smem_slot(j << (REG_BITS * G)), io.p0 + off);
+        for (int j = 0; j < NREG; ++j) {
+            const uint64_t i = io.i0 + io_reg_offset(io, j);
+            cp_async16(sp + smem_slot(j << (REG_BITS * G)), pd.remap_src[remap_sel(pd, i)] + remap_index(pd, i));
+        }
     }
+}
+template <int G>
+__device__ __forceinline__ void tile_prefetch(cplx* tile, const cplx* amp, const PassDesc& pd, uint64_t cbase, int tid) {
+    tile_prefetch_issue<G>(tile, amp, pd, cbase, tid);
     cp_async_commit();
 }
 
@@ -116,6 +138,68 @@ template <int FROM>
 __device__ __forceinline__ void switch_store(cplx* tile, const cplx (&a)[NREG], int tid, const DevOp& op, unsigned flags, uint64_t gbase) {
     if (flags & F_PERM) stage_store_perm<FROM>(tile, a, tid, op, gbase);
     else stage_store<FROM>(tile, a, tid);
+}
+
+// =================================================================================================
+// Two-group persistent form ("ring"): ONE CTA of 2 x NTHREADS threads per SM, three shared-memory tile buffers.
+// The CTA's tiles are numbered as slots s = 0, 1, 2, ...; slot s is computed by thread group s % 2 in buffer s % 3.
+// A buffer only serves the transposes of its slot: as soon as the slot's last transpose has been read back the
+// buffer is free, and the same threads fetch slot s + 3 into it with cp.async -- a full tile period before that
+// slot is needed (by the OTHER group).  Completion travels through one mbarrier per buffer
+// (cp.async.mbarrier.arrive.noinc), so no thread ever waits on a global load it issued itself, and the two
+// groups run half a period apart: HBM reads of slot s + 3, fp64 work of slot s and shared-memory transposes of
+// slot s + 1 overlap inside one SM.  The groups synchronise internally with named barriers (bar.sync id, 256).
+// =================================================================================================
+
+__device__ __forceinline__ void group_sync(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(NTHREADS) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+// the executing thread's earlier cp.async copies arrive on `bar` when they have landed (counted in the init count)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+struct Ring {
+    cplx* tiles;        // RING_BUFFERS x TILE_SLOTS
+    cplx* wc;           // [RING_GROUPS][2][MAX_TABLE_OPS]
+    uint64_t* full;     // RING_BUFFERS mbarriers
+    __device__ __forceinline__ cplx* tile(unsigned slot) const { return tiles + (slot % RING_BUFFERS) * TILE_SLOTS; }
+    __device__ __forceinline__ cplx* wcs(int g, unsigned k) const { return wc + (g * 2 + (k & 1)) * MAX_TABLE_OPS; }
+};
+__device__ __forceinline__ Ring ring_setup(unsigned char* smem_raw) {
+    Ring r;
+    r.tiles = reinterpret_cast<cplx*>(smem_raw);
+    r.wc = r.tiles + RING_BUFFERS * TILE_SLOTS;
+    r.full = reinterpret_cast<uint64_t*>(r.wc + RING_GROUPS * 2 * MAX_TABLE_OPS);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int b = 0; b < RING_BUFFERS; ++b) mbar_init(r.full + b, NTHREADS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    return r;
+}
+// Fetch slot `slot` (tile index t) into its buffer; all NTHREADS threads of one group call this.
+__device__ __forceinline__ void ring_fetch(const Ring& r, unsigned slot, const cplx* amp, const PassDesc& pd, uint64_t t, int tid) {
+    tile_prefetch_issue<IO_GROUP>(r.tile(slot), amp, pd, cta_base_runs(pd, t), tid);
+    cp_async_arrive(r.full + slot % RING_BUFFERS);
+}
+// Wait until slot `slot` has landed in its buffer (its use number slot / RING_BUFFERS gives the phase parity).
+__device__ __forceinline__ void ring_wait(const Ring& r, unsigned slot) {
+    mbar_wait(r.full + slot % RING_BUFFERS, (slot / RING_BUFFERS) & 1u);
 }
 
 }  // namespace dvd

@@ -142,6 +142,11 @@ int dvd_set_jit(dvd_state* s, int mode);
 int dvd_jit_wait(dvd_state* s);
 int dvd_jit_info(dvd_state* s, int64_t* compiled, int64_t* failed, int64_t* pending, double* compile_seconds,
                  char* last_error, int64_t cap);
+/* Kernel forms of the specialised kernels (csrc/jit.h: 0 = one tile per CTA at 2 CTAs/SM, 1 = the same at 3 CTAs/SM,
+ * 2 = two-group persistent "ring" form).  The form is chosen per pass structure by timing the candidates on the first
+ * dense launches.  out[0] = structures still being measured, out[1..3] = structures per chosen form,
+ * out[4..6] = launches per form since the library was loaded. */
+int dvd_jit_forms(int64_t out[7]);
 
 /* ---- planner inspection (host only, no GPU needed) ----------------------------------------- */
 /* Runs the pass planner on a gate list for a state of n_total qubits with n_local local qubits
@@ -153,7 +158,7 @@ int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t 
 /* CUDA source of the structure-specialised kernel the engine would compile for pass `pass_index` of the same plan
  * (NUL-terminated text).  Returns its length, 0 if there is no such pass, -(needed) if cap is too small. */
 int64_t dvd_jit_debug_source(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates, int pass_index,
-                             int persistent /* 1: the experimental cp.async-prefetch form */, char* out, int64_t cap);
+                             int form /* csrc/jit.h JitForm: 0, 1 or 2 */, char* out, int64_t cap);
 /* NVRTC-compiles such a source for sm_100a (no GPU needed): cubin size, or -1 with the log in dvd_last_error(). */
 int64_t dvd_jit_debug_compile(const char* source);
 /* Runs the distributed planner: perm_io[logical] = physical (in/out).  Output:

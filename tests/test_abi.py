@@ -143,9 +143,12 @@ def test_jit_generator_and_nvrtc_compile():
     size = L.dvd_jit_debug_compile(srcs[0])
     assert size > 10000, L.dvd_last_error()
     assert L.dvd_jit_debug_compile(b"this is not CUDA") == -1 and b"error" in L.dvd_last_error()
-    # the experimental persistent (cp.async prefetch) form of the same pass compiles too and differs from the plain one
+    # the other two kernel forms of the same pass (3 CTAs per SM; two-group persistent ring) compile too
     k = L.dvd_jit_debug_source(14, 14, arr, ng, 0, 1, buf, 1 << 20)
-    assert k > 0 and buf.value != srcs[0] and b"tile_prefetch<IO_GROUP>" in buf.value and b"cp_async_wait_all" in buf.value
+    assert k > 0 and buf.value != srcs[0] and b"__launch_bounds__(NTHREADS, 3)" in buf.value
+    assert L.dvd_jit_debug_compile(buf.value) > 10000, L.dvd_last_error()
+    k = L.dvd_jit_debug_source(14, 14, arr, ng, 0, 2, buf, 1 << 20)
+    assert k > 0 and buf.value != srcs[0] and b"ring_fetch(ring, slot + 3" in buf.value and b"group_sync(grp)" in buf.value
     assert L.dvd_jit_debug_compile(buf.value) > 10000, L.dvd_last_error()
 
 

@@ -48,7 +48,7 @@ class StubCircuit:
     def set_unfused(self, f): self._alive()
     def set_jit(self, m): self._alive(); self.jit = m
     def jit_wait(self): self._alive()
-    def jit_info(self): self._alive(); return dict(compiled=3, failed=0, pending=0, compile_seconds=1.0, message="")
+    def jit_info(self): self._alive(); return dict(compiled=3, failed=0, pending=0, compile_seconds=1.0, message="", tuning=0, chosen={}, launches={})
     def synchronize(self): self._alive()
     def stats_reset(self): self._alive(); self._st = {k: type(v)(0) for k, v in self._st.items()}
 

@@ -279,13 +279,14 @@ def env(monkeypatch):
     return set_
 
 
-@pytest.mark.parametrize("kind,n,persist,lazy", [
+@pytest.mark.parametrize("kind,n,ring,lazy", [
     ("random", 21, 1, 1), ("random", 21, 1, 0), ("random", 21, 0, 1), ("random", 21, 0, 0),
-    ("qft", 21, 1, 1), ("qft", 21, 0, 1), ("hea", 21, 1, 1), ("layered", 21, 1, 0)])
-def test_kernel_forms_agree_with_oracle(env, kind, n, persist, lazy):
-    """Persistent (cp.async prefetch) and one-tile-per-CTA forms of the pass, with and without the lazy
-    |0..0> input, against the oracle (2^21 amplitudes so that the persistent form really loops)."""
-    env(DVD_PERSIST=persist, DVD_LAZY_ZERO=lazy)
+    ("qft", 21, 1, 1), ("qft", 21, 0, 1), ("hea", 21, 1, 1), ("layered", 21, 1, 0), ("qft", 13, 1, 0), ("random", 12, 1, 0)])
+def test_kernel_forms_agree_with_oracle(env, kind, n, ring, lazy):
+    """Two-group persistent ("ring", cp.async prefetch through three shared-memory buffers) and one-tile-per-CTA forms
+    of the interpreter pass kernel, with and without the lazy |0..0> input, against the oracle (2^21 amplitudes = 512
+    tiles so that every ring really turns; 13 and 12 qubits = fewer tiles than ring slots)."""
+    env(DVD_RING=ring, DVD_RING_MIN_TILES=1, DVD_LAZY_ZERO=lazy)
     build = {"random": lambda c: circuits.random_circuit(c, n, 120, 21),
              "qft": lambda c: circuits.qft_like(c, n),
              "hea": lambda c: circuits.hea(c, n, 2),
@@ -382,6 +383,66 @@ def test_support_tracking_partial_circuits(n):
         assert g.sample(64, uniforms=u) == o.sample(64, uniforms=u, mode="tree")
 
 
+def _require_jit(info):
+    """Run-time compilation must work wherever the CUDA toolkit ships NVRTC: a silent skip would let the specialised
+    kernels rot.  Only a machine with no libnvrtc at all skips."""
+    if not info["message"]:
+        return
+    import glob
+    have = glob.glob("/usr/local/cuda*/lib64/libnvrtc.so*") + glob.glob("/usr/local/cuda*/targets/*/lib/libnvrtc.so*")
+    try:
+        import nvidia.cuda_nvrtc as m   # the pip wheel torch depends on
+        import os
+        have += glob.glob(os.path.join(os.path.dirname(m.__file__), "lib", "libnvrtc.so*"))
+    except Exception:
+        pass
+    if have:
+        pytest.fail(f"NVRTC is installed ({have[0]}) but the engine cannot use it: {info['message']}")
+    pytest.skip("run-time compilation unavailable (no libnvrtc on this machine): " + info["message"])
+
+
+@pytest.mark.parametrize("form", ["classic2", "classic3", "ring"])
+@pytest.mark.parametrize("kind,n", [("qft", 20), ("hea", 21), ("random", 21), ("qft", 13)])
+def test_jit_kernel_forms_agree_with_oracle(env, kind, n, form):
+    """Every kernel form the run-time generator can emit (one tile per CTA at 2 or 3 CTAs per SM, two-group persistent
+    ring), forced one at a time, against the oracle -- from a reset (support-tracked passes run the classic form) and
+    on the dense state a second forward starts from (the ring form proper)."""
+    env(DVD_JIT_MIN_QUBITS=12, DVD_JIT_FORM=form, DVD_RING_MIN_TILES=1)
+    build = {"qft": lambda c: circuits.qft_like(c, n), "hea": lambda c: circuits.hea(c, n, 2),
+             "random": lambda c: circuits.random_circuit(c, n, 100, 77)}[kind]
+    rec = Recorder(); build(rec)
+    j = rec.replay(gpu_circuit(n)); o = rec.replay(OracleCircuit(n))
+    j.set_jit(2)
+    _require_jit(j.jit_info())
+    before = j.jit_info()["launches"]
+    j.forward(); o.forward()
+    assert rel_err(j.state_numpy(), o.amplitudes()) < TOL
+    j.forward(); o.forward()      # dense input
+    assert rel_err(j.state_numpy(), o.amplitudes()) < TOL
+    st, info = j.stats(), j.jit_info()
+    assert st["jit_launches"] == st["tile_passes"] > 0, info
+    assert info["failed"] == 0, info
+    if form != "classic3":        # (a classic3 kernel that spills too much is dropped in favour of classic2)
+        assert info["launches"][form] > before[form], info
+
+
+def test_jit_form_is_chosen_by_measurement(env):
+    """Without DVD_JIT_FORM the engine times its candidates on the first dense launches of a structure and keeps the
+    fastest; results stay within tolerance of the oracle whichever form each launch used."""
+    env(DVD_JIT_MIN_QUBITS=12, DVD_RING_MIN_TILES=1)
+    n = 22
+    rec = Recorder(); circuits.hea(rec, n, 3)
+    j = rec.replay(gpu_circuit(n)); o = rec.replay(OracleCircuit(n))
+    j.set_jit(2)
+    _require_jit(j.jit_info())
+    for _ in range(8):
+        j.forward(); o.forward()
+        j.synchronize()
+    assert rel_err(j.state_numpy(), o.amplitudes()) < TOL
+    info = j.jit_info()
+    assert info["failed"] == 0 and info["tuning"] == 0 and sum(info["chosen"].values()) > 0, info
+
+
 @pytest.mark.parametrize("kind,n", [("qft", 20), ("hea", 20), ("random", 21), ("partial", 20)])
 def test_jit_specialised_kernels_agree_with_oracle(env, kind, n):
     """Structure-specialised pass kernels (NVRTC, compiled on first use here) against the oracle, and bit for bit
@@ -401,8 +462,7 @@ def test_jit_specialised_kernels_agree_with_oracle(env, kind, n):
     j = rec.replay(gpu_circuit(n)); i = rec.replay(gpu_circuit(n)); o = rec.replay(OracleCircuit(n))
     j.set_jit(2)
     info0 = j.jit_info()
-    if info0["message"]:      # libnvrtc.so.12 / libcuda.so.1 not loadable here: the engine keeps its built-in kernels
-        pytest.skip("run-time compilation unavailable: " + info0["message"])
+    _require_jit(info0)
     j.forward(); i.forward(); o.forward()
     st = j.stats()
     assert st["jit_launches"] == st["tile_passes"] > 0, j.jit_info()
