@@ -37,6 +37,10 @@ class Stats(ctypes.Structure):
         ("gate_algorithmic_bytes", ctypes.c_double),
         ("plan_cache_hits", ctypes.c_int64),
         ("jit_launches", ctypes.c_int64),
+        ("remap_passes", ctypes.c_int64),
+        ("remap_bytes_in", ctypes.c_double),
+        ("remap_ms", ctypes.c_double),
+        ("swap_ms", ctypes.c_double),
     ]
 
     def as_dict(self):

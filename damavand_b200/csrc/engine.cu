@@ -10,6 +10,7 @@
 #include <climits>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -67,10 +68,22 @@ struct dvd_state {
     ncclComm_t comm = nullptr;
     cplx* swap_buf[4] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t swap_chunk = 0;
-    // direct peer path: partner states (rank ^ 2^j) mapped with CUDA IPC; d_bar backs the stream barriers
+    // direct peer path: every other rank's state allocation mapped with CUDA IPC; d_bar backs the stream barriers
     bool peer_swap = false;
-    cplx* peer_amp[16] = {nullptr};
+    std::vector<cplx*> peer_base;   // [world]: base of rank r's allocation (nullptr for this rank / not mapped)
     double* d_bar = nullptr;
+    // Fused remap (world > 1): the allocation holds TWO chunks; a global<->local qubit swap is executed by the LOAD of
+    // the next tile pass, which reads buffer `cur` of this rank and of its partners (NVLink peer memory) and writes
+    // buffer 1 - cur of this rank.  Every rank flips `cur` at the same points of the same plan.
+    cplx* buf[2] = {nullptr, nullptr};
+    int cur = 0;
+    bool fused_remap = false;
+    struct RemapTimer { cudaEvent_t t0 = nullptr, t1 = nullptr; bool is_swap = false; };
+    std::vector<RemapTimer> remap_timers;   // events around the fused passes since the last dvd_stats_reset
+    size_t remap_timers_used = 0;
+    std::unique_ptr<Pass> ident_pass;       // empty pass for swaps with no gate pass to ride on
+    cplx* d_ident_tab = nullptr;
+    cplx* peer_cur(int r) const { return peer_base[r] + (size_t)cur * n_amps; }
     dvd_stats stats;
     bool unfused = false;
     // Support tracking: after a reset only amplitude 0 is stored; `support` holds the local qubits that a
@@ -130,6 +143,19 @@ static int materialize(dvd_state* s) {
     return DVD_OK;
 }
 
+// An event pair from the pool (dvd_get_stats turns the pairs into remap_ms / swap_ms).
+static int timer_acquire(dvd_state* s, bool is_swap, dvd_state::RemapTimer** out) {
+    if (s->remap_timers_used == s->remap_timers.size()) {
+        if (s->remap_timers.size() >= 4096) { *out = nullptr; return DVD_OK; }   // nobody reset the stats: stop timing
+        dvd_state::RemapTimer t;
+        CU(cudaEventCreate(&t.t0)); CU(cudaEventCreate(&t.t1));
+        s->remap_timers.push_back(t);
+    }
+    *out = &s->remap_timers[s->remap_timers_used++];
+    (*out)->is_swap = is_swap;
+    return DVD_OK;
+}
+
 // Stream-ordered barrier over all ranks: a one-element allreduce completes on a rank only after every
 // rank's stream has reached it, i.e. after all earlier kernels on every rank's stream have finished.
 static int stream_barrier(dvd_state* s) {
@@ -144,7 +170,6 @@ static int stream_barrier(dvd_state* s) {
 static int map_peers(dvd_state* s) {
     CU(cudaMalloc(&s->d_bar, 4 * sizeof(double)));
     CU(cudaMemsetAsync(s->d_bar, 0, 4 * sizeof(double), s->stream));
-    int g = 0; while ((1 << g) < s->world) ++g;
     const char* mode = getenv("DVD_SWAP");
     double ok = (mode && std::string(mode) == "nccl") ? 0.0 : 1.0;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -152,19 +177,21 @@ static int map_peers(dvd_state* s) {
     unsigned char* d_h = nullptr;
     CU(cudaMalloc(&d_h, (size_t)s->world * 64));
     cudaIpcMemHandle_t mine;
-    if (cudaIpcGetMemHandle(&mine, s->amp) != cudaSuccess) { cudaGetLastError(); ok = 0.0; std::memset(&mine, 0, sizeof mine); }
+    if (cudaIpcGetMemHandle(&mine, s->buf[0]) != cudaSuccess) { cudaGetLastError(); ok = 0.0; std::memset(&mine, 0, sizeof mine); }
     CU(cudaMemcpyAsync(d_h + (size_t)s->rank * 64, &mine, 64, cudaMemcpyHostToDevice, s->stream));
     NC(g_nccl.AllGather(d_h + (size_t)s->rank * 64, d_h, 64, ncclChar, s->comm, s->stream));
     CU(cudaMemcpyAsync(handles.data(), d_h, (size_t)s->world * 64, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaFree(d_h));
+    s->peer_base.assign(s->world, nullptr);
     if (ok != 0.0) {
-        for (int j = 0; j < g; ++j) {
+        for (int r = 0; r < s->world; ++r) {
+            if (r == s->rank) continue;
             void* p = nullptr;
-            if (cudaIpcOpenMemHandle(&p, handles[s->rank ^ (1 << j)], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            if (cudaIpcOpenMemHandle(&p, handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 cudaGetLastError(); ok = 0.0; break;
             }
-            s->peer_amp[j] = static_cast<cplx*>(p);
+            s->peer_base[r] = static_cast<cplx*>(p);
         }
     }
     double agreed = 0.0;
@@ -174,7 +201,10 @@ static int map_peers(dvd_state* s) {
     CU(cudaStreamSynchronize(s->stream));
     s->peer_swap = agreed != 0.0;
     if (!s->peer_swap)
-        for (auto& p : s->peer_amp) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+        for (auto& p : s->peer_base) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+    // both chunks in place and every partner mapped: global<->local swaps ride on the next pass's load
+    const char* fr = getenv("DVD_FUSED_REMAP");
+    s->fused_remap = s->peer_swap && s->buf[1] != nullptr && !(fr && atoi(fr) == 0);
     return DVD_OK;
 }
 
@@ -223,8 +253,17 @@ static int create_common(int n_qubits, int device, int rank, int world, const vo
         if (cudaEventCreateWithFlags(&s->ev_pack[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&s->ev_comm[i], cudaEventDisableTiming) != cudaSuccess)
             return cleanup(fail(DVD_ERR_CUDA, "event creation failed"));
-    cudaError_t e = cudaMalloc(&s->amp, s->n_amps * sizeof(cplx));
+    // distributed states get room for two chunks when the device has it (fused remap, see dvd_state::buf): the second
+    // chunk costs no more than the reference's own partner buffer (rust_communication.cu:178-197)
+    cudaError_t e = cudaErrorMemoryAllocation;
+    const char* fr = getenv("DVD_FUSED_REMAP");
+    if (world > 1 && !(fr && atoi(fr) == 0) && 2 * s->n_amps * sizeof(cplx) + (1ull << 30) < free_b) {
+        e = cudaMalloc(&s->buf[0], 2 * s->n_amps * sizeof(cplx));
+        if (e == cudaSuccess) s->buf[1] = s->buf[0] + s->n_amps; else cudaGetLastError();
+    }
+    if (e != cudaSuccess) e = cudaMalloc(&s->buf[0], s->n_amps * sizeof(cplx));
     if (e != cudaSuccess) return cleanup(fail(DVD_ERR_CUDA, std::string("cudaMalloc(state): ") + cudaGetErrorString(e)));
+    s->amp = s->buf[0];
     e = cudaMalloc(&s->d_tree, tree_size(s->n_local) * sizeof(double));
     if (e != cudaSuccess) return cleanup(fail(DVD_ERR_CUDA, std::string("cudaMalloc(tree): ") + cudaGetErrorString(e)));
     if (world > 1) {
@@ -289,8 +328,11 @@ int dvd_destroy(dvd_state* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
-    if (s->amp) cudaFree(s->amp);
+    for (auto& p : s->peer_base) if (p) cudaIpcCloseMemHandle(p);
+    if (s->buf[0]) cudaFree(s->buf[0]);
+    for (auto& t : s->remap_timers) { if (t.t0) cudaEventDestroy(t.t0); if (t.t1) cudaEventDestroy(t.t1); }
     if (s->d_tree) cudaFree(s->d_tree);
+    if (s->d_ident_tab) cudaFree(s->d_ident_tab);
     if (s->d_scratch) cudaFree(s->d_scratch);
     for (auto& t : s->tabs) {
         if (t.d) cudaFree(t.d);
@@ -298,7 +340,6 @@ int dvd_destroy(dvd_state* s) {
         if (t.done) cudaEventDestroy(t.done);
     }
     for (auto& b : s->swap_buf) if (b) cudaFree(b);
-    for (auto& p : s->peer_amp) if (p) cudaIpcCloseMemHandle(p);
     if (s->d_bar) cudaFree(s->d_bar);
     for (int i = 0; i < 2; ++i) {
         if (s->ev_pack[i]) cudaEventDestroy(s->ev_pack[i]);
@@ -380,8 +421,12 @@ static int global_swap(dvd_state* s, int gq, int lq) {
         // one kernel over NVLink peer memory: this rank moves the pairs of its half of the element range,
         // the partner the other half; barriers order it against the passes before and after on BOTH ranks
         const uint64_t half = s->n_amps / 2, share = half / 2;
+        dvd_state::RemapTimer* tm = nullptr;
+        TRY(timer_acquire(s, true, &tm));
         TRY(stream_barrier(s));
-        CU(launch_swap_peer(s->amp, s->peer_amp[j], lq, b, b ? share : 0, b ? half : share, s->stream));
+        if (tm) CU(cudaEventRecord(tm->t0, s->stream));
+        CU(launch_swap_peer(s->amp, s->peer_cur(s->rank ^ (1 << j)), lq, b, b ? share : 0, b ? half : share, s->stream));
+        if (tm) CU(cudaEventRecord(tm->t1, s->stream));
         TRY(stream_barrier(s));
         s->stats.kernel_launches++;
         s->stats.global_swaps++;
@@ -395,6 +440,9 @@ static int global_swap(dvd_state* s, int gq, int lq) {
     const uint64_t nchunks = (half + C - 1) / C;
     cplx** sendb = &s->swap_buf[0];
     cplx** recvb = &s->swap_buf[2];
+    dvd_state::RemapTimer* tm = nullptr;
+    TRY(timer_acquire(s, true, &tm));
+    if (tm) CU(cudaEventRecord(tm->t0, s->stream));
     for (uint64_t k = 0; k < nchunks; ++k) {
         const int slot = (int)(k & 1);
         const uint64_t first = k * C, cnt = std::min(C, half - first);
@@ -423,6 +471,7 @@ static int global_swap(dvd_state* s, int gq, int lq) {
         CU(launch_unpack_half(s->amp, lq, mybit, pf, pc, recvb[ps], s->stream));
         s->stats.kernel_launches++;
     }
+    if (tm) CU(cudaEventRecord(tm->t1, s->stream));
     s->stats.global_swaps++;
     s->stats.swap_bytes_sent += (int64_t)(half * sizeof(cplx));
     return DVD_OK;
@@ -515,43 +564,121 @@ static int flush_impl(dvd_state* s) {
     }
     cplx* const d_tabs = s->tabs[s->n_flushes & 1].d;
     size_t tat = 0;
+    // Global<->local swaps waiting to ride on the next pass's load (fused remap): disjoint (gq, lq) pairs.
+    std::vector<std::pair<int, int>> remap;
+    bool fused_any = false;
+    auto run_pass = [&](Pass& p, const cplx* d_tab) -> int {
+        PassParams& pp = s->pass_params;
+        pp.pd = p.desc;
+        pp.pd.rank_bits = s->rank_bits;
+        // support tracking: implied zeros are not read, all-zero tiles are not launched
+        const uint64_t zm = s->zero_mask();
+        pp.pd.zero_mask = zm;
+        uint64_t tile_mask = 0;
+        for (int k = 0; k < TILE_BITS; ++k) tile_mask |= 1ull << pp.pd.tile_q[k];
+        int zregs = 0;
+        for (int k = 0; k < REG_BITS; ++k)
+            if ((zm >> pp.pd.tile_q[IO_GROUP * REG_BITS + k]) & 1ull) zregs |= 1 << k;
+        pp.pd.zero_regbits = (int8_t)zregs;
+        cplx* out = s->amp;
+        uint64_t lmask = 0;
+        if (!remap.empty()) {
+            // the pass reads buffer `cur` of this rank and of its partners, writes buffer 1 - cur of this rank
+            pp.pd.remap_n = (int8_t)remap.size();
+            uint64_t rconst = 0;
+            for (size_t k = 0; k < remap.size(); ++k) {
+                const int j = remap[k].first - s->n_local, lq = remap[k].second;
+                pp.pd.remap_lq[k] = (int8_t)lq;
+                lmask |= 1ull << lq;
+                rconst |= (uint64_t)((s->rank >> j) & 1) << lq;
+            }
+            pp.pd.remap_lmask = lmask;
+            pp.pd.remap_const = rconst;
+            for (unsigned sel = 0; sel < (1u << remap.size()); ++sel) {
+                int r = s->rank;
+                for (size_t k = 0; k < remap.size(); ++k) {
+                    const int j = remap[k].first - s->n_local;
+                    r = (r & ~(1 << j)) | (int)((sel >> k) & 1u) << j;
+                }
+                pp.pd.remap_src[sel] = r == s->rank ? s->amp : s->peer_cur(r);
+            }
+            out = s->buf[1 - s->cur];
+            // every rank's buffer `cur` is complete (and nobody still reads the buffer this pass overwrites: the
+            // previous fused pass, which read it, lies before this barrier on every rank)
+            TRY(stream_barrier(s));
+        }
+        // tiles whose fixed bits make every source amplitude zero are not launched (bits of the swapped-in
+        // positions are rank-index bits of the source: never implied)
+        if (zm & ~tile_mask & ~lmask) fill_cta_runs_sparse(pp.pd, zm & ~tile_mask & ~lmask);   // on failure the full grid stays
+        pp.pd.tables = d_tab;
+        pp.pd.tid_off = reinterpret_cast<const uint64_t*>(d_tab + p.tid_off_slot);
+        std::memcpy(pp.ops, p.ops.data(), p.ops.size() * sizeof(DevOp));
+        dvd_state::RemapTimer* tm = nullptr;
+        if (!remap.empty()) {
+            TRY(timer_acquire(s, false, &tm));
+            if (tm) CU(cudaEventRecord(tm->t0, s->stream));
+        }
+        bool launched = false;
+        if (s->jit_mode != JIT_OFF && s->n_local >= s->jit_min_qubits) {
+            std::string jerr;
+            launched = jit_launch(p, s->jit_mode, s->device, out, pp, s->stream, &jerr);
+            if (launched) s->stats.jit_launches++;
+            else if (!jerr.empty()) s->jit_error = jerr;
+        }
+        if (!launched) CU(launch_tile_pass(out, pp, s->stream));
+        if (tm) CU(cudaEventRecord(tm->t1, s->stream));
+        s->stats.kernel_launches++; s->stats.tile_passes++;
+        s->stats.stage_switches += p.n_switches;
+        {   // HBM bytes this launch moves: its tiles are written in full, read where the input can be non-zero
+            const double tiles_bytes = (double)(1ull << pp.pd.n_cta_bits) * TILE_AMPS * sizeof(cplx);
+            s->stats.pass_bytes += tiles_bytes * (1.0 + 1.0 / (double)(1ull << __builtin_popcountll(zm & tile_mask & ~lmask)));
+        }
+        if (!remap.empty()) {
+            const double chunk = (double)s->n_amps * sizeof(cplx);
+            const double moved = chunk * (1.0 - 1.0 / (double)(1u << remap.size()));   // pulled over NVLink (and served to the partners)
+            s->stats.global_swaps += (int64_t)remap.size();
+            s->stats.swap_bytes_sent += (int64_t)moved;
+            s->stats.remap_passes++;
+            s->stats.remap_bytes_in += moved;
+            s->cur = 1 - s->cur;
+            s->amp = s->buf[s->cur];
+            s->support |= lmask;          // the swapped-in positions hold former rank-index qubits: never implied zero
+            remap.clear();
+            fused_any = true;
+        }
+        s->support |= p.touch_mask;
+        return DVD_OK;
+    };
+    // swaps with no pass to ride on (end of the gate list): an empty pass over the lowest tile, i.e. a plain
+    // out-of-place gather through the same load path
+    auto flush_remap = [&]() -> int {
+        if (remap.empty()) return DVD_OK;
+        if (!s->ident_pass) {
+            s->ident_pass.reset(new Pass(make_identity_pass(s->n_local)));
+            CU(cudaMalloc(&s->d_ident_tab, s->ident_pass->tables.size() * sizeof(cplx)));
+            CU(cudaMemcpyAsync(s->d_ident_tab, s->ident_pass->tables.data(), s->ident_pass->tables.size() * sizeof(cplx),
+                               cudaMemcpyHostToDevice, s->stream));
+            CU(cudaStreamSynchronize(s->stream));     // the host copy lives in the Pass, but keep the upload simple
+        }
+        return run_pass(*s->ident_pass, s->d_ident_tab);
+    };
     for (size_t i = 0; i < steps.size(); ++i) {
         DistStep& st = steps[i];
-        if (st.kind == DistStep::GLOBAL_SWAP) { TRY(materialize(s)); TRY(global_swap(s, st.gq, st.lq)); continue; }
+        if (st.kind == DistStep::GLOBAL_SWAP) {
+            if (tiled && s->fused_remap) {
+                bool disjoint = remap.size() < (size_t)MAX_REMAP;
+                for (auto& pr : remap) if (pr.first == st.gq || pr.second == st.lq) disjoint = false;
+                if (!disjoint) TRY(flush_remap());
+                remap.push_back({st.gq, st.lq});
+                continue;
+            }
+            TRY(materialize(s)); TRY(global_swap(s, st.gq, st.lq));
+            continue;
+        }
         if (tiled) {
             for (auto& p : plans[i]) {
-                PassParams& pp = s->pass_params;
-                pp.pd = p.desc;
-                pp.pd.rank_bits = s->rank_bits;
-                // support tracking: implied zeros are not read, all-zero tiles are not launched
-                const uint64_t zm = s->zero_mask();
-                pp.pd.zero_mask = zm;
-                uint64_t tile_mask = 0;
-                for (int k = 0; k < TILE_BITS; ++k) tile_mask |= 1ull << pp.pd.tile_q[k];
-                int zregs = 0;
-                for (int k = 0; k < REG_BITS; ++k)
-                    if ((zm >> pp.pd.tile_q[IO_GROUP * REG_BITS + k]) & 1ull) zregs |= 1 << k;
-                pp.pd.zero_regbits = (int8_t)zregs;
-                if (zm & ~tile_mask) fill_cta_runs_sparse(pp.pd, zm & ~tile_mask);   // on failure the full grid stays
-                pp.pd.tables = d_tabs + tat;
-                pp.pd.tid_off = reinterpret_cast<const uint64_t*>(d_tabs + tat + p.tid_off_slot);
-                std::memcpy(pp.ops, p.ops.data(), p.ops.size() * sizeof(DevOp));
-                bool launched = false;
-                if (s->jit_mode != JIT_OFF && s->n_local >= s->jit_min_qubits) {
-                    std::string jerr;
-                    launched = jit_launch(p, s->jit_mode, s->device, s->amp, pp, s->stream, &jerr);
-                    if (launched) s->stats.jit_launches++;
-                    else if (!jerr.empty()) s->jit_error = jerr;
-                }
-                if (!launched) CU(launch_tile_pass(s->amp, pp, s->stream));
+                TRY(run_pass(p, d_tabs + tat));
                 tat += p.tables.size();
-                s->stats.kernel_launches++; s->stats.tile_passes++;
-                s->stats.stage_switches += p.n_switches;
-                {   // HBM bytes this launch moves: its tiles are written in full, read where the input can be non-zero
-                    const double tiles_bytes = (double)(1ull << pp.pd.n_cta_bits) * TILE_AMPS * sizeof(cplx);
-                    s->stats.pass_bytes += tiles_bytes * (1.0 + 1.0 / (double)(1ull << __builtin_popcountll(zm & tile_mask)));
-                }
-                s->support |= p.touch_mask;
             }
         } else {
             TRY(materialize(s));
@@ -562,6 +689,10 @@ static int flush_impl(dvd_state* s) {
             }
         }
     }
+    TRY(flush_remap());
+    // every rank has finished reading this rank's buffers before anything after the flush (an observation, a load,
+    // the destruction of the state) touches them
+    if (fused_any) TRY(stream_barrier(s));
     if (tiled && total_tabs) {
         dvd_state::TabSet& ts = s->tabs[s->n_flushes & 1];
         CU(cudaEventRecord(ts.done, s->stream));
@@ -786,14 +917,27 @@ int dvd_num_local_qubits(const dvd_state* s) { return s ? s->n_local : -1; }
 int dvd_rank(const dvd_state* s) { return s ? s->rank : -1; }
 int dvd_world(const dvd_state* s) { return s ? s->world : -1; }
 
-int dvd_get_stats(const dvd_state* s, dvd_stats* out) {
-    if (!s || !out) return fail(DVD_ERR_ARG, "null argument");
+int dvd_get_stats(const dvd_state* cs, dvd_stats* out) {
+    if (!cs || !out) return fail(DVD_ERR_ARG, "null argument");
+    dvd_state* s = const_cast<dvd_state*>(cs);
+    // event pairs around the fused-remap passes / stand-alone exchanges recorded since the last reset
+    double ms_remap = 0.0, ms_swap = 0.0;
+    for (size_t i = 0; i < s->remap_timers_used; ++i) {
+        const dvd_state::RemapTimer& t = s->remap_timers[i];
+        float f = 0.f;
+        if (cudaEventSynchronize(t.t1) == cudaSuccess && cudaEventElapsedTime(&f, t.t0, t.t1) == cudaSuccess)
+            (t.is_swap ? ms_swap : ms_remap) += f;
+        else cudaGetLastError();
+    }
+    s->stats.remap_ms = ms_remap;
+    s->stats.swap_ms = ms_swap;
     *out = s->stats;
     return DVD_OK;
 }
 int dvd_stats_reset(dvd_state* s) {
     if (!s) return fail(DVD_ERR_ARG, "null state");
     std::memset(&s->stats, 0, sizeof s->stats);
+    s->remap_timers_used = 0;
     return DVD_OK;
 }
 int dvd_timer_begin(dvd_state* s) {

@@ -340,18 +340,19 @@ bool jit_launch(const Pass& p, int mode, int device, cplx* amp, const PassParams
         }
         sms = (unsigned)r.sm_count[device];
         std::shared_ptr<Tuner>& slot = r.tuners[pass_structure_key(p, FORM_CLASSIC2)];
-        if (!slot) {
-            slot = std::make_shared<Tuner>();
+        if (!slot) slot = std::make_shared<Tuner>();
+        {   // queue the forms this launch may want and that nobody asked for yet (classic2 always: it can run every launch)
             const int forced = forced_form();
+            bool queued = false;
             for (int f = 0; f < FORM_COUNT; ++f) {
-                if (forced >= 0 && f != forced && f != FORM_CLASSIC2) continue;   // classic2 always exists: it runs every launch
+                if (slot->e[f] || (forced >= 0 && f != forced && f != FORM_CLASSIC2)) continue;
                 slot->e[f] = std::make_shared<Entry>();
                 slot->e[f]->form = f;
                 r.queue.emplace_back(slot->e[f], generate_pass_source(p, "dvd_pass_static", f));
                 ++r.stats.pending;
+                queued = true;
             }
-            r.start_workers();
-            r.cv.notify_all();
+            if (queued) { r.start_workers(); r.cv.notify_all(); }
         }
         tuner = slot;
         Tuner& t = *tuner;
@@ -392,7 +393,8 @@ bool jit_launch(const Pass& p, int mode, int device, cplx* amp, const PassParams
         } else {
             harvest(d);
             const bool dense_full = ring_ok;
-            if (dense_full && d.best_dense < 0 && (d.sig < 0 || d.sig == pp.pd.n_cta_bits)) {
+            // (a pass whose load carries a fused remap pulls half its tile over NVLink: not a fair timing sample)
+            if (dense_full && pp.pd.remap_n == 0 && d.best_dense < 0 && (d.sig < 0 || d.sig == pp.pd.n_cta_bits)) {
                 // measuring: the usable candidate with the fewest timings (finished or in flight) runs next
                 int n_have[FORM_COUNT];
                 for (int f = 0; f < FORM_COUNT; ++f) n_have[f] = (int)d.ms[f].size();

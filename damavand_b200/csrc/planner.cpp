@@ -952,6 +952,17 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates_in, int n_local,
     return passes;
 }
 
+Pass make_identity_pass(int n_local) {
+    if (n_local < TILE_BITS) throw std::runtime_error("make_identity_pass: n_local < TILE_BITS");
+    Pass pass;
+    std::memset(&pass.desc, 0, sizeof(pass.desc));
+    pass.desc.n_local = n_local;
+    for (int p = 0; p < TILE_BITS; ++p) pass.desc.tile_q[p] = pass.desc.sorted_q[p] = p;
+    pass.desc.io_out = IO_GROUP;
+    pass.finish_tables();
+    return pass;
+}
+
 // ---------------------------------------------------------------------------------------------------
 std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n_total, int n_local,
                                        std::vector<int>& perm, bool restore_identity) {
@@ -1015,7 +1026,8 @@ std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n
             for (int gi : pending) {
                 const HostGate& g = gates[gi];
                 if (!g.diag && perm[g.target()] >= n_local && blk.can_pass(g) &&
-                    std::find(want.begin(), want.end(), g.target()) == want.end() && (int)want.size() < n_total - n_local)
+                    std::find(want.begin(), want.end(), g.target()) == want.end() &&
+                    (int)want.size() < std::min(n_total - n_local, n_local))   // one evictable local position per swap-in
                     want.push_back(g.target());
                 blk.skip(g);
             }
@@ -1033,6 +1045,7 @@ std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n
                     if (std::find(want.begin(), want.end(), lq) != want.end()) continue;
                     if (next_use[lq] > best) { best = next_use[lq]; victim = p; }
                 }
+            if (victim < 0) throw std::runtime_error("plan_distributed: no local position left to evict");
             emit_swap(perm[lqbit], victim);
             next_use[lqbit] = -1;    // just swapped in: not a victim for the rest of this round
         }

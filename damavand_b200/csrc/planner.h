@@ -77,6 +77,10 @@ std::vector<HostGate> fuse_diagonal_runs(const std::vector<HostGate>& gates);
 std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, int n_total,
                              const PlanOptions& opt);
 
+// A pass with no ops over the tile of the 12 lowest qubits: reads and writes every amplitude once.  The engine runs
+// it when a fused remap (tile_core.cuh: PassDesc::remap_*) has no gate pass to ride on.
+Pass make_identity_pass(int n_local);
+
 // ---- distributed level ---------------------------------------------------------------------------
 struct DistStep {
     enum Kind { LOCAL_GATES = 0, GLOBAL_SWAP = 1 } kind;

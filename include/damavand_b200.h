@@ -127,6 +127,11 @@ typedef struct {
     double gate_algorithmic_bytes;/* sum over gates of 32*2^n_local (16*2^n_local if controlled) */
     int64_t plan_cache_hits;      /* flushes that reused the previous plan (identical gate list) */
     int64_t jit_launches;         /* tile passes that ran as a structure-specialised (run-time compiled) kernel */
+    int64_t remap_passes;         /* tile passes whose load carried global<->local swaps (fused remap over NVLink peer memory) */
+    double remap_bytes_in;        /* bytes those passes pulled from partner ranks over NVLink, per rank (the same amount is
+                                     served to the partners in the other direction) */
+    double remap_ms;              /* device time of those passes (CUDA events on the state's stream) */
+    double swap_ms;               /* device time of the stand-alone exchanges (in-place peer swap / staged NCCL path) */
 } dvd_stats;
 int dvd_get_stats(const dvd_state* s, dvd_stats* out);
 int dvd_stats_reset(dvd_state* s);

@@ -8,6 +8,7 @@
 // Never loaded by the product.
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <cstdlib>
 #include <vector>
@@ -17,8 +18,39 @@
 
 using namespace dvd;
 
-static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits, uint64_t zero_mask = 0) {
+// Fused remap as the engine sets it up (engine.cu flush_impl / run_pass): `pairs` = (rank-index qubit, local qubit)
+// swaps executed by this pass's load; `snapshot` = every rank's chunk before the pass (the buffers the ranks read).
+struct RemapEmu {
+    std::vector<std::pair<int, int>> pairs;
+    const cplx* snapshot = nullptr;
+    int rank = 0;
+    uint64_t chunk = 0;
+};
+
+static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits, uint64_t zero_mask = 0, const RemapEmu* rm = nullptr) {
     PassDesc pd = pass.desc;
+    uint64_t lmask = 0;
+    if (rm && !rm->pairs.empty()) {
+        if (rm->pairs.size() > (size_t)MAX_REMAP) throw std::runtime_error("emu: too many fused swaps");
+        pd.remap_n = (int8_t)rm->pairs.size();
+        uint64_t rconst = 0;
+        for (size_t k = 0; k < rm->pairs.size(); ++k) {
+            const int j = rm->pairs[k].first - pd.n_local, lq = rm->pairs[k].second;
+            pd.remap_lq[k] = (int8_t)lq;
+            lmask |= 1ull << lq;
+            rconst |= (uint64_t)((rm->rank >> j) & 1) << lq;
+        }
+        pd.remap_lmask = lmask;
+        pd.remap_const = rconst;
+        for (unsigned sel = 0; sel < (1u << rm->pairs.size()); ++sel) {
+            int r = rm->rank;
+            for (size_t k = 0; k < rm->pairs.size(); ++k) {
+                const int j = rm->pairs[k].first - pd.n_local;
+                r = (r & ~(1 << j)) | (int)((sel >> k) & 1u) << j;
+            }
+            pd.remap_src[sel] = rm->snapshot + (uint64_t)r * rm->chunk;
+        }
+    }
     pd.rank_bits = rank_bits;
     pd.tables = pass.tables.data();
     pd.tid_off = reinterpret_cast<const uint64_t*>(pass.tables.data() + pass.tid_off_slot);
@@ -30,7 +62,8 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits, uint64_t z
     int zregs = 0;
     for (int k = 0; k < REG_BITS; ++k) if ((zero_mask >> pd.tile_q[IO_GROUP * REG_BITS + k]) & 1ull) zregs |= 1 << k;
     pd.zero_regbits = (int8_t)zregs;
-    const bool sparse = (zero_mask & ~tile_mask) != 0 && fill_cta_runs_sparse(pd, zero_mask & ~tile_mask);
+    const uint64_t skip = zero_mask & ~tile_mask & ~lmask;
+    const bool sparse = skip != 0 && fill_cta_runs_sparse(pd, skip);
     const uint64_t ctas = 1ull << pd.n_cta_bits;
     if (!sparse && pd.n_cta_bits != pd.n_local - TILE_BITS) throw std::runtime_error("emu: n_cta_bits of the full grid");
     std::vector<cplx> tile(TILE_SLOTS);
@@ -40,7 +73,7 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits, uint64_t z
         const uint64_t base = sparse ? cta_base_runs(pd, cta) : cta_base(pd, cta);
         if (cta_base_runs(pd, cta) != base) throw std::runtime_error("emu: run-compressed CTA base differs");
         if (base & tile_mask) throw std::runtime_error("emu: CTA base overlaps the tile");
-        if (base & zero_mask) { if (sparse) throw std::runtime_error("emu: sparse grid visits an all-zero tile"); continue; }
+        if (base & zero_mask & ~lmask) { if (sparse) throw std::runtime_error("emu: sparse grid visits an all-zero tile"); continue; }
         const uint64_t gbase = base | pd.rank_bits;
         if (pd.n_tab > MAX_TABLE_OPS || pd.n_ops >= MAX_OPS_PER_PASS || (size_t)pd.n_ops != pass.ops.size())
             throw std::runtime_error("emu: pass exceeds the kernel parameter limits");
@@ -48,8 +81,14 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits, uint64_t z
         for (int ti = 0; ti < pd.n_tab; ++ti) wcs[ti] = table_cta_const(pd.tables, ti, gbase);
         for (int tid = 0; tid < NTHREADS; ++tid) {
             const bool thread_zero = (tid_offset(pd, IO_GROUP, tid) & zero_mask) != 0;
-            for (int j = 0; j < NREG; ++j)
-                regs[tid][j] = (thread_zero || (j & pd.zero_regbits)) ? cplx{0.0, 0.0} : amp[base + tile_offset(pd, stage_idx(IO_GROUP, tid, j))];
+            for (int j = 0; j < NREG; ++j) {
+                const uint64_t i = base + tile_offset(pd, stage_idx(IO_GROUP, tid, j));
+                if (pd.remap_n == 0) regs[tid][j] = (thread_zero || (j & pd.zero_regbits)) ? cplx{0.0, 0.0} : amp[i];
+                else {      // tile_kernel.cuh tile_load, remap path
+                    const uint64_t src = remap_index(pd, i);
+                    regs[tid][j] = (src & zero_mask) ? cplx{0.0, 0.0} : pd.remap_src[remap_sel(pd, i)][src];
+                }
+            }
             ctx[tid].pidx = gbase | tile_offset(pd, stage_idx(IO_GROUP, tid, 0));
             for (int g = 0; g < NGROUPS; ++g)
                 if (cta == 0 && tid_offset(pd, g, tid) != tile_offset(pd, stage_idx(g, tid, 0))) throw std::runtime_error("emu: thread offset table differs");
@@ -136,6 +175,8 @@ const char* emu_error() { return g_err.c_str(); }
 // reset leaves it (amplitude 0 of every chunk stored, everything else arbitrary -- the tests fill it with NaN);
 // implied zeros are materialised at the end, before every global swap and before the one-gate path.
 static bool g_track_support = false;
+static bool g_fused = true;      // global<->local swaps ride on the next pass's load (engine default when memory allows)
+void emu_set_fused(int on) { g_fused = on != 0; }
 int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int fuse, double* state, int64_t* stats /*[4]*/);
 int emu_run_sparse(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int fuse, double* state, int64_t* stats) {
     g_track_support = true;
@@ -169,7 +210,37 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
             if (zm) for (uint64_t i = 0; i < chunk; ++i) if (i & zm) amp[(uint64_t)r * chunk + i] = cplx{0.0, 0.0};
             support[r] = ~0ull;
         };
+        // fused remap as in the engine: disjoint swaps wait for the next pass and ride on its load (out of place)
+        std::vector<std::pair<int, int>> remap;
+        std::vector<cplx> snapshot;
+        std::unique_ptr<Pass> ident;
+        auto fused_pass = [&](const Pass& p) {
+            snapshot.assign(amp, amp + ((uint64_t)world << n_local));
+            uint64_t lmask = 0;
+            for (auto& pr : remap) lmask |= 1ull << pr.second;
+            for (int r = 0; r < world; ++r) {
+                RemapEmu rm; rm.pairs = remap; rm.snapshot = snapshot.data(); rm.rank = r; rm.chunk = chunk;
+                run_pass(amp + (uint64_t)r * chunk, p, (uint64_t)r << n_local, ~support[r] & local_mask, &rm);
+                support[r] |= lmask | p.touch_mask;
+            }
+            remap.clear();
+        };
+        auto flush_remap = [&]() {
+            if (remap.empty()) return;
+            if (!ident) ident.reset(new Pass(make_identity_pass(n_local)));
+            ++n_pass;
+            fused_pass(*ident);
+        };
         for (auto& st : steps) {
+            if (st.kind == DistStep::GLOBAL_SWAP && g_fused && n_local >= TILE_BITS) {
+                ++n_swap;
+                if (st.gq < n_local || st.gq >= n_qubits || st.lq < 0 || st.lq >= n_local) throw std::runtime_error("emu: bad swap");
+                bool disjoint = remap.size() < (size_t)MAX_REMAP;
+                for (auto& pr : remap) if (pr.first == st.gq || pr.second == st.lq) disjoint = false;
+                if (!disjoint) flush_remap();
+                remap.push_back({st.gq, st.lq});
+                continue;
+            }
             if (st.kind == DistStep::GLOBAL_SWAP) {
                 ++n_swap;
                 const int j = st.gq - n_local;
@@ -190,10 +261,12 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
             if (n_local >= TILE_BITS) {
                 std::vector<Pass> passes = plan_local(st.gates, n_local, n_qubits, opt);
                 for (auto& p : passes) { ++n_pass; n_switch += p.n_switches; n_ops += (int64_t)p.ops.size(); }
+                size_t first = 0;
+                if (!remap.empty() && !passes.empty()) { fused_pass(passes[0]); first = 1; }
                 for (int r = 0; r < world; ++r)
-                    for (auto& p : passes) {
-                        run_pass(amp + (uint64_t)r * chunk, p, (uint64_t)r << n_local, ~support[r] & local_mask);
-                        support[r] |= p.touch_mask;
+                    for (size_t pi = first; pi < passes.size(); ++pi) {
+                        run_pass(amp + (uint64_t)r * chunk, passes[pi], (uint64_t)r << n_local, ~support[r] & local_mask);
+                        support[r] |= passes[pi].touch_mask;
                     }
             } else {
                 for (int r = 0; r < world; ++r) materialize(r);
@@ -202,6 +275,7 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
                 n_ops += (int64_t)st.gates.size();
             }
         }
+        flush_remap();
         for (int r = 0; r < world; ++r) materialize(r);
         if (stats) { stats[0] = n_pass; stats[1] = n_swap; stats[2] = n_switch; stats[3] = n_ops; }
         return 0;
