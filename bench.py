@@ -231,11 +231,21 @@ def reference_arm(args):
     n = workload_qubits(name)
     gates_per_step = args.cpu_gates_per_step or (2 if n >= 30 else 4 if n >= 28 else 50)
     gps, sec_step, desc, cores, n_cpu = run_cpu(name, args.steps, args.warmup, gates_per_step)
+    factor = 2.0 ** (n - n_cpu)           # sec_step is already scaled to the workload's size
+    measured_ms = sec_step * 1e3 / factor
+    cfg = {"workload": f"{name}: {workload_desc(name)}", "cpu_qubits": n_cpu, "gates_per_step": gates_per_step}
+    if n_cpu != n:
+        # the host cannot hold 2 x 16 * 2^n B: the step is MEASURED at n_cpu qubits; `value` is that rate scaled to the
+        # workload's size (cost per gate of clone + update is linear in the state size) -- an extrapolation, labelled so
+        cfg["extrapolated"] = {"measured_at_qubits": n_cpu, "workload_qubits": n, "factor": factor,
+                               "ms_per_step_at_workload_size": sec_step * 1e3,
+                               "note": "ms_per_step is the measured time of one step of the bounded sample at measured_at_qubits; "
+                                       "value = measured gates/s / factor"}
     line = {
         "impl": "reference", "metric": "gates_per_sec", "value": gps, "unit": "gates/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_step * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": measured_ms, "higher_is_better": True,
         "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{name}: {workload_desc(name)}", "cpu_qubits": n_cpu, "gates_per_step": gates_per_step},
+        "config": cfg,
         "cpu_baseline": {"value": gps, "unit": "gates/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": gps, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -247,65 +257,121 @@ def reference_arm(args):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None)
-    ap.add_argument("--cpu-gates-per-step", type=int, default=0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-scaling-point", action="store_true")
-    ap.add_argument("--no-single-gate", action="store_true")
-    ap.add_argument("--unfused", action="store_true", help="one kernel per gate (no fusion) for comparison")
-    ap.add_argument("--jit", type=int, default=None, help="structure-specialised kernels: 0 off, 1 on (compiled during warm-up)")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return reference_arm(args)
+class Ranks:
+    """The torch.distributed plumbing the harness needs (nothing on the data path): barrier and max over ranks."""
 
-    from damavand_b200 import Circuit, distributed
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks"}))
-            return 2
-    rank = int(os.environ.get("RANK", "0"))
-    name = args.workload or ("qft30" if args.gpus == 1 else "random32")
-    n = workload_qubits(name)
-    method = "gpu" if args.gpus == 1 else "distributed_gpu"
-    if args.gpus > 1:
-        import torch
-        import torch.distributed as dist
-        distributed.initialize("nccl")
+    def __init__(self, gpus: int):
+        self.gpus = gpus
+        self.rank = int(os.environ.get("RANK", "0"))
 
-    circ = Circuit(n, method)
-    if args.unfused:
-        circ.set_unfused(True)
-    n_gates = build_workload(circ, name)
-    n_obs_gates = len(circ.observables)
-    device = int(os.environ.get("LOCAL_RANK", "0"))
-
-    def barrier():
-        if args.gpus > 1:
+    def barrier(self, circ=None):
+        if self.gpus > 1:
             import torch
             import torch.distributed as dist
             dist.barrier()
             torch.cuda.synchronize()
-        circ.synchronize()
+        if circ is not None:
+            circ.synchronize()
+
+    def max(self, x: float) -> float:
+        if self.gpus == 1:
+            return x
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(self, ok: bool) -> bool:
+        return self.max(0.0 if ok else 1.0) == 0.0
+
+
+def parity_check(ranks: Ranks, jit: int, cases=None):
+    """The CUDA path against the CPU oracle (oracle/ is the CHECKER here, never the thing measured) on this run's own
+    ranks, before anything is timed: this rank's chunk of the amplitudes (max-relative and l2-relative error), the
+    allreduced norm and exact <Z_q>, and the sampler's indices bit for bit under injected uniforms (world > 1: against
+    the restatement of sample_distributed, circuit_distributed.rs:42-129).  Returns the `parity` object of the JSON line."""
+    from damavand_b200 import Circuit, circuits
+    from oracle import oracle
+    from oracle.oracle import OracleCircuit
+    world, rank = ranks.gpus, ranks.rank
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(max(1, cores // world))     # every rank runs the oracle itself
+    method = "gpu" if world == 1 else "distributed_gpu"
+    cases = cases or [(22, "random", 300), (22, "qft", 0), (23, "hea", 4)]
+    out = {"ok": True, "tolerance": 1e-12, "max_rel_err": 0.0, "l2_rel_err": 0.0, "ez_err": 0.0, "norm_err": 0.0,
+           "samples_ok": True, "shots": 5000, "cases": [], "jit": bool(jit),
+           "oracle": "oracle/ restatement of circuit_multithreading.rs:9-54 (checker only)"}
+    for n, kind, arg in cases:
+        g = Circuit(n, method)
+        if jit:
+            g.set_jit(2)       # compile on first use: the specialised kernels are what is checked
+        o = OracleCircuit(n)
+        for c in (g, o):
+            if kind == "random":
+                circuits.random_circuit(c, n, arg, seed=n)
+            elif kind == "qft":
+                circuits.qft_like(c, n)
+            else:
+                circuits.hea(c, n, arg)
+            for q in range(n):
+                c.add_pauli_z_gate(q, True)
+        o.forward()
+        full = o.amplitudes()
+        chunk = (1 << n) // world
+        want = full[rank * chunk:(rank + 1) * chunk]
+        p = o.measure_np()
+        idx = np.arange(p.size)
+        ez_want = np.array([(p * (1 - 2.0 * ((idx >> q) & 1))).sum() for q in range(n)])
+        shots = out["shots"]
+        u = np.random.default_rng(1235).random(2 * shots)
+        if world > 1:
+            s_want = oracle.sample_distributed(p, world, u[:shots], u[shots:], "tree")
+        else:
+            s_want = np.asarray(o.sample(shots, uniforms=u[:shots], mode="tree"), dtype=np.uint64)
+        errs = []
+        for rep in range(2):          # from a reset (support-tracked passes), then reset again (plan cache, warm kernels)
+            g.reset_amplitudes()
+            g.forward()
+            got = g.state_numpy()
+            errs.append((float(np.abs(got - want).max() / np.abs(full).max()),
+                         float(np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-300))))
+        err, l2 = max(e[0] for e in errs), max(e[1] for e in errs)
+        ez_err = float(np.abs(g.expectation_z() - ez_want).max())
+        norm_err = abs(g.norm() - 1.0)
+        s = g.sample_numpy(shots, u if world > 1 else u[:shots])
+        s_ok = bool((s == s_want).all())
+        st = g.stats()
+        ok = err < 1e-12 and l2 < 1e-12 and ez_err < 1e-12 and norm_err < 1e-12 and s_ok
+        ok = ranks.all_ok(ok)
+        err, l2, ez_err, norm_err = ranks.max(err), ranks.max(l2), ranks.max(ez_err), ranks.max(norm_err)
+        s_ok = ranks.all_ok(s_ok)
+        out["cases"].append({"n": n, "circuit": kind, "max_rel_err": err, "l2_rel_err": l2, "ez_err": ez_err, "norm_err": norm_err,
+                             "samples_ok": s_ok, "global_swaps": int(st["global_swaps"]), "fused_remap_passes": int(st.get("remap_passes", 0)),
+                             "passes": int(st["tile_passes"]), "jit_launches": int(st["jit_launches"]), "ok": ok})
+        out["ok"] = out["ok"] and ok
+        out["samples_ok"] = out["samples_ok"] and s_ok
+        for k, v in (("max_rel_err", err), ("l2_rel_err", l2), ("ez_err", ez_err), ("norm_err", norm_err)):
+            out[k] = max(out[k], v)
+        g.close()
+    out["n"] = sorted({c["n"] for c in out["cases"]})
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    return out
+
+
+def measure(circ, n_gates, args, ranks: Ranks, jit: int, device: int, sample_clocks: bool):
+    """Warm-up (incl. run-time compilation and kernel-form selection), then the two timed regions:
+    `from_reset` = --steps x (reset + forward), `dense` = --steps x forward on the dense state left behind."""
+    import datetime
 
     def one_step():
         circ.reset_amplitudes()
         circ.forward_async()
 
-    # run-time specialised pass kernels: on for the single-GPU workloads (validated on B200, profiles/r1_*_v11*);
-    # the multi-GPU runs keep the interpreter kernels unless --jit 1 is given
-    jit = args.jit if args.jit is not None else int(os.environ.get("DVD_BENCH_JIT", "1" if args.gpus == 1 else "0"))
     if jit:
         circ.set_jit(1)
     sampler = ClockSampler(device)     # started before the warm-up: nvidia-smi needs ~1 s before its first sample
-    if rank == 0:
+    if sample_clocks and ranks.rank == 0:
         sampler.start()
     for _ in range(args.warmup):
         one_step()
@@ -320,92 +386,207 @@ def main():
             one_step(); circ.forward_async(); circ.synchronize()
             if circ.jit_info()["tuning"] == 0:
                 break
-    barrier()
+    ranks.barrier(circ)
     circ.stats_reset()
-    barrier()
+    ranks.barrier(circ)
     t_wall0 = time.perf_counter()
     circ.timer_begin()
     for _ in range(args.steps):
         one_step()
     ms = circ.timer_end()
-    barrier()
+    ranks.barrier(circ)
     t_wall = time.perf_counter() - t_wall0
     st = circ.stats()
-    # read while the circuit is alive (the scaling-point leg below closes it)
     jit_cfg = dict(circ.jit_info(), launches_in_from_reset_region=int(st.get("jit_launches", 0))) if jit else False
-    if args.gpus > 1:
-        import torch
-        import torch.distributed as dist
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    sec = ms / 1e3
-    value = args.steps * n_gates / sec
+    ms = ranks.max(ms)
 
     # The same circuit applied to a DENSE state (the one the timed steps left behind, no reset): every pass reads and
-    # writes every amplitude, nothing is known to be zero.  This is the timing the roofline of the dominant kernel
-    # (k_tile_pass) is computed from, and it is reported next to `value` as `dense_state`.
+    # writes every amplitude, nothing is known to be zero.  This is the headline region and the timing the roofline of
+    # the dominant kernel is computed from.
     circ.synchronize()
     circ.forward_async(); circ.synchronize()          # the state of the last step is only partly dense for some circuits
     circ.stats_reset()
-    barrier()
-    dense_reps = max(1, args.steps)                    # the headline region: EXACTLY --steps forwards
-    import datetime
+    ranks.barrier(circ)
+    reps = max(1, args.steps)                          # EXACTLY --steps forwards
     t_region0 = datetime.datetime.now()
     t_wall0 = time.perf_counter()
     circ.timer_begin()
-    for _ in range(dense_reps):
+    for _ in range(reps):
         circ.forward_async()
-    fwd_ms = circ.timer_end() / dense_reps
-    barrier()
+    fwd_ms = circ.timer_end() / reps
+    ranks.barrier(circ)
     t_wall_dense = time.perf_counter() - t_wall0
-    clocks = sampler.stop(t_region0, datetime.datetime.now()) if rank == 0 else None
-    if args.gpus > 1:
-        import torch
-        import torch.distributed as dist
-        t = torch.tensor([fwd_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        fwd_ms = float(t.item())
-    st1 = {k: (v / dense_reps if isinstance(v, (int, float)) else v) for k, v in circ.stats().items()}
-    dense_state = {"value": n_gates / (fwd_ms / 1e3), "unit": "gates/s", "ms_per_step": fwd_ms,
-                   "what": "forward of the same circuit on a dense state (no reset, nothing known to be zero): every pass "
-                           "moves 32*2^n_local B"}
-    launches_fwd = st1["tile_passes"] + st1["simple_passes"]
+    clocks = sampler.stop(t_region0, datetime.datetime.now()) if (sample_clocks and ranks.rank == 0) else None
+    fwd_ms = ranks.max(fwd_ms)
+    st1 = {k: (v / reps if isinstance(v, (int, float)) else v) for k, v in circ.stats().items()}
+    if jit:
+        jit_cfg = dict(jit_cfg, launches_per_dense_forward=st1.get("jit_launches", 0), final=circ.jit_info())
+    return {"from_reset_ms": ms / args.steps, "from_reset_stats": st, "dense_ms": fwd_ms, "dense_stats": st1, "reps": reps,
+            "clocks": clocks, "jit": jit_cfg, "wall_dense": t_wall_dense, "wall_from_reset": t_wall,
+            "value": n_gates / (fwd_ms / 1e3), "from_reset_value": n_gates / (ms / args.steps / 1e3)}
+
+
+def roofline_of(m, name, n_local, n_gates, gpus):
+    """`roofline` object of the bench contract for the dominant kernel (the fused pass), from the dense region."""
+    st1, fwd_ms = m["dense_stats"], m["dense_ms"]
+    launches = st1["tile_passes"] + st1["simple_passes"]
+    if launches <= 0:
+        return None
     peak, peak_src, _ = measured_peaks()
-    # algorithmic bytes per launch of the pass kernel: read + write of every local amplitude once
+    fwd_s = fwd_ms / 1e3
+    hbm_gbs = st1["pass_bytes"] / fwd_s / 1e9
+    alg_gbs = st1["gate_algorithmic_bytes"] / fwd_s / 1e9
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(f"{name}_g{gpus}", {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    jitted = st1.get("jit_launches", 0) >= st1["tile_passes"] > 0
+    kernel = ("dvd_pass_static (k_tile_pass specialised at run time for the pass's op structure, csrc/jit.cpp)" if jitted
+              else "k_tile_pass (interpreter form)" if st1["tile_passes"] else "k_simple_gate")
+    r = {"bound": "hbm", "kernel": kernel,
+         # bytes one launch of the pass kernel really moves through HBM: it reads and writes every local amplitude
+         # once, 32 * 2^n_local B, however many gates it applies (ncu: dram read + write per launch = `traffic`)
+         "achieved": hbm_gbs, "peak": peak, "unit": "GB/s", "frac": hbm_gbs / peak, "traffic": traffic, "peak_source": peak_src,
+         "launches_per_circuit": launches, "avg_launch_ms": fwd_ms / launches,
+         "hbm_bytes_per_launch": st1["pass_bytes"] / launches,
+         "hbm_pass_gbs": hbm_gbs, "hbm_pass_frac": hbm_gbs / peak,
+         # SURVEY 8(d) counts one HBM pass per gate (32 * 2^n B, 16 * 2^n if controlled), as the reference executes them;
+         # a fused launch applies gates_per_launch of them in one pass, so this figure exceeds the peak
+         "achieved_algorithmic": alg_gbs, "algorithmic_frac": alg_gbs / peak,
+         "algorithmic_bytes_per_launch": st1["gate_algorithmic_bytes"] / launches, "gates_per_launch": n_gates / launches,
+         "note": "frac = HBM bytes the pass kernel moves per launch / mean launch duration (CUDA events over the timed region, "
+                 "includes NVLink exchanges at N > 1) / measured copy peak; achieved_algorithmic is the per-gate accounting of "
+                 "SURVEY 8(d) and is inflated by fusion"}
+    if st1["global_swaps"]:
+        # NVLink side: fused-remap passes pull (1 - 2^-k) of a chunk from partner ranks while they run (the same
+        # amount leaves through the other direction of the links); stand-alone exchanges are timed on their own
+        nv_ms = st1.get("remap_ms", 0.0) + st1.get("swap_ms", 0.0)
+        nv_bytes = float(st1["swap_bytes_sent"])
+        plain = launches - st1.get("remap_passes", 0)
+        plain_ms = (fwd_ms - nv_ms) / plain if plain > 0 else None
+        r["nvlink"] = {"bytes_per_dir": nv_bytes, "ms": nv_ms, "gbs_per_dir": nv_bytes / (nv_ms / 1e3) / 1e9 if nv_ms > 0 else None,
+                       "frac_of_900": nv_bytes / (nv_ms / 1e3) / 1e9 / 900.0 if nv_ms > 0 else None,
+                       "frac_of_measured_770": nv_bytes / (nv_ms / 1e3) / 1e9 / 770.0 if nv_ms > 0 else None,
+                       "global_swaps": st1["global_swaps"], "fused_remap_passes": st1.get("remap_passes", 0),
+                       "avg_fused_pass_ms": st1.get("remap_ms", 0.0) / st1["remap_passes"] if st1.get("remap_passes") else None,
+                       "avg_plain_pass_ms": plain_ms,
+                       "what": "per rank and per forward; ms = device time (CUDA events) of the passes whose load carries the swaps "
+                               "(they also apply their gates: the exchange is their read) plus any stand-alone exchange"}
+    return r
+
+
+def cfg5_point(args, ranks: Ranks, jit: int):
+    """BASELINE config 5 on 8 ranks: 34-qubit ansatz (10 layers), forward from a reset, 10^5-shot distributed sample,
+    expectation values; parity flag from a 24-qubit twin of the same circuit against the oracle."""
+    from damavand_b200 import Circuit, circuits
+    out = {"workload": workload_desc("hea34"), "n_gpus": ranks.gpus}
+    twin = parity_check(ranks, jit, cases=[(24, "hea", 10)])
+    out["parity_twin"] = {k: twin[k] for k in ("ok", "max_rel_err", "l2_rel_err", "samples_ok", "n")}
+    n = 34
+    c = Circuit(n, "distributed_gpu")
+    ng = circuits.hea(c, n, 10, observables=True)
+    if jit:
+        c.set_jit(1)
+    for _ in range(2):
+        c.reset_amplitudes(); c.forward_async()
+    c.synchronize()
+    if jit:
+        c.jit_wait()
+        c.reset_amplitudes(); c.forward_async(); c.synchronize()
+    ranks.barrier(c)
+    c.stats_reset()
+    k = max(1, min(args.steps, 3))
+    c.timer_begin()
+    for _ in range(k):
+        c.reset_amplitudes(); c.forward_async()
+    fwd = ranks.max(c.timer_end() / k)
+    st = {a: (b / k if isinstance(b, (int, float)) else b) for a, b in c.stats().items()}
+    shots = 100000
+    u = np.random.default_rng(1235).random(2 * shots)
+    ranks.barrier(c)
+    t0 = time.perf_counter()
+    s = c.sample_numpy(shots, u)
+    t_sample = ranks.max(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    ev = c.extract_expectation_values_numpy(s)
+    ev_mean = ev.mean(axis=0)
+    t_ev = ranks.max(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    ez = c.expectation_z()
+    t_ez = ranks.max(time.perf_counter() - t0)
+    norm = c.norm()
+    out.update({"gates": ng, "forward_ms": fwd, "gates_per_sec": ng / (fwd / 1e3), "passes": st["tile_passes"], "global_swaps": st["global_swaps"],
+                "fused_remap_passes": st.get("remap_passes", 0), "nvlink_bytes_per_dir": st["swap_bytes_sent"],
+                "sample_shots": shots, "sample_ms": t_sample * 1e3, "extract_expectation_values_ms": t_ev * 1e3,
+                "expectation_z_ms": t_ez * 1e3, "norm_err": abs(norm - 1.0),
+                "sampled_vs_exact_z_max_abs_diff": float(np.abs(ev_mean - ez).max()),
+                "what": "reset + forward timed with CUDA events (max over ranks); sample = tree build + rank draw + per-rank descent + "
+                        "allreduce, wall clock with host buffers; sampled <Z> against the exact reduction as a statistical cross-check "
+                        "(expected |diff| ~ 1/sqrt(shots) = 0.003)"})
+    c.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--cpu-gates-per-step", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-scaling-point", action="store_true")
+    ap.add_argument("--no-single-gate", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison that precedes the timed regions")
+    ap.add_argument("--no-cfg5", action="store_true", help="N = 8 only: skip the 34-qubit config-5 point")
+    ap.add_argument("--unfused", action="store_true", help="one kernel per gate (no fusion) for comparison")
+    ap.add_argument("--jit", type=int, default=None, help="structure-specialised kernels: 0 off, 1 on (compiled during warm-up)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    from damavand_b200 import Circuit, distributed
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks"}))
+            return 2
+    ranks = Ranks(args.gpus)
+    rank = ranks.rank
+    name = args.workload or ("qft30" if args.gpus == 1 else "random32")
+    n = workload_qubits(name)
+    method = "gpu" if args.gpus == 1 else "distributed_gpu"
+    if args.gpus > 1:
+        distributed.initialize("nccl")
+    device = int(os.environ.get("LOCAL_RANK", "0"))
+    # run-time specialised pass kernels (validated against the oracle in the parity leg below and in tests/)
+    jit = args.jit if args.jit is not None else int(os.environ.get("DVD_BENCH_JIT", "1"))
+
+    # ---- parity first: a fast step that computes the wrong state is not a result -------------------------------
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(ranks, jit)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"error": "parity check against the oracle failed", "parity": parity}), flush=True)
+            return 3
+
+    circ = Circuit(n, method)
+    if args.unfused:
+        circ.set_unfused(True)
+    n_gates = build_workload(circ, name)
+    m = measure(circ, n_gates, args, ranks, jit, device, sample_clocks=True)
+    st, st1 = m["from_reset_stats"], m["dense_stats"]
+    # the state the timed forwards left behind is still a unit vector (one reduction pass, after the timed region)
+    norm = circ.norm()
+    sanity = {"norm_after_timed_region": norm, "ok": abs(norm - 1.0) < 1e-10}
     n_local = n - int(np.log2(args.gpus))
-    pass_bytes = 32.0 * (1 << n_local)
-    roofline = None
-    if launches_fwd > 0:
-        fwd_s = fwd_ms / 1e3
-        # a non-controlled gate = 32*2^n_local B, a controlled gate = 16*2^n_local B; a launch of the
-        # pass kernel processes (gates / launches) of them.  achieved = algorithmic bytes per launch / mean launch
-        # duration = total algorithmic bytes / forward time (CUDA events on the engine's stream).
-        achieved = st1["gate_algorithmic_bytes"] / fwd_s / 1e9
-        hbm_gbs = st1["pass_bytes"] / fwd_s / 1e9
-        traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tj.get(f"{name}_g{args.gpus}", {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "kernel": "k_tile_pass" if st1["tile_passes"] else "k_simple_gate",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src,
-                    "launches_per_circuit": launches_fwd, "avg_launch_ms": fwd_ms / launches_fwd,
-                    "algorithmic_bytes_per_launch": st1["gate_algorithmic_bytes"] / launches_fwd,
-                    "hbm_bytes_per_launch": st1["pass_bytes"] / launches_fwd,
-                    "hbm_pass_gbs": hbm_gbs, "hbm_pass_frac": hbm_gbs / peak,
-                    "note": "achieved counts SURVEY 8(d) algorithmic bytes (32*2^n B per gate, 16*2^n if controlled); "
-                            "it exceeds the HBM peak because one launch applies many gates while moving 32*2^n B once "
-                            "(16*2^n for the first pass after a reset, which synthesises |0..0> instead of reading it). "
-                            "hbm_pass_gbs = bytes the passes really move / time (what ncu's dram__bytes shows) and "
-                            "hbm_pass_frac = that / peak is the fraction to compare with the 70 % target; the fused "
-                            "passes are latency / fp64-pipe bound at 16 warps per SM, not HBM bound (DESIGN.md section 3)"}
-        if st1["global_swaps"]:
-            roofline["kernel"] += " + NVLink half-chunk swaps"
-            roofline["global_swaps"] = st1["global_swaps"]
-            roofline["swap_bytes_sent_per_rank"] = st1["swap_bytes_sent"]
+    roofline = roofline_of(m, name, n_local, n_gates, args.gpus)
+    peak = measured_peaks()[0]
 
     # the pass kernel with ONE gate per pass: gate application as the reference does it (one pass over HBM per
     # gate), on the state the circuit just produced.  This is the number that compares with "gate application at
@@ -419,7 +600,10 @@ def main():
             circ.gates, circ.observables = [], []
             build_one(circ)
             reps = 6
-            circ.forward_async(); circ.synchronize()          # warm-up (non-zero input: no lazy reset involved)
+            for _ in range(4 if jit else 1):                  # warm-up (non-zero input: no lazy reset involved; kernel form settles)
+                circ.forward_async(); circ.synchronize()
+                if jit:
+                    circ.jit_wait()
             circ.timer_begin()
             for _ in range(reps):
                 circ.forward_async()
@@ -443,7 +627,7 @@ def main():
         per_shot = 2 if args.gpus > 1 else 1
         u = np.random.default_rng(1235).random(shots * per_shot)
         k_e2e = max(1, min(args.steps, 3))
-        barrier()
+        ranks.barrier(circ)
         t0 = time.perf_counter()
         for _ in range(k_e2e):
             circ.reset_amplitudes()
@@ -451,44 +635,53 @@ def main():
             s = circ.sample_numpy(shots, u)
             ev = circ.extract_expectation_values_numpy(s)
             float(ev.mean())
-        barrier()
-        dt = (time.perf_counter() - t0) / k_e2e
-        if args.gpus > 1:
-            import torch
-            import torch.distributed as dist
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        ranks.barrier(circ)
+        dt = ranks.max((time.perf_counter() - t0) / k_e2e)
         h2d = 80 * n_gates + 8 * shots * per_shot + 8 * shots + 4 * n
         d2h = 8 * shots + 8 * shots * n
         e2e = {"value": n_gates / dt, "unit": "gates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": dt * 1e3,
                "what": "reset + Circuit.forward() (plan, upload gate list, fused passes) + sample(1000) + extract_expectation_values, host buffers, wall clock"}
+    circ.close()
+    circ = None
 
-    # 1-GPU point of the strong-scaling workload the N > 1 runs use (cfg 4, random32): the headline N = 1 line is
-    # the 30-qubit circuit BASELINE.json's metric names, so the scaling baseline travels as an extra key
-    scaling_point = None
-    if args.gpus == 1 and args.workload is None and not args.no_scaling_point:
+    # Strong scaling (cfg 4): the N > 1 lines run random32 and must be divided by the 1-GPU rate of the SAME workload,
+    # measured the same way (same step, same kernels, --steps / --warmup).  N = 1: it travels as `scaling_point` (the
+    # headline line itself is cfg 3).  N > 1: rank 0 measures it on its own GPU right here -- the other ranks wait --
+    # so that every line carries its own efficiency and nobody divides qft30 by random32.
+    scaling_point = strong_scaling = None
+    want_base = (args.gpus == 1 and args.workload is None and not args.no_scaling_point) or \
+                (args.gpus > 1 and not args.no_scaling_point)
+    if want_base:
+        sp_name = "random32" if args.gpus == 1 else name
+        base = None
+        if rank == 0:
+            try:
+                c2 = Circuit(workload_qubits(sp_name), "gpu")
+                ng2 = build_workload(c2, sp_name)
+                m2 = measure(c2, ng2, args, Ranks(1), jit, device, sample_clocks=True)
+                base = {"workload": f"{sp_name}: {workload_desc(sp_name)}", "n_gpus": 1, "value": m2["value"], "unit": "gates/s",
+                        "ms_per_step": m2["dense_ms"], "from_reset_ms": m2["from_reset_ms"], "steps": args.steps, "warmup": args.warmup,
+                        "passes": int(round(m2["dense_stats"]["tile_passes"])), "jit": bool(jit), "clocks": m2["clocks"],
+                        "hbm_pass_frac": (roofline_of(m2, sp_name, workload_qubits(sp_name), ng2, 1) or {}).get("hbm_pass_frac"),
+                        "note": "same step definition as `value` (forward on a dense state), same kernels, same --steps/--warmup"}
+                c2.close()
+            except Exception as e:
+                base = {"workload": sp_name, "value": None, "note": f"failed: {e}"}
+        ranks.barrier()
+        if args.gpus == 1:
+            scaling_point = base
+        elif rank == 0:
+            strong_scaling = {"base": base, "base_value": base.get("value"), "value": m["value"],
+                              "efficiency": (m["value"] / (args.gpus * base["value"])) if base.get("value") else None,
+                              "what": "value / (n_gpus x base_value): 1-GPU rate of the same workload measured by rank 0 in this run"}
+
+    cfg5 = None
+    if args.gpus == 8 and args.workload is None and not args.no_cfg5:
         try:
-            circ.close()
-            circ = None
-            sp_name = "random32"
-            c2 = Circuit(workload_qubits(sp_name), "gpu")
-            ng2 = build_workload(c2, sp_name)
-            # same step definition and the same (interpreter) kernels as the N > 1 runs use by default
-            c2.reset_amplitudes(); c2.forward_async()
-            c2.forward_async(); c2.synchronize()
-            c2.timer_begin()
-            for _ in range(2):
-                c2.forward_async()
-            ms2 = c2.timer_end()
-            scaling_point = {"workload": f"{sp_name}: {workload_desc(sp_name)}", "n_gpus": 1, "value": 2 * ng2 / (ms2 / 1e3),
-                             "unit": "gates/s", "ms_per_step": ms2 / 2, "steps": 2, "warmup": 2, "jit": False,
-                             "note": "same step definition as `value` (forward on a dense state), interpreter kernels as in "
-                                     "the default N > 1 runs; divide an N-GPU line's value by N x this for strong-scaling efficiency"}
-            c2.close()
+            cfg5 = cfg5_point(args, ranks, jit)
         except Exception as e:
-            scaling_point = {"workload": "random32", "value": None, "note": f"failed: {e}"}
+            cfg5 = {"error": f"{type(e).__name__}: {e}"}
 
     cpu_baseline = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
@@ -500,9 +693,12 @@ def main():
             cpu_baseline = {"value": None, "unit": "gates/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
 
     if rank == 0:
+        dense_state = {"value": m["value"], "unit": "gates/s", "ms_per_step": m["dense_ms"],
+                       "what": "forward of the same circuit on a dense state (no reset, nothing known to be zero): every pass "
+                               "moves 32*2^n_local B"}
         line = {
-            "metric": "gates_per_sec", "value": dense_state["value"], "unit": "gates/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dense_state["ms_per_step"], "higher_is_better": True,
+            "metric": "gates_per_sec", "value": m["value"], "unit": "gates/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": m["dense_ms"], "higher_is_better": True,
             "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{name}: {workload_desc(name)}", "apply_method": method,
                        "step": "forward of the whole circuit on a DENSE state (no reset between steps, nothing known to be zero: "
@@ -510,27 +706,29 @@ def main():
                                "reference's API runs it, reset to |0..0> + forward, where the engine tracks which qubits have "
                                "left |0> and neither reads nor launches tiles that are zero by construction",
                        "l2": "state (>= 4 GiB per GPU) is far larger than the 126 MB L2; no flush needed",
-                       "fused": not args.unfused, "wall_s_timed_region": t_wall_dense, "wall_s_from_reset_region": t_wall,
-                       "jit": jit_cfg},
-            "gpu_launches": int(round(st1["kernel_launches"] * dense_reps)),
+                       "fused": not args.unfused, "wall_s_timed_region": m["wall_dense"], "wall_s_from_reset_region": m["wall_from_reset"],
+                       "jit": m["jit"]},
+            "gpu_launches": int(round(st1["kernel_launches"] * m["reps"])),
             "passes_per_circuit": int(round(st1["tile_passes"])),
             "global_swaps_per_circuit": int(round(st1["global_swaps"])),
-            "from_reset": {"value": value, "unit": "gates/s", "ms_per_step": ms / args.steps, "steps": args.steps,
+            "from_reset": {"value": m["from_reset_value"], "unit": "gates/s", "ms_per_step": m["from_reset_ms"], "steps": args.steps,
                            "gpu_launches": int(st["kernel_launches"]),
                            "what": "reset to |0..0> + forward, timed like `value` (the step every BASELINE config describes)"},
-            "dense_state": dense_state,
-            "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline,
+            "dense_state": dense_state, "parity": parity, "sanity": sanity,
+            "clocks": m["clocks"], "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline,
         }
         if scaling_point is not None:
             line["scaling_point"] = scaling_point
+        if strong_scaling is not None:
+            line["strong_scaling"] = strong_scaling
+        if cfg5 is not None:
+            line["cfg5_point"] = cfg5
         print(json.dumps(line), flush=True)
-    if circ is not None:
-        circ.close()
     if args.gpus > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return 0 if sanity["ok"] else 4
 
 
 if __name__ == "__main__":

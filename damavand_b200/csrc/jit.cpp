@@ -41,7 +41,7 @@ std::string generate_pass_source(const Pass& p, const std::string& fn_name, int 
     // of this group's next slot
     auto release_buffer = [&]() {
         o << ind << "group_sync(grp);   // every thread has read its registers back: the buffer is free\n"
-          << ind << "if (t + 3 * stride < n_tiles) ring_fetch(ring, slot + 3, amp_in, pd, t + 3 * stride, tid);\n";
+          << ind << "if (t + 3 * stride < n_tiles) ring_fetch(ring, slot + 3, amp_in, pd, t + 3 * stride, tid, toff.get(IO_GROUP));\n";
         if (has_tab)
             o << ind << "if (tid < n_tab && t + 2 * stride < n_tiles)\n"
               << ind << "    ring.wcs(grp, k + 1)[tid] = table_cta_const(tables, tid, cta_base_runs(pd, t + 2 * stride) | pd.rank_bits);\n";
@@ -59,22 +59,26 @@ std::string generate_pass_source(const Pass& p, const std::string& fn_name, int 
     if (!ring) {
         o << "    cplx* tile = reinterpret_cast<cplx*>(smem_raw);\n"
              "    __shared__ cplx s_wc[MAX_TABLE_OPS];\n"
+             "    __shared__ uint32_t s_toff[TOFF_WORDS];\n"
              "    const int tid = threadIdx.x;\n"
              "    const uint64_t cbase = cta_base_runs(pd, (uint64_t)blockIdx.x);\n"
              "    const uint64_t gbase = cbase | pd.rank_bits;\n";
         if (has_tab) o << "    if (tid < n_tab) s_wc[tid] = table_cta_const(tables, tid, gbase);\n";
         o << "    if (cbase & pd.zero_mask & ~pd.remap_lmask) return;\n"
              "    cplx a[NREG];\n"
-             "    tile_load<IO_GROUP>(amp_in, pd, a, cbase, tid);\n";
+             "    tile_load<IO_GROUP>(amp_in, pd, a, cbase, tid_offset_arith(pd, IO_GROUP, tid));\n"
+             "    const Toff toff = toff_fill(s_toff, pd, tid);   // table lookups in the shadow of the tile's loads\n";
         if (has_tab) o << "    __syncthreads();\n";
     } else {
         o << "    const Ring ring = ring_setup(smem_raw);\n"
              "    const int grp = threadIdx.x / NTHREADS, tid = threadIdx.x % NTHREADS;\n"
+             "    const uint32_t* s_toff = ring.toff;\n"
+             "    const Toff toff = toff_fill(ring.toff, pd, tid);   // once per CTA: the offsets do not depend on the tile\n"
              "    const unsigned n_tiles = 1u << pd.n_cta_bits, stride = gridDim.x;   // dense states only (zero_mask == 0)\n"
              "    {   // prologue: slots 0 and 2 are fetched by group 0, slot 1 by group 1\n"
              "        const unsigned t0 = blockIdx.x + grp * stride;\n"
-             "        if (t0 < n_tiles) ring_fetch(ring, grp, amp_in, pd, t0, tid);\n"
-             "        if (grp == 0 && blockIdx.x + 2 * stride < n_tiles) ring_fetch(ring, 2, amp_in, pd, blockIdx.x + 2 * stride, tid);\n";
+             "        if (t0 < n_tiles) ring_fetch(ring, grp, amp_in, pd, t0, tid, toff.get(IO_GROUP));\n"
+             "        if (grp == 0 && blockIdx.x + 2 * stride < n_tiles) ring_fetch(ring, 2, amp_in, pd, blockIdx.x + 2 * stride, tid, toff.get(IO_GROUP));\n";
         if (has_tab) o << "        if (tid < n_tab && t0 < n_tiles) ring.wcs(grp, 0)[tid] = table_cta_const(tables, tid, cta_base_runs(pd, t0) | pd.rank_bits);\n";
         o << "    }\n"
              "    unsigned k = 0;\n"
@@ -91,7 +95,7 @@ std::string generate_pass_source(const Pass& p, const std::string& fn_name, int 
         if (last_switch < 0) release_buffer();
     }
     o << ind << "ThreadCtx ctx;\n"
-      << ind << "ctx.pidx = gbase | tid_offset(pd, IO_GROUP, tid);\n"
+      << ind << "ctx.pidx = gbase | toff.get(IO_GROUP);\n"
       << ind << "ctx.ph = cplx{1.0, 0.0};\n"
       << ind << "ctx.ph_dirty = false;\n"
       << ind << "ctx.tid = tid;\n";
@@ -103,14 +107,14 @@ std::string generate_pass_source(const Pass& p, const std::string& fn_name, int 
             const int from = (code - OC_SWITCH) / NGROUPS, to = (code - OC_SWITCH) % NGROUPS;
             o << ind << "flush_phase(a, ctx); " << sync << ";\n"
               << ind << "switch_store<" << from << ">(tile, a, tid, pp.ops[" << k << "], " << flags << "u, gbase); " << sync << ";\n"
-              << ind << "stage_load<" << to << ">(tile, a, tid); ctx.pidx = gbase | tid_offset(pd, " << to << ", tid);\n";
+              << ind << "stage_load<" << to << ">(tile, a, tid); ctx.pidx = gbase | toff.get(" << to << ");\n";
             if (ring && (int)k == last_switch) release_buffer();
         } else {
             o << ind << "apply_op<C_ALL>(a, &pp.ops[" << k << "], " << code << ", " << flags << "u, ctx, tables, n_tab, " << wcs << ");\n";
         }
     }
     o << ind << "flush_phase(a, ctx);\n"
-      << ind << "tile_store<" << (int)p.desc.io_out << ">(amp, pd, a, gbase - pd.rank_bits);\n";
+      << ind << "tile_store<" << (int)p.desc.io_out << ">(amp, pd, a, gbase - pd.rank_bits, s_toff);\n";
     if (ring) o << "    }\n";
     o << "}\n";
     return o.str();

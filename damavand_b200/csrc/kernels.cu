@@ -23,6 +23,7 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* tile = reinterpret_cast<cplx*>(smem_raw);
     __shared__ cplx s_wc[MAX_TABLE_OPS];      // per-CTA constants of the pass's table ops
+    __shared__ uint32_t s_toff[TOFF_WORDS];   // per-thread tile offsets of the three layouts (tile_kernel.cuh: Toff)
     const PassDesc& pd = pp.pd;
 
     const int tid = threadIdx.x;
@@ -37,11 +38,13 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     // normally does not even launch those)
     if (cbase & pd.zero_mask & ~pd.remap_lmask) return;
     cplx a[NREG];
-    tile_load<IO_GROUP>(amp, pd, a, cbase, tid);   // with a fused remap (pd.remap_n > 0) the input is pd.remap_src[..], out of place
+    // with a fused remap (pd.remap_n > 0) the input is pd.remap_src[..], out of place
+    tile_load<IO_GROUP>(amp, pd, a, cbase, tid_offset_arith(pd, IO_GROUP, tid));
+    const Toff toff = toff_fill(s_toff, pd, tid);   // table lookups in the shadow of the tile's loads
 
     if (n_tab > 0) __syncthreads();
     ThreadCtx ctx;
-    ctx.pidx = gbase | tid_offset(pd, IO_GROUP, tid);
+    ctx.pidx = gbase | toff.get(IO_GROUP);
     ctx.ph = cplx{1.0, 0.0};
     ctx.ph_dirty = false;
     ctx.tid = tid;
@@ -62,7 +65,7 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
             if (to == 0) stage_load<0>(tile, a, tid);
             else if (to == 1) stage_load<1>(tile, a, tid);
             else stage_load<2>(tile, a, tid);
-            ctx.pidx = gbase | tid_offset(pd, to, tid);
+            ctx.pidx = gbase | toff.get(to);
             continue;
         }
         k += apply_op<SET>(a, &op, code, op.flags, ctx, tables, n_tab, s_wc);
@@ -70,8 +73,8 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     flush_phase(a, ctx);
     // the planner ends a pass in the group-2 or the group-1 layout: both store 128-byte segments per quarter warp
     // (rank bits lie above the local index bits, so gbase - rank_bits is the tile's base again)
-    if (pd.io_out == IO_GROUP) tile_store<IO_GROUP>(amp, pd, a, gbase - pd.rank_bits);
-    else tile_store<1>(amp, pd, a, gbase - pd.rank_bits);
+    if (pd.io_out == IO_GROUP) tile_store<IO_GROUP>(amp, pd, a, gbase - pd.rank_bits, s_toff);
+    else tile_store<1>(amp, pd, a, gbase - pd.rank_bits, s_toff);
 }
 
 // Two-group persistent form of the same pass (tile_kernel.cuh, "ring"): one CTA of 2 x 256 threads per SM, three
@@ -89,13 +92,14 @@ k_tile_pass_ring(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) 
     const cplx* amp_in = amp;
     const Ring ring = ring_setup(smem_raw);
     const int grp = threadIdx.x / NTHREADS, tid = threadIdx.x % NTHREADS;
+    const Toff toff = toff_fill(ring.toff, pd, tid);      // once per CTA: the offsets do not depend on the tile
     const unsigned n_tiles = 1u << pd.n_cta_bits, stride = gridDim.x;
     const int n_ops = pd.n_ops;
     const int last_switch = pd.last_switch;
     {   // prologue: slots 0 and 2 are fetched by group 0, slot 1 by group 1
         const unsigned t0 = blockIdx.x + grp * stride;
-        if (t0 < n_tiles) ring_fetch(ring, grp, amp_in, pd, t0, tid);
-        if (grp == 0 && blockIdx.x + 2 * stride < n_tiles) ring_fetch(ring, 2, amp_in, pd, blockIdx.x + 2 * stride, tid);
+        if (t0 < n_tiles) ring_fetch(ring, grp, amp_in, pd, t0, tid, toff.get(IO_GROUP));
+        if (grp == 0 && blockIdx.x + 2 * stride < n_tiles) ring_fetch(ring, 2, amp_in, pd, blockIdx.x + 2 * stride, tid, toff.get(IO_GROUP));
         if (tid < n_tab && t0 < n_tiles) ring.wcs(grp, 0)[tid] = table_cta_const(tables, tid, cta_base_runs(pd, t0) | pd.rank_bits);
     }
     unsigned kslot = 0;
@@ -112,13 +116,13 @@ k_tile_pass_ring(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) 
         // the slot's buffer is free once its last transpose has been read back: fetch slot + 3 into it
         auto release_buffer = [&]() {
             group_sync(grp);
-            if (t + 3 * stride < n_tiles) ring_fetch(ring, slot + 3, amp_in, pd, t + 3 * stride, tid);
+            if (t + 3 * stride < n_tiles) ring_fetch(ring, slot + 3, amp_in, pd, t + 3 * stride, tid, toff.get(IO_GROUP));
             if (tid < n_tab && t + 2 * stride < n_tiles)
                 ring.wcs(grp, kslot + 1)[tid] = table_cta_const(tables, tid, cta_base_runs(pd, t + 2 * stride) | pd.rank_bits);
         };
         if (last_switch < 0) release_buffer();
         ThreadCtx ctx;
-        ctx.pidx = gbase | tid_offset(pd, IO_GROUP, tid);
+        ctx.pidx = gbase | toff.get(IO_GROUP);
         ctx.ph = cplx{1.0, 0.0};
         ctx.ph_dirty = false;
         ctx.tid = tid;
@@ -136,15 +140,15 @@ k_tile_pass_ring(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) 
                 if (to == 0) stage_load<0>(tile, a, tid);
                 else if (to == 1) stage_load<1>(tile, a, tid);
                 else stage_load<2>(tile, a, tid);
-                ctx.pidx = gbase | tid_offset(pd, to, tid);
+                ctx.pidx = gbase | toff.get(to);
                 if (k == last_switch) release_buffer();
                 continue;
             }
             k += apply_op<SET>(a, &op, code, op.flags, ctx, tables, n_tab, wcs);
         }
         flush_phase(a, ctx);
-        if (pd.io_out == IO_GROUP) tile_store<IO_GROUP>(amp, pd, a, gbase - pd.rank_bits);
-        else tile_store<1>(amp, pd, a, gbase - pd.rank_bits);
+        if (pd.io_out == IO_GROUP) tile_store<IO_GROUP>(amp, pd, a, gbase - pd.rank_bits, ring.toff);
+        else tile_store<1>(amp, pd, a, gbase - pd.rank_bits, ring.toff);
     }
 }
 

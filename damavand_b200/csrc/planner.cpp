@@ -672,7 +672,7 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates_in, int n_local,
     }
     std::vector<int> pending(G);
     for (int i = 0; i < G; ++i) pending[i] = i;
-    const int min_low = std::min(opt.min_low, TILE_BITS);
+    const int min_low = std::max(3, std::min(opt.min_low, TILE_BITS));   // >= 3: 128-byte segments, and the kernels' offset stash relies on it
 
     int gate_budget = opt.max_ops_per_pass;
     // The phase polynomial outlives a pass: a term is only emitted when a non-diagonal gate is about to hit

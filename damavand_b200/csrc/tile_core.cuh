@@ -231,7 +231,7 @@ DVD_HD int smem_slot(int idx) { return idx + (idx >> 4); }
 constexpr int RING_BUFFERS = 3;
 constexpr int RING_GROUPS = 2;
 constexpr int RING_WC_BYTES = RING_GROUPS * 2 * MAX_TABLE_OPS * (int)sizeof(cplx);
-constexpr int RING_SMEM_BYTES = RING_BUFFERS * TILE_SLOTS * (int)sizeof(cplx) + RING_WC_BYTES + 64;
+constexpr int RING_SMEM_BYTES = RING_BUFFERS * TILE_SLOTS * (int)sizeof(cplx) + RING_WC_BYTES + 64 + NGROUPS * NTHREADS * 4;
 
 // Physical offset (in amplitudes) of tile index idx.
 DVD_HD uint64_t tile_offset(const PassDesc& pd, int idx) {
@@ -468,13 +468,25 @@ DVD_HD void table_reg(cplx (&a)[NREG], const DevOp& op, unsigned flags, const Th
 DVD_HD uint64_t thread_pidx(const PassDesc& pd, uint64_t gbase, int g, int tid) {
     return gbase | tile_offset(pd, stage_idx(g, tid, 0));
 }
-// The same through the planner's table.
+// The same through the planner's table (device: read-only data path).
 DVD_HD uint64_t tid_offset(const PassDesc& pd, int g, int tid) {
 #ifdef __CUDA_ARCH__
     return __ldg(reinterpret_cast<const unsigned long long*>(pd.tid_off) + g * NTHREADS + tid);
 #else
     return pd.tid_off[g * NTHREADS + tid];
 #endif
+}
+// The same by arithmetic over the thread's 8 index bits (shift amounts from the constant bank, ~25 integer
+// instructions, nothing waits on memory): used where the offset is needed at once -- in front of the tile's loads.
+DVD_HD uint64_t tid_offset_arith(const PassDesc& pd, int g, int tid) {
+    uint64_t off = 0;
+    const int sh = REG_BITS * g;
+#pragma unroll
+    for (int k = 0; k < THREAD_BITS; ++k) {
+        const int p = k < sh ? k : k + REG_BITS;      // tile position of thread-index bit k in group g's layout
+        off |= (uint64_t)((tid >> k) & 1) << pd.tile_q[p];
+    }
+    return off;
 }
 // Constant part of a permuting switch for one CTA: v0 ^ conditional flips.
 DVD_HD unsigned perm_const(const DevOp& op, uint64_t gbase) {

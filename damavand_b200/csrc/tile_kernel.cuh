@@ -50,17 +50,41 @@ __device__ __forceinline__ int group_tid() {
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     return (int)(tid & (NTHREADS - 1));
 }
+// Per-thread tile offsets of the three register-group layouts, stashed in shared memory at the start of the kernel:
+// they are needed again after every transpose (thread-level controls and parities) and for the write-back, when all
+// registers hold amplitudes, and fetching them from the planner's table at that point put a dependent global load
+// in front of the stores (7 % of the stall samples of a dense 30-qubit pass, profiles/r2_ncu_qft30_classic2.txt).
+// 32 bits per entry: tile positions 0..2 are always qubits 0..2 (PlanOptions::min_low >= 3), so the low three bits of
+// an offset are the low three bits of the thread index (layouts 1, 2) or zero (layout 0).  Every thread only reads
+// the slots it wrote itself: no barrier.
+constexpr int TOFF_WORDS = NGROUPS * NTHREADS;
+struct Toff {
+    const uint32_t* s;
+    int tid;
+    __device__ __forceinline__ uint64_t get(int g) const {
+        return ((uint64_t)s[g * NTHREADS + tid] << 3) | (g == 0 ? 0u : (unsigned)(tid & 7));
+    }
+};
+__device__ __forceinline__ Toff toff_fill(uint32_t* s, const PassDesc& pd, int tid) {
+    uint64_t v[NGROUPS];
+#pragma unroll
+    for (int g = 0; g < NGROUPS; ++g) v[g] = tid_offset(pd, g, tid);
+#pragma unroll
+    for (int g = 0; g < NGROUPS; ++g) s[g * NTHREADS + tid] = (uint32_t)(v[g] >> 3);
+    return Toff{s, tid};
+}
 // Every amplitude is touched exactly once per pass: stream it past L1 so that the phase tables stay there.
 __device__ __forceinline__ cplx ld_stream(const cplx* p) {
     const double2 v = __ldcs(reinterpret_cast<const double2*>(p));
     return cplx{v.x, v.y};
 }
 __device__ __forceinline__ void st_stream(cplx* p, cplx v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
-// `cbase` = cta_base_runs(tile index): the tile's physical base, computed once per tile by the caller.
+// `cbase` = cta_base_runs(tile index): the tile's physical base, computed once per tile by the caller;
+// `toff` = this thread's offset in the group-G layout.
 template <int G>
-__device__ __forceinline__ IoAddr io_addr(const PassDesc& pd, uint64_t cbase) {
+__device__ __forceinline__ IoAddr io_addr(const PassDesc& pd, uint64_t cbase, uint64_t toff) {
     IoAddr io;
-    io.i0 = cbase + tid_offset(pd, G, group_tid());
+    io.i0 = cbase + toff;
 #pragma unroll
     for (int k = 0; k < REG_BITS; ++k) io.hs[k] = 1ull << pd.tile_q[G * REG_BITS + k];
     return io;
@@ -72,8 +96,9 @@ __device__ __forceinline__ uint64_t io_reg_offset(const IoAddr& io, int j) {
     return off;
 }
 template <int G>
-__device__ __forceinline__ void tile_store(cplx* amp, const PassDesc& pd, const cplx (&a)[NREG], uint64_t cbase) {
-    const IoAddr io = io_addr<G>(pd, cbase);
+__device__ __forceinline__ void tile_store(cplx* amp, const PassDesc& pd, const cplx (&a)[NREG], uint64_t cbase, const uint32_t* s_toff) {
+    const Toff t{s_toff, group_tid()};       // (opaque re-read of %tid: nothing address-related stays live across the gates)
+    const IoAddr io = io_addr<G>(pd, cbase, t.get(G));
     cplx* p0 = amp + io.i0;
 #pragma unroll
     for (int j = 0; j < NREG; ++j) st_stream(p0 + io_reg_offset(io, j), a[j]);
@@ -82,13 +107,14 @@ __device__ __forceinline__ void tile_store(cplx* amp, const PassDesc& pd, const 
 // are zero by construction and their memory is never read (after a reset it has not even been written).
 // With a fused remap (PassDesc::remap_n > 0) every amplitude comes from the buffer -- this rank's input or a partner
 // rank's, over NVLink -- that held it before the global<->local qubit swap(s); zero_mask then applies to the source index.
+// `toff`: the thread's offset in the group-G layout (tid_offset_arith at the start of a kernel, else the stash).
 template <int G>
-__device__ __forceinline__ void tile_load(const cplx* amp, const PassDesc& pd, cplx (&a)[NREG], uint64_t cbase, int tid) {
-    const IoAddr io = io_addr<G>(pd, cbase);
+__device__ __forceinline__ void tile_load(const cplx* amp, const PassDesc& pd, cplx (&a)[NREG], uint64_t cbase, uint64_t toff) {
+    const IoAddr io = io_addr<G>(pd, cbase, toff);
     const uint64_t zmask = pd.zero_mask;
     if (pd.remap_n == 0) {
         const cplx* p0 = amp + io.i0;
-        const bool thread_zero = (tid_offset(pd, G, tid) & zmask) != 0;
+        const bool thread_zero = (toff & zmask) != 0;
         const int zregs = pd.zero_regbits;
 #pragma unroll
         for (int j = 0; j < NREG; ++j)
@@ -113,8 +139,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Every thread fetches exactly the 16 amplitudes it will hold in the group-G layout, into the slots
 // stage_load<G> reads them back from (dense states only: no zero_mask handling).  Fused remaps are honoured.
 template <int G>
-__device__ __forceinline__ void tile_prefetch_issue(cplx* tile, const cplx* amp, const PassDesc& pd, uint64_t cbase, int tid) {
-    const IoAddr io = io_addr<G>(pd, cbase);
+__device__ __forceinline__ void tile_prefetch_issue(cplx* tile, const cplx* amp, const PassDesc& pd, uint64_t cbase, int tid, uint64_t toff) {
+    const IoAddr io = io_addr<G>(pd, cbase, toff);
     cplx* sp = tile + smem_slot(stage_idx(G, tid, 0));
     if (pd.remap_n == 0) {
         const cplx* p0 = amp + io.i0;
@@ -128,12 +154,6 @@ __device__ __forceinline__ void tile_prefetch_issue(cplx* tile, const cplx* amp,
         }
     }
 }
-template <int G>
-__device__ __forceinline__ void tile_prefetch(cplx* tile, const cplx* amp, const PassDesc& pd, uint64_t cbase, int tid) {
-    tile_prefetch_issue<G>(tile, amp, pd, cbase, tid);
-    cp_async_commit();
-}
-
 template <int FROM>
 __device__ __forceinline__ void switch_store(cplx* tile, const cplx (&a)[NREG], int tid, const DevOp& op, unsigned flags, uint64_t gbase) {
     if (flags & F_PERM) stage_store_perm<FROM>(tile, a, tid, op, gbase);
@@ -176,6 +196,7 @@ struct Ring {
     cplx* tiles;        // RING_BUFFERS x TILE_SLOTS
     cplx* wc;           // [RING_GROUPS][2][MAX_TABLE_OPS]
     uint64_t* full;     // RING_BUFFERS mbarriers
+    uint32_t* toff;     // TOFF_WORDS: thread-offset stash (the same for both groups)
     __device__ __forceinline__ cplx* tile(unsigned slot) const { return tiles + (slot % RING_BUFFERS) * TILE_SLOTS; }
     __device__ __forceinline__ cplx* wcs(int g, unsigned k) const { return wc + (g * 2 + (k & 1)) * MAX_TABLE_OPS; }
 };
@@ -184,6 +205,7 @@ __device__ __forceinline__ Ring ring_setup(unsigned char* smem_raw) {
     r.tiles = reinterpret_cast<cplx*>(smem_raw);
     r.wc = r.tiles + RING_BUFFERS * TILE_SLOTS;
     r.full = reinterpret_cast<uint64_t*>(r.wc + RING_GROUPS * 2 * MAX_TABLE_OPS);
+    r.toff = reinterpret_cast<uint32_t*>(r.full + 8);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int b = 0; b < RING_BUFFERS; ++b) mbar_init(r.full + b, NTHREADS);
@@ -193,8 +215,8 @@ __device__ __forceinline__ Ring ring_setup(unsigned char* smem_raw) {
     return r;
 }
 // Fetch slot `slot` (tile index t) into its buffer; all NTHREADS threads of one group call this.
-__device__ __forceinline__ void ring_fetch(const Ring& r, unsigned slot, const cplx* amp, const PassDesc& pd, uint64_t t, int tid) {
-    tile_prefetch_issue<IO_GROUP>(r.tile(slot), amp, pd, cta_base_runs(pd, t), tid);
+__device__ __forceinline__ void ring_fetch(const Ring& r, unsigned slot, const cplx* amp, const PassDesc& pd, uint64_t t, int tid, uint64_t toff) {
+    tile_prefetch_issue<IO_GROUP>(r.tile(slot), amp, pd, cta_base_runs(pd, t), tid, toff);
     cp_async_arrive(r.full + slot % RING_BUFFERS);
 }
 // Wait until slot `slot` has landed in its buffer (its use number slot / RING_BUFFERS gives the phase parity).

@@ -72,6 +72,46 @@ __global__ void __launch_bounds__(256) k_persist(double2* a, int seg_bits, int h
     }
     if (c == 123.456) pad[threadIdx.x] = 0;
 }
+// G: one tile per CTA + L2 prefetch of the tile `dist` CTAs ahead (each 128-byte line once: lanes with (tid & 7) == 0)
+template <int MODE>   // 0: prefetch.global.L2, 1: cp.async.bulk.prefetch.L2 (128 B), 2: prefetch.global.L2::evict_last
+__global__ void __launch_bounds__(256) k_one_pf(double2* a, int seg_bits, int hi_start, uint64_t n_tiles, int dist, double c) {
+    extern __shared__ unsigned char pad[];
+    const uint64_t tn = (uint64_t)blockIdx.x + dist;
+    if (tn < n_tiles && (threadIdx.x & 7) == 0) {
+        const uint64_t base = tile_base(tn, seg_bits, hi_start);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const double2* p = a + base + tile_off(k * 256 + threadIdx.x, seg_bits, hi_start);
+            if (MODE == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            else if (MODE == 1) asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;" ::"l"(p));
+            else asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
+        }
+    }
+    rmw_tile<1>(a, tile_base(blockIdx.x, seg_bits, hi_start), seg_bits, hi_start, c);
+    if (c == 123.456) pad[threadIdx.x] = 0;
+}
+// H: one tile per CTA + "prefetch by load": cp.async (LDGSTS) of 4 bytes per SECTORS-th 32-byte sector of every line of
+// the tile `dist` CTAs ahead into a scratch word of shared memory (no register, never waited for)
+template <int PER_LINE>   // 1: one word per 128-byte line, 2: one per 64 bytes, 4: one per 32-byte sector
+__global__ void __launch_bounds__(256) k_one_pfld(double2* a, int seg_bits, int hi_start, uint64_t n_tiles, int dist, double c) {
+    extern __shared__ unsigned char pad[];
+    __shared__ unsigned scratch[256];
+    const uint64_t tn = (uint64_t)blockIdx.x + dist;
+    if (tn < n_tiles) {
+        const uint64_t base = tile_base(tn, seg_bits, hi_start);
+        const unsigned d = (unsigned)__cvta_generic_to_shared(&scratch[threadIdx.x]);
+        // 512 lines x PER_LINE words per tile, 256 threads: 2 * PER_LINE copies per thread
+#pragma unroll
+        for (int k = 0; k < 2 * PER_LINE; ++k) {
+            const int w = k * 256 + threadIdx.x;               // word index in [0, 512 * PER_LINE)
+            const int line = w / PER_LINE, sub = w % PER_LINE;
+            const char* p = reinterpret_cast<const char*>(a + base + tile_off(line * 8, seg_bits, hi_start)) + sub * (128 / PER_LINE);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(p) : "memory");
+        }
+    }
+    rmw_tile<1>(a, tile_base(blockIdx.x, seg_bits, hi_start), seg_bits, hi_start, c);
+    if (c == 123.456) pad[threadIdx.x] = (unsigned char)scratch[threadIdx.x];
+}
 // F: read-only and write-only halves of the traffic (where is the loss: reads or writes?)
 __global__ void __launch_bounds__(256) k_read_only(const double2* a, int seg_bits, int hi_start, double* sink) {
     const uint64_t base = tile_base(blockIdx.x, seg_bits, hi_start);
@@ -118,10 +158,10 @@ int main(int argc, char** argv) {
     struct Shape { const char* name; int seg_bits, hi_start; };
     const Shape shapes[] = {{"seg128B hi[n-9..]", 3, n - 9}, {"seg128B mid[12..20]", 3, 12}, {"seg256B hi[n-8..]", 4, n - 8},
                             {"seg128B hi[n-10..n-2]", 3, n - 10}, {"contig[0..11]", 12, 12}};
-    CK(cudaFuncSetAttribute(k_one<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CK(cudaFuncSetAttribute(k_one<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CK(cudaFuncSetAttribute(k_one<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CK(cudaFuncSetAttribute(k_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_one<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_one<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_one<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     char name[160];
     for (const Shape& sh : shapes) {
         if (sh.seg_bits == 12) {   // contiguous tiles: base = b << 12
@@ -140,6 +180,28 @@ int main(int argc, char** argv) {
             const size_t smem = per_sm >= 5 ? 0 : (size_t)(220 * 1024 / per_sm) - 2048;
             snprintf(name, sizeof name, "A %s cs, CTAs/SM <= %d (smem %zu KB)", sh.name, per_sm >= 5 ? 8 : per_sm, smem / 1024);
             report(name, time_it([&] { k_one<1><<<(unsigned)n_tiles, 256, smem>>>(a, sh.seg_bits, sh.hi_start, 1.0); }), bytes);
+        }
+        CK(cudaFuncSetAttribute(k_one_pf<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        CK(cudaFuncSetAttribute(k_one_pf<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        CK(cudaFuncSetAttribute(k_one_pf<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        CK(cudaFuncSetAttribute(k_one_pfld<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 230000));
+        CK(cudaFuncSetAttribute(k_one_pfld<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 230000));
+        CK(cudaFuncSetAttribute(k_one_pfld<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 230000));
+        for (size_t gran : {(size_t)0, (size_t)128, (size_t)32}) {
+            if (gran) { cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); printf("set L2 fetch granularity %zu: %s\n", gran, cudaGetErrorString(e)); }
+            size_t got = 0; cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity); printf("L2 fetch granularity now %zu\n", got);
+            for (int per_sm = 2; per_sm <= 3; ++per_sm)
+                for (int pl : {1, 2, 4})
+                    for (int dist : {296, 592, 1184}) {
+                        const size_t smem = (size_t)(216 * 1024 / per_sm) - 2048;
+                        snprintf(name, sizeof name, "H prefetch by LDGSTS.32 x%d/line dist %4d, CTAs/SM <= %d", pl, dist, per_sm);
+                        float ms = pl == 1 ? time_it([&] { k_one_pfld<1><<<(unsigned)n_tiles, 256, smem>>>(a, sh.seg_bits, sh.hi_start, n_tiles, dist, 1.0); })
+                                 : pl == 2 ? time_it([&] { k_one_pfld<2><<<(unsigned)n_tiles, 256, smem>>>(a, sh.seg_bits, sh.hi_start, n_tiles, dist, 1.0); })
+                                           : time_it([&] { k_one_pfld<4><<<(unsigned)n_tiles, 256, smem>>>(a, sh.seg_bits, sh.hi_start, n_tiles, dist, 1.0); });
+                        report(name, ms, bytes);
+                    }
+            snprintf(name, sizeof name, "A (no prefetch) CTAs/SM <= 2, granularity %zu", got);
+            report(name, time_it([&] { k_one<1><<<(unsigned)n_tiles, 256, (size_t)(216 * 1024 / 2) - 2048>>>(a, sh.seg_bits, sh.hi_start, 1.0); }), bytes);
         }
         report("B pair of adjacent tiles, sequential", time_it([&] { k_pair_seq<<<(unsigned)(n_tiles / 2), 256>>>(a, sh.seg_bits, sh.hi_start, 1.0); }), bytes);
         report("C pair of adjacent tiles, joint (512 thr)", time_it([&] { k_pair_joint<<<(unsigned)(n_tiles / 2), 512>>>(a, sh.seg_bits, sh.hi_start, 1.0); }), bytes);

@@ -60,12 +60,16 @@ def emu():
         L.emu_run_sparse.restype = ctypes.c_int
         L.emu_error.restype = ctypes.c_char_p
         L.emu_max_bank_conflict.restype = ctypes.c_int
+        L.emu_set_fused.argtypes = [ctypes.c_int]
         _emu = L
     return _emu
 
 
-def emu_run(oracle_circ: OracleCircuit, world: int = 1, state=None, fuse: bool = True, track_support: bool = False):
+def emu_run(oracle_circ: OracleCircuit, world: int = 1, state=None, fuse: bool = True, track_support: bool = False,
+            fused_remap: bool = True):
     """Run the recorded gates of `oracle_circ` through the CPU replay of the CUDA path.
+    fused_remap: global<->local swaps ride on the next pass's load (the engine's default when both chunks fit), else
+    every swap is an exchange of its own (in-place peer swap / staged NCCL path).
     track_support: replay the engine's support tracking after a reset -- only amplitude 0 of every rank's chunk is
     stored, the rest of the buffer is NaN (never-written memory) and must never be read."""
     n = oracle_circ.num_qubits
@@ -84,6 +88,7 @@ def emu_run(oracle_circ: OracleCircuit, world: int = 1, state=None, fuse: bool =
         state[0] = 1.0
     stats = (ctypes.c_int64 * 4)()
     run = emu().emu_run_sparse if track_support else emu().emu_run
+    emu().emu_set_fused(int(fused_remap))
     rc = run(n, world, arr, ng, int(fuse), state.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stats)
     if rc != 0:
         raise RuntimeError(emu().emu_error().decode())

@@ -21,6 +21,13 @@ def _check(circ: OracleCircuit, world=1):
     assert rel_err(got_raw, circ.amplitudes()) < TOL
     assert not np.isnan(got_sp.view(np.float64)).any()
     assert rel_err(got_sp, circ.amplitudes()) < TOL
+    if world > 1:
+        # the same plan with every global<->local swap as an exchange of its own (the fallback when the second
+        # chunk does not fit): the default above lets the swaps ride on the next pass's load
+        got_x, stats_x = emu_run(circ, world, fused_remap=False)
+        got_xs, _ = emu_run(circ, world, track_support=True, fused_remap=False)
+        assert rel_err(got_x, circ.amplitudes()) < TOL and rel_err(got_xs, circ.amplitudes()) < TOL
+        assert stats_x["swaps"] == stats["swaps"]
     return stats
 
 
@@ -93,6 +100,38 @@ def test_distributed_replay(world, n):
     assert stats["swaps"] >= 1          # gates on rank-index qubits force exchanges
     circ = OracleCircuit(n); circuits.qft_like(circ, n); _check(circ, world)
     circ = OracleCircuit(n); circuits.hea(circ, n, 3); _check(circ, world)
+
+
+def test_distributed_planner_with_fewer_local_than_rank_index_qubits():
+    """More rank-index qubits wanted in one round than there are local positions to evict (n_local < log2(world)):
+    the planner must bring them in over several rounds instead of evicting position -1."""
+    import ctypes
+    from damavand_b200 import _lib
+    from tests.helpers import gate_array
+    L = _lib.load()
+    for n, n_local in ((3, 1), (5, 2), (4, 1), (6, 3)):
+        c = OracleCircuit(n)
+        for q in range(n_local, n):
+            c.add_hadamard_gate(q)
+        for q in range(n - 1):
+            c.add_cnot_gate(q, q + 1)
+        arr, ng = gate_array(c)
+        perm = (ctypes.c_int32 * n)(*range(n))
+        out = (ctypes.c_int32 * 4096)()
+        k = L.dvd_plan_distributed_debug(n, n_local, arr, ng, perm, 1, out, 4096)
+        assert k > 0, L.dvd_last_error()
+        assert list(perm) == list(range(n))
+        pos, n_steps = 1, out[0]
+        for _ in range(n_steps):
+            kind, a, b, cnt = out[pos], out[pos + 1], out[pos + 2], out[pos + 3]
+            pos += 4
+            if kind == 1:
+                assert n_local <= a < n and 0 <= b < n_local, (n, n_local, a, b)
+            for _g in range(cnt):
+                assert 0 <= out[pos + 1] < n and -1 <= out[pos + 2] < n
+                pos += 3
+        # and the replay of that plan on 2^(n - n_local) ranks reproduces the oracle (one-gate kernel path)
+        _check(c, 1 << (n - n_local))
 
 
 def test_distributed_small_chunks_use_simple_kernel():
