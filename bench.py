@@ -382,9 +382,13 @@ def measure(circ, n_gates, args, ranks: Ranks, jit: int, device: int, sample_clo
         one_step(); circ.forward_async(); circ.synchronize(); circ.jit_wait()
         # ... and the kernel form of every pass structure is chosen by timing its candidates on dense launches
         # (csrc/jit_rt.cpp): keep warming up until nothing is being measured any more
+        last, idle = None, 0
         for _ in range(12):
             one_step(); circ.forward_async(); circ.synchronize()
-            if circ.jit_info()["tuning"] == 0:
+            left = circ.jit_info()["tuning"]
+            idle = idle + 1 if left == last else 0
+            last = left
+            if left == 0 or idle >= 2:       # (structures of another circuit of this process may stay half-measured)
                 break
     ranks.barrier(circ)
     circ.stats_reset()

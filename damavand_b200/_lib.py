@@ -78,10 +78,12 @@ SIGNATURES = {
     "dvd_load_state": (ctypes.c_int, [_VP, _DP, _DP, ctypes.c_int64, ctypes.c_int64]),
     "dvd_fidelity": (ctypes.c_int, [_VP, _VP, _DP]),
     "dvd_copy_state": (ctypes.c_int, [_VP, _VP]),
+    "dvd_snapshot": (ctypes.c_int, [_VP, ctypes.POINTER(_VP)]),
     "dvd_num_qubits": (ctypes.c_int, [_VP]),
     "dvd_num_local_qubits": (ctypes.c_int, [_VP]),
     "dvd_rank": (ctypes.c_int, [_VP]),
     "dvd_world": (ctypes.c_int, [_VP]),
+    "dvd_device": (ctypes.c_int, [_VP]),
     "dvd_get_stats": (ctypes.c_int, [_VP, ctypes.POINTER(Stats)]),
     "dvd_stats_reset": (ctypes.c_int, [_VP]),
     "dvd_timer_begin": (ctypes.c_int, [_VP]),

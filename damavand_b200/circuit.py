@@ -33,7 +33,14 @@ def _dp(a: np.ndarray):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
 
-class _Profiler:  # src/profiler.rs:11-43
+class _Profiler:
+    """src/profiler.rs:11-43: iterations + cumulated elapsed nanoseconds, mean = cumulated / iterations.  The reference
+    brackets host code with Instant::now(); here the buckets are fed with DEVICE time where the work is on the device:
+    Forward = CUDA events on the engine's stream around the fused passes of one forward(), InterGPUCommunication = CUDA
+    events around the passes whose load carries a global<->local qubit swap over NVLink (plus any stand-alone exchange)
+    of that forward (csrc/engine.cu: remap_ms / swap_ms), Sampling = wall clock of sample() (host buffers in and out).
+    InterNodeCommunication stays empty: one node (the reference feeds it from its MPI exchange, circuit_distributed_gpu.rs:109-115)."""
+
     def __init__(self):
         self.iterations = 0
         self.cumulated = 0.0
@@ -44,6 +51,10 @@ class _Profiler:  # src/profiler.rs:11-43
 
     def stop(self):
         self.cumulated += time.perf_counter_ns() - self._t0
+        self.iterations += 1
+
+    def add_ms(self, ms: float):
+        self.cumulated += ms * 1e6
         self.iterations += 1
 
     def mean(self):
@@ -89,6 +100,7 @@ class Circuit:
                 _lib.check(self._lib.dvd_create_distributed(self.num_qubits, device, self.rank, self.num_nodes,
                                                             idbuf, ctypes.byref(self._handle)),
                            "dvd_create_distributed")
+        self.device = device
         self.num_amplitudes_per_node = (1 << self.num_qubits) // self.num_nodes   # circuit.rs:135-136
         self.num_gpus_per_node = 1
         self.num_amplitudes_per_gpu = self.num_amplitudes_per_node
@@ -163,6 +175,18 @@ class Circuit:
     def add_t_gate(self, active_qubit: int):
         self.gates.append(["T", self._check_qubit(active_qubit), None, None])
 
+    # the FFI carries an arbitrary 2x2 and a control (circuit_gpu.rs:31-60); the reference's add_* set never exposes it
+    def add_unitary_gate(self, active_qubit: int, matrix):
+        """Arbitrary 2x2 (row-major, complex) on one qubit."""
+        self.gates.append(["Unitary", self._check_qubit(active_qubit), None, None, gates.from_2x2(matrix)])
+
+    def add_controlled_gate(self, control_qubit: int, target_qubit: int, matrix):
+        """Arbitrary 2x2 on `target_qubit`, applied where `control_qubit` is 1 (the rule of circuit_multithreading.rs:36-38)."""
+        c, t = self._check_qubit(control_qubit), self._check_qubit(target_qubit)
+        if c == t:
+            raise ValueError("control and target must differ")
+        self.gates.append(["Unitary", t, c, None, gates.from_2x2(matrix)])
+
     def print_operations(self):  # circuit.rs:693-698 prints `operations`, which nothing ever fills
         pass
 
@@ -172,25 +196,33 @@ class Circuit:
         todo = [g for i, g in enumerate(self.gates) if i not in obs]     # :347-349
         # `gates` / `observables` are public lists (the reference's fields): the marshalled array is reused only
         # while their contents are unchanged
-        key = tuple(tuple(g) for g in todo)
+        key = tuple(tuple(tuple(x) if isinstance(x, list) else x for x in g) for g in todo)
         if self._gate_cache is not None and self._gate_cache[0] == key:
             return self._gate_cache[1], len(todo)
         arr = (_lib.Gate * max(1, len(todo)))()
-        for k, (name, t, c, p) in enumerate(todo):
+        for k, g in enumerate(todo):
+            name, t, c, p = g[:4]
             arr[k].target = t
             arr[k].control = -1 if c is None else c
-            arr[k].m[:] = gates.matrix(name, p)
+            arr[k].m[:] = gates.matrix(name, p, g[4] if len(g) > 4 else None)
         self._gate_cache = (key, arr)
         return arr, len(todo)
 
     def forward(self):
         """Apply every non-observable gate, in order, to the current state (no implicit reset)."""
-        self._profilers["forward"].start()
         arr, n = self._gate_array()
+        before = self.stats() if self.num_nodes > 1 else None
+        _lib.check(self._lib.dvd_timer_begin(self._handle), "dvd_timer_begin")
         _lib.check(self._lib.dvd_apply_circuit(self._handle, arr, n), "dvd_apply_circuit")
         _lib.check(self._lib.dvd_flush(self._handle), "dvd_flush")
+        ms = ctypes.c_double()
+        _lib.check(self._lib.dvd_timer_end(self._handle, ctypes.byref(ms)), "dvd_timer_end")   # records + waits for the stream
         _lib.check(self._lib.dvd_synchronize(self._handle), "dvd_synchronize")
-        self._profilers["forward"].stop()
+        self._profilers["forward"].add_ms(ms.value)
+        if before is not None:
+            after = self.stats()
+            if after["global_swaps"] > before["global_swaps"]:
+                self._profilers["inter_gpu"].add_ms((after["remap_ms"] + after["swap_ms"]) - (before["remap_ms"] + before["swap_ms"]))
 
     def forward_async(self):
         """forward() without the final device synchronisation (used by the bench harness)."""
@@ -286,15 +318,13 @@ class Circuit:
         return out
 
     def get_fidelity_between_two_states_with_parameters(self, parameters_1, parameters_2) -> float:
-        """circuit.rs:753-769 + circuit_metrics.rs:12-33: |<psi(p1)|psi(p2)>|^2, then reset()."""
+        """circuit.rs:753-769 + circuit_metrics.rs:12-92: |<psi(p1)|psi(p2)>|^2, then reset().  The first state stays on
+        the device as a snapshot (same device / rank / communicator); on distributed states the partial dots are
+        allreduced over the ranks (the reference's distributed_dot gathers them on the root and broadcasts)."""
         other = ctypes.c_void_p()
         self.reset_amplitudes(); self.set_parameters(parameters_1); self.forward()
-        if self.num_nodes == 1:
-            _lib.check(self._lib.dvd_create(self.num_qubits, 0, ctypes.byref(other)), "dvd_create")
-        else:
-            raise NotImplementedError("fidelity on distributed states needs a second communicator (next round)")
+        _lib.check(self._lib.dvd_snapshot(self._handle, ctypes.byref(other)), "dvd_snapshot")
         try:
-            _lib.check(self._lib.dvd_copy_state(other, self._handle), "dvd_copy_state")
             self.reset_amplitudes(); self.set_parameters(parameters_2); self.forward()
             out = ctypes.c_double()
             _lib.check(self._lib.dvd_fidelity(other, self._handle, ctypes.byref(out)), "dvd_fidelity")

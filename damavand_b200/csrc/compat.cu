@@ -54,7 +54,15 @@ void init_quantum_state(int num_amplitudes_per_gpu, int num_gpus_per_node_requir
     while ((1ll << n_local) < (long long)num_amplitudes_per_gpu) ++n_local;
     int g = 0;
     while ((1 << g) < g_world) ++g;
-    if (g_state) { dvd_destroy(g_state); g_state = nullptr; }   // the reference leaks here
+    // The reference calls init_quantum_state from every reset_amplitudes() (circuit.rs:271-301): the same shape again is
+    // a reset of the state that already exists (no re-allocation, and above all no second ncclCommInitRank with an id
+    // that has been consumed); a different shape replaces it (the reference leaks here).
+    if (g_state && dvd_num_qubits(g_state) == n_local + g && dvd_rank(g_state) == g_rank && dvd_world(g_state) == g_world &&
+        dvd_device(g_state) == g_device) {
+        check(dvd_reset_zero_state(g_state), "init_quantum_state");
+        return;
+    }
+    if (g_state) { dvd_destroy(g_state); g_state = nullptr; }
     if (g_world > 1) check(dvd_create_distributed(n_local + g, g_device, g_rank, g_world, g_have_id ? g_id : nullptr, &g_state), "init_quantum_state");
     else check(dvd_create(n_local, g_device, &g_state), "init_quantum_state");
 }

@@ -66,6 +66,7 @@ struct dvd_state {
     double* d_tree = nullptr; bool tree_valid = false;
     double* d_scratch = nullptr; size_t scratch_doubles = 0;
     ncclComm_t comm = nullptr;
+    bool comm_borrowed = false;   // a snapshot (dvd_snapshot) uses its source's communicator and must not destroy it
     cplx* swap_buf[4] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t swap_chunk = 0;
     // direct peer path: every other rank's state allocation mapped with CUDA IPC; d_bar backs the stream barriers
@@ -327,7 +328,7 @@ int dvd_destroy(dvd_state* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
-    if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+    if (s->comm && !s->comm_borrowed && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     for (auto& p : s->peer_base) if (p) cudaIpcCloseMemHandle(p);
     if (s->buf[0]) cudaFree(s->buf[0]);
     for (auto& t : s->remap_timers) { if (t.t0) cudaEventDestroy(t.t0); if (t.t1) cudaEventDestroy(t.t1); }
@@ -899,6 +900,52 @@ int dvd_fidelity(dvd_state* a, dvd_state* b, double* out) {
     return DVD_OK;
 }
 
+// A second resident state holding a copy of src's amplitudes: same shape, device and rank, and -- for distributed
+// states -- src's communicator (borrowed: the snapshot must be destroyed before src).  This is what
+// get_fidelity_between_two_states_with_parameters needs for its first state (circuit.rs:753-769 keeps the first
+// state's amplitudes on the host; circuit_metrics.rs:35-92 distributed_dot reduces the partial dots over the ranks).
+int dvd_snapshot(dvd_state* src, dvd_state** out) {
+    if (!src || !out) return fail(DVD_ERR_ARG, "null argument");
+    *out = nullptr;
+    TRY(sync_state(src));
+    CU(cudaSetDevice(src->device));
+    dvd_state* s = new dvd_state();
+    std::memset(&s->stats, 0, sizeof(s->stats));
+    s->n_qubits = src->n_qubits; s->n_local = src->n_local; s->rank = src->rank; s->world = src->world; s->device = src->device;
+    s->n_amps = src->n_amps; s->rank_bits = src->rank_bits;
+    s->opt = src->opt; s->lazy_zero = src->lazy_zero; s->plan_cache = src->plan_cache;
+    s->jit_mode = src->jit_mode; s->jit_min_qubits = src->jit_min_qubits;
+    s->perm.resize(s->n_qubits);
+    for (int q = 0; q < s->n_qubits; ++q) s->perm[q] = q;
+    s->comm = src->comm; s->comm_borrowed = true;
+    auto cleanup = [&](int code) { dvd_destroy(s); return code; };
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&s->ev_t0) != cudaSuccess || cudaEventCreate(&s->ev_t1) != cudaSuccess)
+        return cleanup(fail(DVD_ERR_CUDA, "stream/event creation failed"));
+    for (int i = 0; i < 2; ++i)
+        if (cudaEventCreateWithFlags(&s->ev_pack[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->ev_comm[i], cudaEventDisableTiming) != cudaSuccess)
+            return cleanup(fail(DVD_ERR_CUDA, "event creation failed"));
+    cudaError_t e = cudaMalloc(&s->buf[0], s->n_amps * sizeof(cplx));
+    if (e != cudaSuccess) return cleanup(fail(DVD_ERR_CUDA, std::string("cudaMalloc(snapshot): ") + cudaGetErrorString(e)));
+    s->amp = s->buf[0];
+    e = cudaMalloc(&s->d_tree, tree_size(s->n_local) * sizeof(double));
+    if (e != cudaSuccess) return cleanup(fail(DVD_ERR_CUDA, std::string("cudaMalloc(tree): ") + cudaGetErrorString(e)));
+    if (s->world > 1) {
+        e = cudaMalloc(&s->d_bar, 4 * sizeof(double));
+        if (e != cudaSuccess) return cleanup(fail(DVD_ERR_CUDA, std::string("cudaMalloc(barrier): ") + cudaGetErrorString(e)));
+        cudaMemsetAsync(s->d_bar, 0, 4 * sizeof(double), s->stream);
+    }
+    CU(cudaStreamSynchronize(src->stream));
+    e = cudaMemcpyAsync(s->amp, src->amp, s->n_amps * sizeof(cplx), cudaMemcpyDeviceToDevice, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) return cleanup(fail(DVD_ERR_CUDA, std::string("snapshot copy: ") + cudaGetErrorString(e)));
+    s->support = ~0ull;
+    *out = s;
+    return DVD_OK;
+}
+
 int dvd_copy_state(dvd_state* dst, dvd_state* src) {
     if (!dst || !src) return fail(DVD_ERR_ARG, "null argument");
     if (dst->n_qubits != src->n_qubits || dst->world != src->world || dst->device != src->device)
@@ -916,6 +963,7 @@ int dvd_num_qubits(const dvd_state* s) { return s ? s->n_qubits : -1; }
 int dvd_num_local_qubits(const dvd_state* s) { return s ? s->n_local : -1; }
 int dvd_rank(const dvd_state* s) { return s ? s->rank : -1; }
 int dvd_world(const dvd_state* s) { return s ? s->world : -1; }
+int dvd_device(const dvd_state* s) { return s ? s->device : -1; }
 
 int dvd_get_stats(const dvd_state* cs, dvd_stats* out) {
     if (!cs || !out) return fail(DVD_ERR_ARG, "null argument");

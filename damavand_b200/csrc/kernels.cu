@@ -339,35 +339,42 @@ k_extract_expectation(const unsigned long long* __restrict__ samples, uint64_t s
 // =================================================================================================
 constexpr int EZ_CTAS = 148 * 4;
 constexpr int EZ_Q = 64;
+constexpr int EZ_LOW = 8;          // bits [0, EZ_LOW) of an index are fixed per thread (grid stride is a multiple of 256)
+constexpr int EZ_HIGH = 32;        // accumulators for bits [EZ_LOW, EZ_LOW + EZ_HIGH): local qubits up to 40
 uint64_t ez_partial_size() { return (uint64_t)EZ_CTAS * EZ_Q; }
 
+// partial[cta][q] = sum over the CTA's amplitudes of p_i * (1 - 2 bit_q(i)) for q < 40, partial[cta][63] = sum p_i.
+// The grid-stride loop advances by a multiple of 256, so bits 0..7 of every index a thread visits equal its thread
+// index: those eight sums are +-(the thread's total) and need no accumulator of their own.
 __global__ void __launch_bounds__(256)
 k_expect_z_partial(const cplx* __restrict__ amp, int n_local, double* __restrict__ partial) {
-    __shared__ double red[8][33];
-    double acc[33];
+    __shared__ double red[8][EZ_LOW + EZ_HIGH + 1];
+    double acc[EZ_HIGH];
+    double tot = 0.0;
 #pragma unroll
-    for (int q = 0; q < 33; ++q) acc[q] = 0.0;
+    for (int q = 0; q < EZ_HIGH; ++q) acc[q] = 0.0;
     const uint64_t n = 1ull << n_local;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double p = norm_sqr(amp[i]);
-        acc[32] += p;
+        tot += p;
+        const uint64_t hi = i >> EZ_LOW;
 #pragma unroll
-        for (int q = 0; q < 32; ++q) acc[q] += ((i >> q) & 1ull) ? -p : p;
+        for (int q = 0; q < EZ_HIGH; ++q) acc[q] += ((hi >> q) & 1ull) ? -p : p;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int q = 0; q < 33; ++q) {
-        double v = acc[q];
+    for (int q = 0; q < EZ_LOW + EZ_HIGH + 1; ++q) {
+        double v = q < EZ_LOW ? (((threadIdx.x >> q) & 1) ? -tot : tot) : q < EZ_LOW + EZ_HIGH ? acc[q < EZ_LOW ? 0 : q - EZ_LOW] : tot;
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         if (lane == 0) red[warp][q] = v;
     }
     __syncthreads();
-    if (threadIdx.x < 33) {
+    if (threadIdx.x < EZ_LOW + EZ_HIGH + 1) {
         double v = 0.0;
         for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
-        partial[(uint64_t)blockIdx.x * EZ_Q + threadIdx.x] = v;
+        partial[(uint64_t)blockIdx.x * EZ_Q + (threadIdx.x == EZ_LOW + EZ_HIGH ? EZ_Q - 1 : threadIdx.x)] = v;
     }
 }
 
@@ -375,7 +382,7 @@ __global__ void k_expect_z_final(const double* __restrict__ partial, int n_ctas,
                                  uint64_t rank_bits, double* __restrict__ out) {
     const int q = threadIdx.x;
     if (q >= n_total) return;
-    const int src = q < n_local ? q : 32;
+    const int src = q < n_local ? q : EZ_Q - 1;     // rank-index qubits: +-(the chunk's total probability)
     double v = 0.0;
     for (int c = 0; c < n_ctas; ++c) v += partial[(uint64_t)c * EZ_Q + src];
     if (q >= n_local && ((rank_bits >> q) & 1ull)) v = -v;

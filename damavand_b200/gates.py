@@ -64,5 +64,18 @@ _BUILDERS = {
 }
 
 
-def matrix(name: str, parameter=None):
+def from_2x2(m):
+    """Row-major 2x2 of complex numbers (nested or flat, anything numpy-like) -> the 8 doubles of the C ABI."""
+    flat = [complex(z) for row in m for z in (row if hasattr(row, "__len__") else [row])]
+    if len(flat) != 4:
+        raise ValueError("expected a 2x2 matrix")
+    out = []
+    for z in flat:
+        out += [float(z.real), float(z.imag)]
+    return out
+
+
+def matrix(name: str, parameter=None, custom=None):
+    if name == "Unitary":      # caller-supplied 2x2 (add_unitary_gate / add_controlled_gate)
+        return list(custom)
     return _BUILDERS[name](parameter)

@@ -107,12 +107,17 @@ int dvd_load_state(dvd_state* s, const double* re, const double* im, int64_t fir
 int dvd_fidelity(dvd_state* a, dvd_state* b, double* out);
 /* copy src's amplitudes into dst (same shape) */
 int dvd_copy_state(dvd_state* dst, dvd_state* src);
+/* a second resident state with a copy of src's amplitudes (same shape, device, rank; distributed: src's communicator,
+ * so destroy the snapshot before src).  First operand of dvd_fidelity in circuit.rs:753-769 /
+ * circuit_metrics.rs:35-92 (distributed_dot). */
+int dvd_snapshot(dvd_state* src, dvd_state** out);
 
 /* ---- introspection --------------------------------------------------------------------------- */
 int dvd_num_qubits(const dvd_state* s);
 int dvd_num_local_qubits(const dvd_state* s);
 int dvd_rank(const dvd_state* s);
 int dvd_world(const dvd_state* s);
+int dvd_device(const dvd_state* s);
 
 typedef struct {
     int64_t gates_applied;        /* gates executed since creation / dvd_stats_reset */

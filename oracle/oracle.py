@@ -121,13 +121,15 @@ def mat_t():  # gates.rs:684-703
 
 
 class _Gate:
-    __slots__ = ("name", "target", "control", "parameter")
+    __slots__ = ("name", "target", "control", "parameter", "custom")
 
-    def __init__(self, name, target, control=None, parameter=None):
-        self.name, self.target, self.control, self.parameter = name, target, control, parameter
+    def __init__(self, name, target, control=None, parameter=None, custom=None):
+        self.name, self.target, self.control, self.parameter, self.custom = name, target, control, parameter, custom
 
     def matrix(self):
         n = self.name
+        if n == "Unitary":      # caller-supplied 2x2, row-major (the product's add_unitary_gate / add_controlled_gate)
+            return list(self.custom)
         if n == "Hadamard":
             return mat_hadamard()
         if n in ("PauliX", "CNOT"):
@@ -162,8 +164,8 @@ def _flat(m):
 # --------------------------------------------------------------------------------------------
 def brute_force_operator(num_qubits: int, gate: _Gate) -> np.ndarray:
     I2 = np.eye(2, dtype=np.complex128)
-    if gate.name != "CNOT":
-        m = np.array(gate.matrix(), dtype=np.complex128).reshape(2, 2)
+    m = np.array(gate.matrix(), dtype=np.complex128).reshape(2, 2)
+    if gate.control is None:
         if num_qubits == 1:
             return m
         mats = [m if q == gate.target else I2 for q in reversed(range(num_qubits))]
@@ -173,7 +175,7 @@ def brute_force_operator(num_qubits: int, gate: _Gate) -> np.ndarray:
         return op
     p0 = np.array([[1, 0], [0, 0]], dtype=np.complex128)
     p1 = np.array([[0, 0], [0, 1]], dtype=np.complex128)
-    sx = np.array(mat_pauli_x(), dtype=np.complex128).reshape(2, 2)
+    sx = m     # CNOT: the Pauli-X block (utils.rs:230-241); a general controlled gate puts its own 2x2 there (extension)
     inactive, active = [], []
     for q in reversed(range(num_qubits)):  # utils.rs:230-241
         if q == gate.control:
@@ -315,6 +317,12 @@ class OracleCircuit:
 
     # gates.rs defines S (:617-641) and T (:675-703) but circuit.rs has no add_ method for them; the product offers
     # add_s_gate / add_t_gate as extensions and the oracle mirrors that with the reference's matrices
+    def add_unitary_gate(self, q, matrix):
+        self.gates.append(_Gate("Unitary", q, custom=[complex(z) for row in matrix for z in row]))
+
+    def add_controlled_gate(self, control, target, matrix):   # update rule unchanged: circuit_multithreading.rs:36-38
+        self.gates.append(_Gate("Unitary", target, control=control, custom=[complex(z) for row in matrix for z in row]))
+
     def add_s_gate(self, q):
         self.gates.append(_Gate("S", q))
 

@@ -27,8 +27,11 @@ def main():
     cases = []
     for n in (int(x) for x in os.environ.get("DIST_CHECK_N", "14,17,21,24").split(",")):
         cases += [(n, "random", 300), (n, "qft", 0), (n, "hea", 4), (n, "layered", 3)]
+    jit = int(os.environ.get("DIST_CHECK_JIT", "0"))
     for n, kind, arg in cases:
         g = Circuit(n, "distributed_gpu")
+        if jit:
+            g.set_jit(2)          # run-time specialised kernels, compiled on first use
         o = OracleCircuit(n)
         for c in (g, o):
             if kind == "random":
@@ -47,6 +50,7 @@ def main():
         want = o.amplitudes()[rank * chunk:(rank + 1) * chunk]
         got = g.state_numpy()
         err = float(np.abs(got - want).max() / np.abs(o.amplitudes()).max())
+        l2 = float(np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-300))
         p = o.measure_np()
         idx = np.arange(p.size)
         ez_want = np.array([(p * (1 - 2.0 * ((idx >> q) & 1))).sum() for q in range(n)])
@@ -60,13 +64,19 @@ def main():
         s_ok = bool((s == s_want).all())
         ev_ok = g.extract_expectation_values(s[:50].tolist()) == o.extract_expectation_values(s[:50].tolist())
         st = g.stats()
-        ok = err < 1e-12 and ez_err < 1e-12 and norm_err < 1e-12 and s_ok and ev_ok
+        # a second forward starts from a dense state in the layout the first one restored
+        g.forward(); o.forward()
+        got2 = g.state_numpy()
+        err2 = float(np.abs(got2 - o.amplitudes()[rank * chunk:(rank + 1) * chunk]).max() / np.abs(o.amplitudes()).max())
+        st = g.stats()
+        ok = err < 1e-12 and l2 < 1e-12 and err2 < 1e-12 and ez_err < 1e-12 and norm_err < 1e-12 and s_ok and ev_ok
         import torch
         t = torch.tensor([0 if ok else 1], device="cuda")
         dist.all_reduce(t)
         if rank == 0:
-            print(f"n={n} world={world} {kind:8s} err={err:.2e} ez_err={ez_err:.2e} norm_err={norm_err:.1e} "
-                  f"samples_ok={s_ok} ev_ok={ev_ok} swaps={st['global_swaps']} passes={st['tile_passes']} "
+            print(f"n={n} world={world} {kind:8s} err={err:.2e} l2={l2:.2e} err_2nd_forward={err2:.2e} ez_err={ez_err:.2e} norm_err={norm_err:.1e} "
+                  f"samples_ok={s_ok} ev_ok={ev_ok} swaps={st['global_swaps']} fused_remap_passes={st['remap_passes']} "
+                  f"jit_launches={st['jit_launches']} passes={st['tile_passes']} "
                   f"simple={st['simple_passes']} all_ranks_ok={int(t.item()) == 0}", flush=True)
         fails += int(t.item())
         g.close()

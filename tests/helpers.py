@@ -41,7 +41,7 @@ def gate_array(circ):
     for k, g in enumerate(todo):
         arr[k].target = g.target
         arr[k].control = -1 if g.control is None else g.control
-        arr[k].m[:] = pgates.matrix(g.name, g.parameter)
+        arr[k].m[:] = pgates.matrix(g.name, g.parameter, None if g.custom is None else pgates.from_2x2([g.custom[:2], g.custom[2:]]))
     return arr, len(todo)
 
 

@@ -185,3 +185,26 @@ def test_oracle_regression_fixtures(kind):
     assert s == c.sample(64, uniforms=fx[f"{kind}_uniforms"], mode="tree")
     assert (np.asarray(c.extract_expectation_values(s)) == fx[f"{kind}_expectation"]).all()
     assert abs(np.linalg.norm(fx[f"{kind}_amplitudes"]) - 1.0) < 1e-13
+
+
+def test_unitary_and_controlled_gates_match_brute_force():
+    """The oracle's add_unitary_gate / add_controlled_gate (arbitrary 2x2 through the reference's update rule,
+    circuit_multithreading.rs:9-54) against the brute_force restatement (full Kronecker operator)."""
+    rng = np.random.default_rng(5)
+    n = 6
+    a, b = OracleCircuit(n, "multithreading"), OracleCircuit(n, "brute_force")
+    for c in (a, b):
+        r = np.random.default_rng(5)
+        for q in range(n):
+            c.add_hadamard_gate(q)
+        for k in range(30):
+            t = int(r.integers(0, n)); ctl = int(r.integers(0, n - 1)); ctl += ctl >= t
+            z = r.normal(size=(2, 2)) + 1j * r.normal(size=(2, 2))
+            u, _ = np.linalg.qr(z)
+            if k % 2:
+                c.add_controlled_gate(ctl, t, u.tolist())
+            else:
+                c.add_unitary_gate(t, u.tolist())
+        c.forward()
+    assert np.abs(a.amplitudes() - b.amplitudes()).max() < 1e-13
+    assert abs(np.linalg.norm(a.amplitudes()) - 1.0) < 1e-12
