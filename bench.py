@@ -483,10 +483,10 @@ def roofline_of(m, name, n_local, n_gates, gpus):
 
 def cfg5_point(args, ranks: Ranks, jit: int):
     """BASELINE config 5 on 8 ranks: 34-qubit ansatz (10 layers), forward from a reset, 10^5-shot distributed sample,
-    expectation values; parity flag from a 24-qubit twin of the same circuit against the oracle."""
+    expectation values; parity flag from a 22-qubit twin of the same circuit against the oracle."""
     from damavand_b200 import Circuit, circuits
     out = {"workload": workload_desc("hea34"), "n_gpus": ranks.gpus}
-    twin = parity_check(ranks, jit, cases=[(24, "hea", 10)])
+    twin = parity_check(ranks, jit, cases=[(22, "hea", 10)])
     out["parity_twin"] = {k: twin[k] for k in ("ok", "max_rel_err", "l2_rel_err", "samples_ok", "n")}
     n = 34
     c = Circuit(n, "distributed_gpu")

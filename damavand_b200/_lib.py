@@ -72,6 +72,7 @@ SIGNATURES = {
     "dvd_probabilities": (ctypes.c_int, [_VP, _DP, ctypes.c_int64, ctypes.c_int64]),
     "dvd_norm": (ctypes.c_int, [_VP, _DP]),
     "dvd_sample": (ctypes.c_int, [_VP, _DP, ctypes.c_int64, _U64P]),
+    "dvd_set_sampler": (ctypes.c_int, [_VP, ctypes.c_int]),
     "dvd_extract_expectation_values": (ctypes.c_int, [_VP, _U64P, ctypes.c_int64, _I32P, ctypes.c_int32, _DP]),
     "dvd_expectation_z": (ctypes.c_int, [_VP, _DP]),
     "dvd_read_state": (ctypes.c_int, [_VP, _DP, _DP, ctypes.c_int64, ctypes.c_int64]),

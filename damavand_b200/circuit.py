@@ -243,6 +243,13 @@ class Circuit:
         _lib.check(self._lib.dvd_read_state(self._handle, _dp(re), _dp(im), 0, n), "dvd_read_state")
         return re + 1j * im
 
+    def load_state_numpy(self, amplitudes, first: int = 0):
+        """Overwrite local amplitudes [first, first + len) with a complex array (the reference's TODO'd
+        load_amplitudes_local_on_device, rust_communication.cu:384-398, done properly)."""
+        a = np.asarray(amplitudes, dtype=np.complex128)
+        re = np.ascontiguousarray(a.real); im = np.ascontiguousarray(a.imag)
+        _lib.check(self._lib.dvd_load_state(self._handle, _dp(re), _dp(im), int(first), a.shape[0]), "dvd_load_state")
+
     def retrieve_amplitudes_on_host(self):  # circuit.rs:380-405
         self._host_state = self.state_numpy()
 
@@ -265,6 +272,14 @@ class Circuit:
         out = ctypes.c_double()
         _lib.check(self._lib.dvd_norm(self._handle, ctypes.byref(out)), "dvd_norm")
         return out.value
+
+    def set_sampler(self, order: str):
+        """'tree' (default: pairwise summation tree, any size) or 'sequential' (the reference's strict left-to-right
+        cumulative sums, utils.rs:270-274: the reference's indices for every draw; at most 30 local qubits)."""
+        orders = {"tree": 0, "sequential": 1}
+        if order not in orders:
+            raise ValueError(f"sampler order must be one of {sorted(orders)}")
+        _lib.check(self._lib.dvd_set_sampler(self._handle, orders[order]), "dvd_set_sampler")
 
     def sample_numpy(self, num_samples: Optional[int] = None, uniforms=None) -> np.ndarray:
         shots = 1000 if num_samples is None else int(num_samples)          # circuit.rs:439-443

@@ -99,12 +99,19 @@ def workload(name: str):
     """Resolve a workload name: the five BASELINE configs, or `qft<n>`, `hea<n>[x<layers>]`,
     `random<n>[x<gates>]`, `layered<n>[x<layers>]` for other sizes.  Returns (n_qubits, builder)."""
     import re
-    m = re.fullmatch(r"(qft|hea|random|layered)(\d+)(?:x(\d+))?", name)
+    m = re.fullmatch(r"(qft|hea|random|layered|hhi)(\d+)(?:x(\d+))?", name)
     if not m:
         raise KeyError(name)
     kind, n, k = m.group(1), int(m.group(2)), m.group(3)
     if kind == "qft":
         return n, (lambda c: qft_like(c, n))
+    if kind == "hhi":      # one Hadamard on each of the k highest qubits: ONE pass over a high-stride tile, next to no arithmetic
+        top = int(k) if k else 9
+        def build(c):
+            for q in range(n - top, n):
+                c.add_hadamard_gate(q)
+            return top
+        return n, build
     if kind == "hea":
         layers = int(k) if k else (50 if n <= 28 else 10)
         return n, (lambda c: hea(c, n, layers, observables=(n >= 34)))

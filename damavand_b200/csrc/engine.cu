@@ -64,7 +64,12 @@ struct dvd_state {
     TabSet tabs[2];
     uint64_t n_flushes = 0;
     double* d_tree = nullptr; bool tree_valid = false;
+    // reference-order sampler (dvd_set_sampler): sequential cumulative sums at the block boundaries
+    int sampler = DVD_SAMPLER_TREE;
+    double* d_seq_cum = nullptr; bool seq_valid = false;
     double* d_scratch = nullptr; size_t scratch_doubles = 0;
+    double* h_stage = nullptr;                      // pinned staging of dvd_read_state / dvd_load_state (lazily allocated)
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     ncclComm_t comm = nullptr;
     bool comm_borrowed = false;   // a snapshot (dvd_snapshot) uses its source's communicator and must not destroy it
     cplx* swap_buf[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -123,7 +128,7 @@ static int ensure_scratch(dvd_state* s, size_t doubles) {
 // Reset to |0..0>: amplitude 0 lives on the first rank (circuit.rs:168-170, kernels.cu:62-81).  With support
 // tracking only that one amplitude is written (16 B instead of 16 B per amplitude).
 static int set_zero_state(dvd_state* s) {
-    s->tree_valid = false;
+    s->tree_valid = false; s->seq_valid = false;
     if (s->lazy_zero && !s->unfused && s->n_local >= TILE_BITS) {
         s->support = ~(s->n_amps - 1);    // no local qubit touched yet; rank-index bits always count as touched
     } else {
@@ -334,6 +339,9 @@ int dvd_destroy(dvd_state* s) {
     for (auto& t : s->remap_timers) { if (t.t0) cudaEventDestroy(t.t0); if (t.t1) cudaEventDestroy(t.t1); }
     if (s->d_tree) cudaFree(s->d_tree);
     if (s->d_ident_tab) cudaFree(s->d_ident_tab);
+    if (s->d_seq_cum) cudaFree(s->d_seq_cum);
+    if (s->h_stage) cudaFreeHost(s->h_stage);
+    for (auto& e : s->ev_stage) if (e) cudaEventDestroy(e);
     if (s->d_scratch) cudaFree(s->d_scratch);
     for (auto& t : s->tabs) {
         if (t.d) cudaFree(t.d);
@@ -701,7 +709,7 @@ static int flush_impl(dvd_state* s) {
     }
     s->n_flushes++;
     s->pending.clear();
-    s->tree_valid = false;
+    s->tree_valid = false; s->seq_valid = false;
     return DVD_OK;
 }
 
@@ -766,11 +774,38 @@ int dvd_norm(dvd_state* s, double* out) {
     return DVD_OK;
 }
 
+// Reference summation order: one sequential pass over the chunk per state (see k_seq_block_cum).
+static const int SEQ_SAMPLER_MAX_LOCAL = 30;
+static int ensure_seq_cum(dvd_state* s) {
+    TRY(sync_state(s));
+    if (s->seq_valid) return DVD_OK;
+    const int nb = std::min(s->n_local, BLK_BITS);
+    if (!s->d_seq_cum) CU(cudaMalloc(&s->d_seq_cum, (1ull << (s->n_local - nb)) * sizeof(double)));
+    CU(launch_seq_block_cum(s->amp, s->n_local, s->d_seq_cum, s->stream));
+    s->stats.kernel_launches++;
+    s->seq_valid = true;
+    return DVD_OK;
+}
+
+int dvd_set_sampler(dvd_state* s, int order) {
+    if (!s) return fail(DVD_ERR_ARG, "null state");
+    if (order != DVD_SAMPLER_TREE && order != DVD_SAMPLER_SEQUENTIAL) return fail(DVD_ERR_ARG, "sampler order must be 0 (tree) or 1 (sequential)");
+    if (order == DVD_SAMPLER_SEQUENTIAL && s->n_local > SEQ_SAMPLER_MAX_LOCAL)
+        return fail(DVD_ERR_ARG, "the reference-order sampler walks the chunk sequentially: at most 30 local qubits");
+    s->sampler = order;
+    return DVD_OK;
+}
+
 int dvd_sample(dvd_state* s, const double* uniforms, int64_t shots, uint64_t* out) {
     if (!s || ((!uniforms || !out) && shots > 0)) return fail(DVD_ERR_ARG, "null argument");
     if (shots < 0) return fail(DVD_ERR_ARG, "negative shot count");
-    TRY(ensure_tree(s));
+    const bool seq = s->sampler == DVD_SAMPLER_SEQUENTIAL;
+    if (seq) TRY(ensure_seq_cum(s)); else TRY(ensure_tree(s));
     if (shots == 0) return DVD_OK;
+    const int nb_seq = std::min(s->n_local, BLK_BITS);
+    // this chunk's total probability: the root of the pairwise tree, or the last sequential cumulative sum
+    const double* d_total = seq ? s->d_seq_cum + ((1ull << (s->n_local - nb_seq)) - 1)
+                                : s->d_tree + tree_level_offset(s->n_local, s->n_local);
     // scratch layout (in doubles): [u: shots][out: shots (u64)][sel: shots (i32, padded)][totals: world]
     const size_t need = (size_t)shots * 3 + s->world + 8;
     TRY(ensure_scratch(s, need));
@@ -780,13 +815,13 @@ int dvd_sample(dvd_state* s, const double* uniforms, int64_t shots, uint64_t* ou
     double* d_tot = s->d_scratch + 3 * shots;
     if (s->world == 1) {
         CU(cudaMemcpyAsync(d_u, uniforms, shots * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-        CU(launch_sample(s->amp, s->n_local, s->d_tree, d_u, nullptr, 0, 0, shots, d_out, s->stream));
+        if (seq) CU(launch_sample_seq(s->amp, s->n_local, s->d_seq_cum, d_u, nullptr, 0, 0, shots, d_out, s->stream));
+        else CU(launch_sample(s->amp, s->n_local, s->d_tree, d_u, nullptr, 0, 0, shots, d_out, s->stream));
         s->stats.kernel_launches++;
     } else {
         // sample_distributed, circuit_distributed.rs:42-129: per-rank totals -> rank per shot (first
         // draw) -> local index on that rank (second draw) -> index + amps_per_rank * rank.
-        const double* root = s->d_tree + tree_level_offset(s->n_local, s->n_local);
-        NC(g_nccl.AllGather(root, d_tot, 1, ncclDouble, s->comm, s->stream));
+        NC(g_nccl.AllGather(d_total, d_tot, 1, ncclDouble, s->comm, s->stream));
         std::vector<double> tot(s->world);
         CU(cudaMemcpyAsync(tot.data(), d_tot, s->world * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
@@ -802,8 +837,10 @@ int dvd_sample(dvd_state* s, const double* uniforms, int64_t shots, uint64_t* ou
         CU(cudaMemcpyAsync(d_u, uniforms + shots, shots * sizeof(double), cudaMemcpyHostToDevice, s->stream));
         CU(cudaMemcpyAsync(d_sel, sel.data(), shots * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
         CU(cudaMemsetAsync(d_out, 0, shots * sizeof(unsigned long long), s->stream));
-        CU(launch_sample(s->amp, s->n_local, s->d_tree, d_u, d_sel, s->rank, (uint64_t)s->rank * s->n_amps,
-                         shots, d_out, s->stream));
+        if (seq) CU(launch_sample_seq(s->amp, s->n_local, s->d_seq_cum, d_u, d_sel, s->rank, (uint64_t)s->rank * s->n_amps,
+                                      shots, d_out, s->stream));
+        else CU(launch_sample(s->amp, s->n_local, s->d_tree, d_u, d_sel, s->rank, (uint64_t)s->rank * s->n_amps,
+                              shots, d_out, s->stream));
         s->stats.kernel_launches++;
         NC(g_nccl.AllReduce(d_out, d_out, shots, ncclUint64, ncclSum, s->comm, s->stream));
         CU(cudaStreamSynchronize(s->stream));   // sel must outlive the copy
@@ -850,34 +887,86 @@ int dvd_expectation_z(dvd_state* s, double* out) {
     return DVD_OK;
 }
 
+// Pinned staging for dvd_read_state / dvd_load_state: two slots of [re | im], STAGE_AMPS amplitudes each.
+static const uint64_t STAGE_AMPS = 1ull << 22;      // 32 MiB per array and slot
+static int ensure_staging(dvd_state* s) {
+    if (s->h_stage) return DVD_OK;
+    CU(cudaMallocHost(&s->h_stage, 4 * STAGE_AMPS * sizeof(double)));
+    for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&s->ev_stage[i], cudaEventDisableTiming));
+    return DVD_OK;
+}
+
+// retrieve_amplitudes_on_host (rust_communication.cu:450-482 + the interleave loop of circuit.rs:396-401): the split into
+// real and imaginary arrays runs on the device; chunks travel through two pinned slots, so that the copy of chunk k + 1
+// over PCIe overlaps the host's memcpy of chunk k into the caller's (pageable) arrays.
 int dvd_read_state(dvd_state* s, double* re, double* im, int64_t first, int64_t count) {
     if (!s || ((!re || !im) && count > 0)) return fail(DVD_ERR_ARG, "null argument");
     if (first < 0 || count < 0 || (uint64_t)(first + count) > s->n_amps) return fail(DVD_ERR_ARG, "range outside the local chunk");
     TRY(sync_state(s));
-    const uint64_t CH = 1ull << 22;
-    std::vector<cplx> tmp(std::min<uint64_t>(CH, std::max<int64_t>(count, 1)));
-    for (uint64_t done = 0; done < (uint64_t)count; done += CH) {
-        const uint64_t c = std::min<uint64_t>(CH, count - done);
-        CU(cudaMemcpyAsync(tmp.data(), s->amp + first + done, c * sizeof(cplx), cudaMemcpyDeviceToHost, s->stream));
+    if (count == 0) return DVD_OK;
+    const uint64_t CH = STAGE_AMPS, n = (uint64_t)count;
+    if (n <= 4096) {      // a handful of amplitudes: one small copy
+        std::vector<cplx> tmp(n);
+        CU(cudaMemcpyAsync(tmp.data(), s->amp + first, n * sizeof(cplx), cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
-        for (uint64_t i = 0; i < c; ++i) { re[done + i] = tmp[i].x; im[done + i] = tmp[i].y; }
+        for (uint64_t i = 0; i < n; ++i) { re[i] = tmp[i].x; im[i] = tmp[i].y; }
+        return DVD_OK;
+    }
+    TRY(ensure_staging(s));
+    TRY(ensure_scratch(s, 4 * std::min(CH, n)));
+    const uint64_t cap = std::min(CH, n), n_chunks = (n + CH - 1) / CH;
+    auto issue = [&](uint64_t k) -> int {
+        const int slot = (int)(k & 1);
+        const uint64_t off = k * CH, c = std::min(CH, n - off);
+        double* d_re = s->d_scratch + (size_t)slot * 2 * cap;
+        double* h_re = s->h_stage + (size_t)slot * 2 * CH;
+        CU(launch_split_re_im(s->amp + first + off, c, d_re, d_re + cap, s->stream));
+        s->stats.kernel_launches++;
+        CU(cudaMemcpyAsync(h_re, d_re, c * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(h_re + CH, d_re + cap, c * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaEventRecord(s->ev_stage[slot], s->stream));
+        return DVD_OK;
+    };
+    TRY(issue(0));
+    for (uint64_t k = 0; k < n_chunks; ++k) {
+        if (k + 1 < n_chunks) TRY(issue(k + 1));
+        const int slot = (int)(k & 1);
+        const uint64_t off = k * CH, c = std::min(CH, n - off);
+        CU(cudaEventSynchronize(s->ev_stage[slot]));
+        const double* h_re = s->h_stage + (size_t)slot * 2 * CH;
+        std::memcpy(re + off, h_re, c * sizeof(double));
+        std::memcpy(im + off, h_re + CH, c * sizeof(double));
     }
     return DVD_OK;
 }
 
+// load_amplitudes_local_on_device / split_amplitudes_between_gpus (rust_communication.cu:384-448), the same pipeline
+// in the other direction: host memcpy of chunk k + 1 into a pinned slot overlaps the upload + join of chunk k.
 int dvd_load_state(dvd_state* s, const double* re, const double* im, int64_t first, int64_t count) {
     if (!s || ((!re || !im) && count > 0)) return fail(DVD_ERR_ARG, "null argument");
     if (first < 0 || count < 0 || (uint64_t)(first + count) > s->n_amps) return fail(DVD_ERR_ARG, "range outside the local chunk");
     TRY(sync_state(s));
-    const uint64_t CH = 1ull << 22;
-    std::vector<cplx> tmp(std::min<uint64_t>(CH, std::max<int64_t>(count, 1)));
-    for (uint64_t done = 0; done < (uint64_t)count; done += CH) {
-        const uint64_t c = std::min<uint64_t>(CH, count - done);
-        for (uint64_t i = 0; i < c; ++i) { tmp[i].x = re[done + i]; tmp[i].y = im[done + i]; }
-        CU(cudaMemcpyAsync(s->amp + first + done, tmp.data(), c * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
+    s->tree_valid = false; s->seq_valid = false;
+    if (count == 0) return DVD_OK;
+    const uint64_t CH = STAGE_AMPS, n = (uint64_t)count;
+    TRY(ensure_staging(s));
+    TRY(ensure_scratch(s, 4 * std::min(CH, n)));
+    const uint64_t cap = std::min(CH, n), n_chunks = (n + CH - 1) / CH;
+    for (uint64_t k = 0; k < n_chunks; ++k) {
+        const int slot = (int)(k & 1);
+        const uint64_t off = k * CH, c = std::min(CH, n - off);
+        double* d_re = s->d_scratch + (size_t)slot * 2 * cap;
+        double* h_re = s->h_stage + (size_t)slot * 2 * CH;
+        if (k >= 2) CU(cudaEventSynchronize(s->ev_stage[slot]));     // the upload that last used this slot is over
+        std::memcpy(h_re, re + off, c * sizeof(double));
+        std::memcpy(h_re + CH, im + off, c * sizeof(double));
+        CU(cudaMemcpyAsync(d_re, h_re, c * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(d_re + cap, h_re + CH, c * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CU(cudaEventRecord(s->ev_stage[slot], s->stream));
+        CU(launch_join_re_im(s->amp + first + off, c, d_re, d_re + cap, s->stream));
+        s->stats.kernel_launches++;
     }
-    s->tree_valid = false;
+    CU(cudaStreamSynchronize(s->stream));
     return DVD_OK;
 }
 
@@ -954,7 +1043,7 @@ int dvd_copy_state(dvd_state* dst, dvd_state* src) {
     dst->pending.clear();
     CU(cudaStreamSynchronize(src->stream));
     CU(cudaMemcpyAsync(dst->amp, src->amp, src->n_amps * sizeof(cplx), cudaMemcpyDeviceToDevice, dst->stream));
-    dst->tree_valid = false;
+    dst->tree_valid = false; dst->seq_valid = false;
     dst->support = ~0ull;
     return DVD_OK;
 }

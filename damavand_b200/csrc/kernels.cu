@@ -322,6 +322,71 @@ k_sample(const cplx* __restrict__ amp, int n_local, int nb, const double* __rest
     }
 }
 
+// ---- reference-order sampler (optional mode) ---------------------------------------------------
+// The reference's cumulative array is a strict left-to-right fp64 sum (utils.rs:270-274); a parallel reduction
+// rounds differently, and no parallel algorithm reproduces sequential rounding.  For states small enough to afford
+// it this mode pays for the sequential order: ONE warp walks the whole chunk once per state (lanes fetch and square
+// 32 amplitudes at a time, lane 0 adds them in index order) and stores the running sum at every block boundary
+// (cum[(b+1) * 2^nb]); a shot then needs a binary search over the boundaries and a sequential scan of one block.
+// The sums are exactly the reference's cum[] entries, so the sampled indices are the reference's for every draw.
+__global__ void __launch_bounds__(32)
+k_seq_block_cum(const cplx* __restrict__ amp, int nb, uint64_t n_blocks, double* __restrict__ block_cum) {
+    __shared__ double p[2][32];
+    const int lane = threadIdx.x;
+    const uint64_t n = n_blocks << nb;
+    double s = 0.0;
+    const uint64_t per_block = 1ull << nb;
+    // double-buffered: lanes fetch chunk c + 1 while lane 0 adds chunk c
+    if (lane < (int)(n < 32 ? n : 32)) p[0][lane] = norm_sqr(amp[lane]);
+    __syncwarp();
+    const uint64_t n_chunks = (n + 31) / 32;
+    for (uint64_t c = 0; c < n_chunks; ++c) {
+        const int cur = (int)(c & 1);
+        const uint64_t nxt = (c + 1) * 32 + lane;
+        double v = 0.0;
+        if (c + 1 < n_chunks && nxt < n) v = norm_sqr(amp[nxt]);
+        if (lane == 0) {
+            const uint64_t base = c * 32;
+            const int cnt = (int)(n - base < 32 ? n - base : 32);
+#pragma unroll 8
+            for (int i = 0; i < cnt; ++i) {
+                s = __dadd_rn(s, p[cur][i]);
+                if (((base + i + 1) & (per_block - 1)) == 0) block_cum[(base + i) >> nb] = s;
+            }
+        }
+        p[cur ^ 1][lane] = v;
+        __syncwarp();
+    }
+}
+
+// One thread per shot: out[s] = first j with xsi <= cum[j + 1] (utils.rs:258-268; xsi = 0 -> 0).
+__global__ void __launch_bounds__(128)
+k_sample_seq(const cplx* __restrict__ amp, int nb, uint64_t n_blocks, const double* __restrict__ block_cum,
+             const double* __restrict__ u, const int32_t* __restrict__ sel, int32_t sel_value, uint64_t index_offset,
+             uint64_t shots, unsigned long long* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const double total = block_cum[n_blocks - 1];
+    for (uint64_t sh = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; sh < shots; sh += stride) {
+        if (sel != nullptr && sel[sh] != sel_value) continue;
+        const double xsi = __dmul_rn(u[sh], total);
+        // first block b with xsi <= cum at its end (the boundary sums are non-decreasing)
+        uint64_t lo = 0, hi = n_blocks - 1;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (xsi <= block_cum[mid]) hi = mid; else lo = mid + 1;
+        }
+        double sacc = lo > 0 ? block_cum[lo - 1] : 0.0;
+        const cplx* src = amp + (lo << nb);
+        const uint64_t cnt = 1ull << nb;
+        uint64_t k = cnt - 1;
+        for (uint64_t i = 0; i < cnt; ++i) {
+            sacc = __dadd_rn(sacc, norm_sqr(src[i]));
+            if (xsi <= sacc) { k = i; break; }
+        }
+        out[sh] = index_offset + (lo << nb) + k;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_extract_expectation(const unsigned long long* __restrict__ samples, uint64_t shots, const int* __restrict__ qubits,
                       int n_obs, double* __restrict__ out) {
@@ -437,6 +502,23 @@ k_swap_peer(cplx* __restrict__ mine, cplx* __restrict__ peer, int lq, int my_bit
         *reinterpret_cast<double2*>(mine + im) = y;
         *reinterpret_cast<double2*>(peer + ip) = x;
     }
+}
+
+// Split / join of the interleaved complex128 state into the separate real and imaginary arrays of the reference's
+// boundary (retrieve_amplitudes_on_host / split_amplitudes_between_gpus, rust_communication.cu:400-482): done on the
+// device, so that the host only moves bytes.
+__global__ void __launch_bounds__(256)
+k_split_re_im(const cplx* __restrict__ amp, uint64_t count, double* __restrict__ re, double* __restrict__ im) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const cplx v = amp[i];
+        re[i] = v.x; im[i] = v.y;
+    }
+}
+__global__ void __launch_bounds__(256)
+k_join_re_im(cplx* __restrict__ amp, uint64_t count, const double* __restrict__ re, const double* __restrict__ im) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) amp[i] = cplx{re[i], im[i]};
 }
 
 constexpr int DOT_CTAS = 148 * 4;
@@ -594,6 +676,20 @@ cudaError_t launch_sample(const cplx* amp, int n_local, const double* tree, cons
     return cudaGetLastError();
 }
 
+cudaError_t launch_seq_block_cum(const cplx* amp, int n_local, double* block_cum, cudaStream_t s) {
+    const int nb = n_local < BLK_BITS ? n_local : BLK_BITS;
+    k_seq_block_cum<<<1, 32, 0, s>>>(amp, nb, 1ull << (n_local - nb), block_cum);
+    return cudaGetLastError();
+}
+cudaError_t launch_sample_seq(const cplx* amp, int n_local, const double* block_cum, const double* u, const int32_t* sel,
+                              int32_t sel_value, uint64_t index_offset, uint64_t shots, unsigned long long* out, cudaStream_t s) {
+    if (shots == 0) return cudaSuccess;
+    const int nb = n_local < BLK_BITS ? n_local : BLK_BITS;
+    k_sample_seq<<<grid_for(shots, 128, 148 * 8), 128, 0, s>>>(amp, nb, 1ull << (n_local - nb), block_cum, u, sel, sel_value,
+                                                               index_offset, shots, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_extract_expectation(const unsigned long long* samples, uint64_t shots, const int* qubits,
                                        int n_obs, double* out, cudaStream_t s) {
     const uint64_t total = shots * (uint64_t)n_obs;
@@ -626,6 +722,17 @@ cudaError_t launch_unpack_half(cplx* amp, int lq, int bitval, uint64_t first, ui
 cudaError_t launch_swap_peer(cplx* mine, cplx* peer, int lq, int my_bit, uint64_t e_begin, uint64_t e_end, cudaStream_t s) {
     if (e_end <= e_begin) return cudaSuccess;
     k_swap_peer<<<grid_for(e_end - e_begin, 256 * SWAP_UNROLL, 148 * 16), 256, 0, s>>>(mine, peer, lq, my_bit, e_begin, e_end);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_split_re_im(const cplx* amp, uint64_t count, double* re, double* im, cudaStream_t s) {
+    if (count == 0) return cudaSuccess;
+    k_split_re_im<<<grid_for(count, 256, STREAM_CAP), 256, 0, s>>>(amp, count, re, im);
+    return cudaGetLastError();
+}
+cudaError_t launch_join_re_im(cplx* amp, uint64_t count, const double* re, const double* im, cudaStream_t s) {
+    if (count == 0) return cudaSuccess;
+    k_join_re_im<<<grid_for(count, 256, STREAM_CAP), 256, 0, s>>>(amp, count, re, im);
     return cudaGetLastError();
 }
 

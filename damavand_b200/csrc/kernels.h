@@ -38,6 +38,12 @@ cudaError_t launch_sample(const cplx* amp, int n_local, const double* tree, cons
                           const int32_t* sel, int32_t sel_value, uint64_t index_offset,
                           uint64_t shots, unsigned long long* out, cudaStream_t s);
 
+// Reference-order sampler (strict left-to-right cumulative sums, utils.rs:258-277): block_cum[b] = cum[(b + 1) * 2^nb]
+// (nb = min(BLK_BITS, n_local); 2^(n_local - nb) entries), built by one warp in index order; then one thread per shot.
+cudaError_t launch_seq_block_cum(const cplx* amp, int n_local, double* block_cum, cudaStream_t s);
+cudaError_t launch_sample_seq(const cplx* amp, int n_local, const double* block_cum, const double* u, const int32_t* sel,
+                              int32_t sel_value, uint64_t index_offset, uint64_t shots, unsigned long long* out, cudaStream_t s);
+
 // out[s*n_obs + o] = ((samples[s] >> qubits[o]) & 1) ? -1 : +1
 cudaError_t launch_extract_expectation(const unsigned long long* samples, uint64_t shots, const int* qubits,
                                        int n_obs, double* out, cudaStream_t s);
@@ -56,6 +62,10 @@ cudaError_t launch_unpack_half(cplx* amp, int lq, int bitval, uint64_t first, ui
 // Direct NVLink swap: exchange elements [e_begin, e_end) of this rank's leaving half (bit lq == 1 - my_bit)
 // with the partner's leaving half (its bit lq == my_bit); `peer` is the partner's state mapped with CUDA IPC.
 cudaError_t launch_swap_peer(cplx* mine, cplx* peer, int lq, int my_bit, uint64_t e_begin, uint64_t e_end, cudaStream_t s);
+
+// interleaved complex128 <-> separate real / imaginary arrays (device side of dvd_read_state / dvd_load_state)
+cudaError_t launch_split_re_im(const cplx* amp, uint64_t count, double* re, double* im, cudaStream_t s);
+cudaError_t launch_join_re_im(cplx* amp, uint64_t count, const double* re, const double* im, cudaStream_t s);
 
 // <a|b> partial dot (conj(a).b), deterministic two-stage reduction; out[0]=re, out[1]=im
 cudaError_t launch_dot(const cplx* a, const cplx* b, uint64_t count, double* partial, double* out, cudaStream_t s);

@@ -97,6 +97,12 @@ int dvd_sample(dvd_state* s, const double* uniforms, int64_t shots, uint64_t* ou
  * qubits[o] of samples[s].  Runs on s's device. */
 int dvd_extract_expectation_values(dvd_state* s, const uint64_t* samples, int64_t shots,
                                    const int32_t* qubits, int32_t n_obs, double* out);
+/* Summation order of the sampler's cumulative probabilities.  DVD_SAMPLER_TREE (default): fixed pairwise tree, any
+ * size.  DVD_SAMPLER_SEQUENTIAL: the reference's strict left-to-right order (utils.rs:270-274) -- the indices are the
+ * reference's for EVERY draw, at the price of one sequential walk over the chunk per state (<= 30 local qubits). */
+#define DVD_SAMPLER_TREE 0
+#define DVD_SAMPLER_SEQUENTIAL 1
+int dvd_set_sampler(dvd_state* s, int order);
 /* exact <Z_q> for q in [0, n_qubits) (extension; allreduced) */
 int dvd_expectation_z(dvd_state* s, double* out_per_qubit);
 /* replaces retrieve_amplitudes_on_host, rust_communication.cu:450-482: LOCAL chunk, split arrays */

@@ -38,7 +38,7 @@ def test_distributed_gpu_against_oracle_on_all_visible_gpus(mode):
         pytest.skip("one visible GPU: the multi-rank path needs at least two (bench.py --gpus N carries the same oracle "
                     "comparison in its `parity` field)")
     env = dict(os.environ)
-    env.update({"DIST_CHECK_N": "14,21,23", "DIST_CHECK_JIT": "1" if mode == "fused_remap_jit" else "0", "DVD_JIT_MIN_QUBITS": "12"})
+    env.update({"DIST_CHECK_N": "14,20,22", "DIST_CHECK_QFT_MAX": "20", "DIST_CHECK_JIT": "1" if mode == "fused_remap_jit" else "0", "DVD_JIT_MIN_QUBITS": "12"})
     if mode == "in_place_peer_swap":
         env["DVD_FUSED_REMAP"] = "0"            # every global<->local swap as a k_swap_peer exchange of its own
     if mode == "staged_nccl":
@@ -49,7 +49,7 @@ def test_distributed_gpu_against_oracle_on_all_visible_gpus(mode):
     tail = (res.stdout + res.stderr)[-4000:]
     assert res.returncode == 0 and "DIST_CHECK PASS" in res.stdout, tail
     lines = [l for l in res.stdout.splitlines() if l.startswith("n=")]
-    assert len(lines) == 12 and all("all_ranks_ok=True" in l for l in lines), tail
+    assert len(lines) == 10 and all("all_ranks_ok=True" in l for l in lines), tail
     if mode.startswith("fused_remap"):
         assert any("fused_remap_passes=" in l and "fused_remap_passes=0 " not in l for l in lines), tail
     else:

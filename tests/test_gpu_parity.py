@@ -601,3 +601,40 @@ def test_expectation_z_beyond_32_local_qubits():
     assert np.abs(ez - want).max() < 1e-12
     assert abs(g.norm() - 1.0) < 1e-12
     g.close()
+
+
+@pytest.mark.parametrize("kind", ["random", "hea", "qft"])
+def test_config_scale_parity_26_qubits(kind):
+    """26 qubits (1 GiB state, the largest the oracle finishes in minutes): every amplitude against the oracle, in the
+    max-relative and the l2-relative metric; then 10^5 shots on identical amplitudes (the oracle's, loaded into the
+    engine) in both summation orders -- the default pairwise tree against the oracle's tree, the reference-order mode
+    against the oracle's sequential cumulative sums (utils.rs:258-277), bit for bit -- and the two orders against each
+    other: a shot may only differ where xsi falls within rounding of a bin edge, by one populated bin."""
+    n = 26
+    build = {"qft": lambda c: circuits.qft_like(c, n),                    # 1655 gates, all three passes' worth of twiddles
+             "hea": lambda c: circuits.hea(c, n, 5),
+             "random": lambda c: circuits.random_circuit(c, n, 200, 26)}[kind]
+    g, o = both(n, build)
+    a, b = g.state_numpy(), o.amplitudes()
+    assert rel_err(a, b) < TOL
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < TOL
+    assert np.abs(np.abs(a) ** 2 - np.abs(b) ** 2).max() / (np.abs(b) ** 2).max() < TOL      # probabilities
+    g.load_state_numpy(b)
+    p = o.measure_np()
+    shots = 100000
+    u = np.random.default_rng(2626).random(shots)
+    u[:3] = [0.0, 1.0 - 2.0 ** -53, 0.5]
+    s_tree = g.sample_numpy(shots, u)
+    assert (s_tree == oracle.sample_tree(p, u)).all()
+    g.set_sampler("sequential")
+    s_seq = g.sample_numpy(shots, u)
+    assert (s_seq == oracle.sample_sequential(p, u)).all()
+    diff = np.nonzero(s_tree != s_seq)[0]
+    assert diff.size <= 5, diff.size          # expected ~shots * |tree - sequential prefix| / bin width ~ 1e-3 at 26 qubits
+    cum = np.cumsum(p)
+    for k in diff:      # both answers bracket xsi to within the summation error of the prefix
+        xsi = u[k] * cum[-1]
+        for idx in (int(s_tree[k]), int(s_seq[k])):
+            lo = cum[idx - 1] if idx else 0.0
+            assert lo - 1e-12 <= xsi <= cum[idx] + 1e-12
+    g.close()
