@@ -463,6 +463,18 @@ def roofline_of(m, name, n_local, n_gates, gpus):
          "note": "frac = HBM bytes the pass kernel moves per launch / mean launch duration (CUDA events over the timed region, "
                  "includes NVLink exchanges at N > 1) / measured copy peak; achieved_algorithmic is the per-gate accounting of "
                  "SURVEY 8(d) and is inflated by fusion"}
+    # Second roofline: the fp64 pipe.  The planner counts the DADD / DMUL / DFMA each thread executes per pass (an estimate
+    # from the op list: general 2x2 = 16 per pair, real = 8, Hadamard = 4, complex multiply = 4); the peak is the DFMA
+    # issue rate measured on B200 (profiles/r1_microbench2.log: 33.5 TFLOP/s = 16.75e12 fp64 instructions per second).
+    # Gate-dense passes (ansatz layers, random circuits) are bound by this pipe, not by HBM.
+    if st1.get("pass_fp64_instr"):
+        rate = st1["pass_fp64_instr"] / fwd_s
+        r["fp64"] = {"instr_per_s": rate, "peak_instr_per_s": 16.75e12, "frac": rate / 16.75e12,
+                     "instr_per_amplitude_per_pass": st1["pass_fp64_instr"] / launches / (st1["pass_bytes"] / launches / 32.0),
+                     "bound_ms_per_circuit": st1["pass_fp64_instr"] / 16.75e12 * 1e3,
+                     "hbm_bound_ms_per_circuit": st1["pass_bytes"] / (peak * 1e9) * 1e3,
+                     "note": "planner estimate of executed fp64 instructions / time / measured DFMA issue peak; the circuit cannot run "
+                             "faster than max(bound_ms_per_circuit, hbm_bound_ms_per_circuit)"}
     if st1["global_swaps"]:
         # NVLink side: fused-remap passes pull (1 - 2^-k) of a chunk from partner ranks while they run (the same
         # amount leaves through the other direction of the links); stand-alone exchanges are timed on their own

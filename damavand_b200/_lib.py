@@ -41,6 +41,7 @@ class Stats(ctypes.Structure):
         ("remap_bytes_in", ctypes.c_double),
         ("remap_ms", ctypes.c_double),
         ("swap_ms", ctypes.c_double),
+        ("pass_fp64_instr", ctypes.c_double),
     ]
 
     def as_dict(self):

@@ -638,6 +638,7 @@ static int flush_impl(dvd_state* s) {
         if (tm) CU(cudaEventRecord(tm->t1, s->stream));
         s->stats.kernel_launches++; s->stats.tile_passes++;
         s->stats.stage_switches += p.n_switches;
+        s->stats.pass_fp64_instr += (double)p.fp64_per_thread * (double)(1ull << pp.pd.n_cta_bits) * NTHREADS;
         {   // HBM bytes this launch moves: its tiles are written in full, read where the input can be non-zero
             const double tiles_bytes = (double)(1ull << pp.pd.n_cta_bits) * TILE_AMPS * sizeof(cplx);
             s->stats.pass_bytes += tiles_bytes * (1.0 + 1.0 / (double)(1ull << __builtin_popcountll(zm & tile_mask & ~lmask)));

@@ -917,6 +917,7 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates_in, int n_local,
         }
         pass.desc.n_ops = (int)pass.ops.size();
         pass.desc.n_tab = (int)pass.tab_desc.size();
+        pass.fp64_per_thread = estimate_fp64(pass.ops);
         pass.touch_mask = 0;
         for (int gi : taken) if (!gates[gi].diag) pass.touch_mask |= gates[gi].tmask;
         if (pass.desc.n_ops >= MAX_OPS_PER_PASS || pass.desc.n_tab > MAX_TABLE_OPS) {
@@ -950,6 +951,33 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates_in, int n_local,
         pending.swap(rest);
     }
     return passes;
+}
+
+int estimate_fp64(const std::vector<DevOp>& ops) {
+    int total = 0;
+    bool scalar_dirty = false;
+    for (const DevOp& raw : ops) {
+        int code = raw.code;
+        if (code == OC_REALPH4) code = OC_GATE + 4 * K_REALPH;
+        if (code == OC_TWHAD4) code = OC_TWHAD;
+        const unsigned pm = (raw.flags >> F_PM_SHIFT) & 7u;
+        const int w4 = 4 * (int)((pm & 1u) + 2 * ((pm >> 1) & 1u) + 4 * ((pm >> 2) & 1u));     // twiddle variants over the other register bits
+        if (code >= OC_SWITCH) { if (scalar_dirty) total += 4 * NREG; scalar_dirty = false; continue; }
+        if (code < OC_CGEN) {
+            static const int per_pair[] = {16, 8, 8, 8, 4, 12};     // K_GENERAL, K_REAL, K_RXLIKE, K_ANTIDIAG, K_HADAMARD, K_REALPH
+            const int c = per_pair[(code - OC_GATE) / 4] * (NREG / 2);
+            total += (raw.flags & F_TCTRL) ? c / 2 : c;             // thread-level control: half the threads on average
+        } else if (code < OC_DIAG1) total += 16 * (NREG / 4);       // OC_CGEN: half the pairs
+        else if (code < OC_PHASE) total += 4 * (NREG / 2);          // OC_DIAG1
+        else if (code == OC_PHASE) { total += 4; scalar_dirty = true; }
+        else if (code == OC_DIAGGEN) total += 4 * NREG;
+        else if (code == OC_TABLE) { total += 12; scalar_dirty = true; }
+        else if (code < OC_PAIR) total += ((raw.flags & F_TABLE) ? 8 : 0) + w4 + 4 * (NREG / 2);                    // OC_TABLE_REG
+        else if (code < OC_TWHAD) total += 4 * (NREG / 4);          // OC_PAIR
+        else total += ((raw.flags & F_TABLE) ? 8 : 0) + w4 + 4 * (NREG / 2) + 4 * (NREG / 2);                     // OC_TWHAD
+    }
+    if (scalar_dirty) total += 4 * NREG;
+    return total;
 }
 
 Pass make_identity_pass(int n_local) {

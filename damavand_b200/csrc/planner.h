@@ -45,6 +45,9 @@ struct Pass {
     size_t tid_off_slot = 0;           // start (in cplx slots) of the [NGROUPS][NTHREADS] thread-offset table inside `tables`
     void finish_tables();              // concatenate [desc][tile][bytes][thread offsets] into `tables`, fill desc.run_*
     int n_switches = 0;        // stage switches inside the pass (shared-memory transposes)
+    int fp64_per_thread = 0;   // estimate of the fp64 instructions (DADD / DMUL / DFMA) one thread executes for its 16
+                               //   amplitudes in this pass (estimate_fp64): the passes of gate-dense circuits are bound by
+                               //   the fp64 pipe, not by HBM, and bench.py reports that roofline next to the HBM one
     uint64_t touch_mask = 0;   // targets of the pass's non-diagonal gates (X / CNOT included): the only qubits whose
                                //   |0> can turn into a superposition in this pass (support tracking in the engine)
 };
@@ -56,7 +59,7 @@ struct PlanOptions {
     int max_ops_per_pass = 1024;   // gates taken into one pass (halved and retried while the op stream exceeds MAX_OPS_PER_PASS)
     bool macro_ops = true;     // fuse 4-op runs on the four register bits into one dispatch (OC_REALPH4, OC_TWHAD4)
     bool best_group = false;   // stage order: group with the most runnable work (true) or group of the first waiting gate
-    bool relabel = false;      // tile relabelling (experimental, replay-tested only): the pinned low tile positions are
+    bool relabel = true;       // tile relabelling (measured on B200 in round 2: hea28 80 -> 55 passes, 236 -> 204 ms; DVD_RELABEL=0 turns it off): the pinned low tile positions are
                                //   physical qubits [0, min_low), present in every tile; at the end of a pass the logical
                                //   qubit held there may trade places with one of the tile's other qubits that the
                                //   following gates need sooner (three CNOTs = one more column swap of the permuting
@@ -76,6 +79,10 @@ std::vector<HostGate> fuse_diagonal_runs(const std::vector<HostGate>& gates);
 // Requires n_local >= TILE_BITS.
 std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, int n_total,
                              const PlanOptions& opt);
+
+// fp64 instructions per thread of an op list (per-kind costs of tile_core.cuh: general 2x2 = 16 per pair, real / RX-like
+// = 8, Hadamard = 4, real + phase = 12, one complex multiply = 4).
+int estimate_fp64(const std::vector<DevOp>& ops);
 
 // A pass with no ops over the tile of the 12 lowest qubits: reads and writes every amplitude once.  The engine runs
 // it when a fused remap (tile_core.cuh: PassDesc::remap_*) has no gate pass to ride on.

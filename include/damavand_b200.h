@@ -143,6 +143,8 @@ typedef struct {
                                      served to the partners in the other direction) */
     double remap_ms;              /* device time of those passes (CUDA events on the state's stream) */
     double swap_ms;               /* device time of the stand-alone exchanges (in-place peer swap / staged NCCL path) */
+    double pass_fp64_instr;       /* planner's estimate of the fp64 instructions (per lane: one DADD / DMUL / DFMA of one thread) the
+                                     tile passes executed: the second roofline of gate-dense passes */
 } dvd_stats;
 int dvd_get_stats(const dvd_state* s, dvd_stats* out);
 int dvd_stats_reset(dvd_state* s);
