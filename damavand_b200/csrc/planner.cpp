@@ -652,8 +652,24 @@ struct StageEmitter {
 
 }  // namespace
 
-std::vector<Pass> plan_local(const std::vector<HostGate>& gates_in, int n_local, int n_total,
-                             const PlanOptions& opt) {
+static std::vector<Pass> plan_local_impl(const std::vector<HostGate>& gates_in, int n_local, int n_total, const PlanOptions& opt);
+
+// Tile relabelling pays when it saves passes (chain-like circuits: hea28 80 -> 55); where it does not (random32,
+// qft30: the same pass count either way) its extra swap gates only add transposes and make untouched qubits look
+// touched to the support tracking -- measured on B200: random32 from a reset 274 -> 329 ms.  So both plans are made
+// (host time, cached with the plan) and relabelling is kept only if it needs strictly fewer passes.
+std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, int n_total, const PlanOptions& opt) {
+    if (!opt.relabel) return plan_local_impl(gates, n_local, n_total, opt);
+    PlanOptions plain = opt;
+    plain.relabel = false;
+    std::vector<Pass> a = plan_local_impl(gates, n_local, n_total, plain);
+    if (a.size() <= 1) return a;
+    std::vector<Pass> b = plan_local_impl(gates, n_local, n_total, opt);
+    return b.size() < a.size() ? b : a;
+}
+
+static std::vector<Pass> plan_local_impl(const std::vector<HostGate>& gates_in, int n_local, int n_total,
+                                         const PlanOptions& opt) {
     std::vector<HostGate> gates = gates_in;   // relabelling appends swap gates and renames qubits of the gates still to run
     if (n_local < TILE_BITS) throw std::runtime_error("plan_local: n_local < TILE_BITS");
     if (n_total > 62) throw std::runtime_error("plan_local: too many qubits");
