@@ -591,26 +591,17 @@ static int flush_impl(dvd_state* s) {
         pp.pd.zero_regbits = (int8_t)zregs;
         cplx* out = s->amp;
         uint64_t lmask = 0;
+        RemapPlan rp;
+        if (!remap.empty()) {
+            if (!compose_remap(remap, s->n_local, s->rank, &rp)) return fail(DVD_ERR_INTERNAL, "fused remap over too many positions");
+            if (!rp.on) remap.clear();          // the swaps cancel: nothing moves
+        }
         if (!remap.empty()) {
             // the pass reads buffer `cur` of this rank and of its partners, writes buffer 1 - cur of this rank
-            pp.pd.remap_n = (int8_t)remap.size();
-            uint64_t rconst = 0;
-            for (size_t k = 0; k < remap.size(); ++k) {
-                const int j = remap[k].first - s->n_local, lq = remap[k].second;
-                pp.pd.remap_lq[k] = (int8_t)lq;
-                lmask |= 1ull << lq;
-                rconst |= (uint64_t)((s->rank >> j) & 1) << lq;
-            }
-            pp.pd.remap_lmask = lmask;
-            pp.pd.remap_const = rconst;
-            for (unsigned sel = 0; sel < (1u << remap.size()); ++sel) {
-                int r = s->rank;
-                for (size_t k = 0; k < remap.size(); ++k) {
-                    const int j = remap[k].first - s->n_local;
-                    r = (r & ~(1 << j)) | (int)((sel >> k) & 1u) << j;
-                }
-                pp.pd.remap_src[sel] = r == s->rank ? s->amp : s->peer_cur(r);
-            }
+            apply_remap(rp, &pp.pd);
+            lmask = rp.lmask;
+            for (int sel = 0; sel < (1 << rp.n_sel); ++sel)
+                pp.pd.remap_src[sel] = rp.src_rank[sel] == s->rank ? s->amp : s->peer_cur(rp.src_rank[sel]);
             out = s->buf[1 - s->cur];
             // every rank's buffer `cur` is complete (and nobody still reads the buffer this pass overwrites: the
             // previous fused pass, which read it, lies before this barrier on every rank)
@@ -618,7 +609,15 @@ static int flush_impl(dvd_state* s) {
         }
         // tiles whose fixed bits make every source amplitude zero are not launched (bits of the swapped-in
         // positions are rank-index bits of the source: never implied)
-        if (zm & ~tile_mask & ~lmask) fill_cta_runs_sparse(pp.pd, zm & ~tile_mask & ~lmask);   // on failure the full grid stays
+        if (pp.pd.remap_on) {
+            // the index bits that select the source rank become the lowest bits of the CTA index: tiles fetched over
+            // NVLink and tiles fetched from local HBM alternate in launch order (on failure the default order stays)
+            uint64_t sel_bits = 0;
+            for (int k = 0; k < pp.pd.remap_n; ++k) sel_bits |= 1ull << pp.pd.remap_lq[k];
+            fill_cta_runs_ex(pp.pd, zm & ~tile_mask & ~lmask, sel_bits);
+        } else if (zm & ~tile_mask) {
+            fill_cta_runs_sparse(pp.pd, zm & ~tile_mask);   // on failure the full grid stays
+        }
         pp.pd.tables = d_tab;
         pp.pd.tid_off = reinterpret_cast<const uint64_t*>(d_tab + p.tid_off_slot);
         std::memcpy(pp.ops, p.ops.data(), p.ops.size() * sizeof(DevOp));
@@ -645,14 +644,16 @@ static int flush_impl(dvd_state* s) {
         }
         if (!remap.empty()) {
             const double chunk = (double)s->n_amps * sizeof(cplx);
-            const double moved = chunk * (1.0 - 1.0 / (double)(1u << remap.size()));   // pulled over NVLink (and served to the partners)
+            int local_sel = 0;
+            for (int sel = 0; sel < (1 << rp.n_sel); ++sel) local_sel += rp.src_rank[sel] == s->rank;
+            const double moved = chunk * (1.0 - (double)local_sel / (double)(1 << rp.n_sel));   // pulled over NVLink (and served to the partners)
             s->stats.global_swaps += (int64_t)remap.size();
             s->stats.swap_bytes_sent += (int64_t)moved;
             s->stats.remap_passes++;
             s->stats.remap_bytes_in += moved;
             s->cur = 1 - s->cur;
             s->amp = s->buf[s->cur];
-            s->support |= lmask;          // the swapped-in positions hold former rank-index qubits: never implied zero
+            s->support |= lmask;          // the rebuilt positions may hold former rank-index qubits: never implied zero
             remap.clear();
             fused_any = true;
         }
@@ -676,10 +677,15 @@ static int flush_impl(dvd_state* s) {
         DistStep& st = steps[i];
         if (st.kind == DistStep::GLOBAL_SWAP) {
             if (tiled && s->fused_remap) {
-                bool disjoint = remap.size() < (size_t)MAX_REMAP;
-                for (auto& pr : remap) if (pr.first == st.gq || pr.second == st.lq) disjoint = false;
-                if (!disjoint) TRY(flush_remap());
+                // consecutive swaps compose into one remap as long as they stay within MAX_REMAP rank-index and
+                // MAX_REMAP local positions (any permutation of those: shared positions included)
                 remap.push_back({st.gq, st.lq});
+                RemapPlan probe;
+                if (!compose_remap(remap, s->n_local, s->rank, &probe)) {
+                    remap.pop_back();
+                    TRY(flush_remap());
+                    remap.push_back({st.gq, st.lq});
+                }
                 continue;
             }
             TRY(materialize(s)); TRY(global_swap(s, st.gq, st.lq));

@@ -394,7 +394,7 @@ bool jit_launch(const Pass& p, int mode, int device, cplx* amp, const PassParams
             harvest(d);
             const bool dense_full = ring_ok;
             // (a pass whose load carries a fused remap pulls half its tile over NVLink: not a fair timing sample)
-            if (dense_full && pp.pd.remap_n == 0 && d.best_dense < 0 && (d.sig < 0 || d.sig == pp.pd.n_cta_bits)) {
+            if (dense_full && !pp.pd.remap_on && d.best_dense < 0 && (d.sig < 0 || d.sig == pp.pd.n_cta_bits)) {
                 // measuring: the usable candidate with the fewest timings (finished or in flight) runs next
                 int n_have[FORM_COUNT];
                 for (int f = 0; f < FORM_COUNT; ++f) n_have[f] = (int)d.ms[f].size();

@@ -38,7 +38,7 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     // normally does not even launch those)
     if (cbase & pd.zero_mask & ~pd.remap_lmask) return;
     cplx a[NREG];
-    // with a fused remap (pd.remap_n > 0) the input is pd.remap_src[..], out of place
+    // with a fused remap (pd.remap_on) the input is pd.remap_src[..], out of place
     tile_load<IO_GROUP>(amp, pd, a, cbase, tid_offset_arith(pd, IO_GROUP, tid));
     const Toff toff = toff_fill(s_toff, pd, tid);   // table lookups in the shadow of the tile's loads
 

@@ -996,6 +996,71 @@ int estimate_fp64(const std::vector<DevOp>& ops) {
     return total;
 }
 
+bool compose_remap(const std::vector<std::pair<int, int>>& swaps, int n_local, int rank, RemapPlan* out) {
+    // at[p] = the position whose (old) bit sits at position p after the swaps: new_bit[p] = old_bit[at[p]]
+    std::vector<int> pos;      // positions involved, in order of first appearance
+    auto idx_of = [&](int p) {
+        for (size_t k = 0; k < pos.size(); ++k) if (pos[k] == p) return (int)k;
+        pos.push_back(p);
+        return (int)pos.size() - 1;
+    };
+    std::vector<int> at;
+    for (auto& sw : swaps) {
+        const int a = idx_of(sw.first), b = idx_of(sw.second);
+        at.resize(pos.size(), -1);
+        for (size_t k = 0; k < at.size(); ++k) if (at[k] < 0) at[k] = pos[k];
+        std::swap(at[a], at[b]);
+    }
+    RemapPlan rp;
+    std::vector<int> G, L;
+    for (int p : pos) (p >= n_local ? G : L).push_back(p);
+    rp.n_global = (int)G.size(); rp.n_local_pos = (int)L.size();
+    if ((int)G.size() > MAX_REMAP || (int)L.size() > MAX_REMAP) return false;
+    auto where = [&](int q) {          // the position the old bit q ends up at
+        for (size_t k = 0; k < pos.size(); ++k) if (at[k] == q) return pos[k];
+        return q;
+    };
+    bool identity = true;
+    for (size_t k = 0; k < pos.size(); ++k) if (at[k] != pos[k]) identity = false;
+    if (identity) { *out = rp; return true; }
+    rp.on = true;
+    // selector bits: the local positions of the new index that carry an old rank-index bit
+    int sel_of_g[MAX_REMAP];
+    for (size_t g = 0; g < G.size(); ++g) {
+        const int w = where(G[g]);
+        sel_of_g[g] = -1;
+        if (w < n_local) { sel_of_g[g] = rp.n_sel; rp.sel_lq[rp.n_sel++] = w; }
+    }
+    for (int sel = 0; sel < (1 << rp.n_sel); ++sel) {
+        int r = rank;
+        for (size_t g = 0; g < G.size(); ++g) {
+            const int j = G[g] - n_local, w = where(G[g]);
+            const int bit = sel_of_g[g] >= 0 ? (sel >> sel_of_g[g]) & 1 : (rank >> (w - n_local)) & 1;
+            r = (r & ~(1 << j)) | (bit << j);
+        }
+        rp.src_rank[sel] = r;
+    }
+    // the local positions of the source index: this rank's bits (constants) or other local bits of the new index
+    for (int q : L) {
+        rp.lmask |= 1ull << q;
+        const int w = where(q);
+        if (w >= n_local) rp.rconst |= (uint64_t)((rank >> (w - n_local)) & 1) << q;
+        else { rp.mv_from[rp.n_mv] = w; rp.mv_to[rp.n_mv] = q; ++rp.n_mv; }
+    }
+    *out = rp;
+    return true;
+}
+
+void apply_remap(const RemapPlan& rp, PassDesc* pd) {
+    pd->remap_on = rp.on ? 1 : 0;
+    pd->remap_n = (int8_t)rp.n_sel;
+    for (int k = 0; k < rp.n_sel; ++k) pd->remap_lq[k] = (int8_t)rp.sel_lq[k];
+    pd->remap_n_mv = (int8_t)rp.n_mv;
+    for (int k = 0; k < rp.n_mv; ++k) { pd->remap_mv_from[k] = (int8_t)rp.mv_from[k]; pd->remap_mv_to[k] = (int8_t)rp.mv_to[k]; }
+    pd->remap_lmask = rp.lmask;
+    pd->remap_const = rp.rconst;
+}
+
 Pass make_identity_pass(int n_local) {
     if (n_local < TILE_BITS) throw std::runtime_error("make_identity_pass: n_local < TILE_BITS");
     Pass pass;

@@ -15,6 +15,7 @@
 //      compile its diagonal gates into a phase polynomial emitted as table / register-bit / pair ops.
 #pragma once
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 #include "tile_core.cuh"
@@ -96,6 +97,23 @@ struct DistStep {
     // GLOBAL_SWAP: exchange physical global qubit `gq` (>= n_local) with physical local qubit `lq`
     int gq = -1, lq = -1;
 };
+
+// A sequence of GLOBAL_SWAP steps composed into ONE fused remap (tile_core.cuh: PassDesc::remap_*), for rank `rank`.
+// Returns false when the sequence touches more than MAX_REMAP rank-index or more than MAX_REMAP local positions (the
+// caller then executes what it has and starts a new remap).  An identity composition gives on = false.
+struct RemapPlan {
+    bool on = false;
+    int n_sel = 0;
+    int sel_lq[MAX_REMAP];          // local positions of the NEW index whose bits select the source rank
+    int src_rank[1 << MAX_REMAP];   // source rank per selector value
+    int n_mv = 0;
+    int mv_from[MAX_REMAP], mv_to[MAX_REMAP];
+    uint64_t lmask = 0, rconst = 0;
+    int n_global = 0, n_local_pos = 0;
+};
+bool compose_remap(const std::vector<std::pair<int, int>>& swaps, int n_local, int rank, RemapPlan* out);
+// Fill the remap fields of a pass descriptor (all but remap_src, which the caller derives from src_rank).
+void apply_remap(const RemapPlan& rp, PassDesc* pd);
 
 // perm[logical] = physical, updated in place.  When `restore_identity` is set, trailing swaps bring
 // the layout back to perm[q] = q (needed before measure / sample / readback, whose semantics are

@@ -189,16 +189,22 @@ struct PassDesc {
                                   //   a reset): amplitudes with one of these bits set are zero by construction, are never
                                   //   read, and tiles whose fixed bits hit the mask are not launched at all.  0 = dense state
                                   //   (with a fused remap: a mask over the SOURCE index, i.e. the layout before the swap)
-    // Fused global<->local qubit remap (distributed_gpu, set by the engine): up to MAX_REMAP disjoint swaps of a
-    // rank-index qubit with a local qubit are executed by this pass's LOAD instead of by an exchange of their own.
-    // The pass then runs out of place: the amplitude at (new) local index i is read from
-    //     remap_src[sel(i)] + ((i & ~remap_lmask) | remap_const),   sel(i) = sum_k bit(remap_lq[k] of i) << k,
-    // where remap_src[sel] is this rank's own input buffer or a partner rank's (peer memory over NVLink, mapped with
-    // CUDA IPC) and remap_const holds this rank's bits of the swapped rank-index qubits, deposited at remap_lq[k].
-    // remap_n == 0: plain in-place pass.  Replaces exchange_amplitudes_between_gpus + the distributed gate kernel
-    // (rust_communication.cu:106-141, kernels.cu:174-230): the exchange IS the next pass's read.
+    // Fused global<->local qubit remap (distributed_gpu, set by the engine from planner.h: compose_remap): a SEQUENCE of
+    // swaps between rank-index qubits and local qubits -- any bit permutation over at most MAX_REMAP rank-index and
+    // MAX_REMAP local positions -- is executed by this pass's LOAD instead of by exchanges of their own.  The pass then
+    // runs out of place: the amplitude at (new) local index i is read from buffer remap_src[sel(i)], with
+    //     sel(i) = sum_k bit(remap_lq[k] of i) << k                       (which rank held it: remap_n <= 3 index bits)
+    // at local index
+    //     (i & ~remap_lmask) | remap_const | sum_m bit(remap_mv_from[m] of i) << remap_mv_to[m]
+    // (the local positions involved are rebuilt from this rank's own rank bits -- a constant -- or from other local
+    // bits of i).  remap_src[sel] is this rank's own input buffer or a partner rank's (peer memory over NVLink, mapped
+    // with CUDA IPC).  remap_on == 0: plain in-place pass.  Replaces exchange_amplitudes_between_gpus + the distributed
+    // gate kernel (rust_communication.cu:106-141, kernels.cu:174-230): the exchange IS the next pass's read.
+    int8_t remap_on;
     int8_t remap_n;
     int8_t remap_lq[3];
+    int8_t remap_n_mv;
+    int8_t remap_mv_from[3], remap_mv_to[3];
     uint64_t remap_lmask, remap_const;
     const cplx* remap_src[8];
 };
@@ -290,6 +296,35 @@ inline bool fill_cta_runs_sparse(PassDesc& pd, uint64_t skip) {
     pd.n_cta_bits = (int8_t)src;
     return true;
 }
+// Host: the general form.  Bits in `skip` are fixed to zero (tiles that are zero by construction are not launched);
+// the non-tile bits in `first` take the LOWEST bits of the CTA index.  A pass whose load carries a fused remap puts
+// the bits that select the source rank there: tiles fetched over NVLink and tiles fetched from local HBM then
+// alternate in launch order, so the links are busy for the whole pass instead of for its second half only.
+inline bool fill_cta_runs_ex(PassDesc& pd, uint64_t skip, uint64_t first) {
+    uint64_t tile = 0;
+    for (int p = 0; p < TILE_BITS; ++p) tile |= 1ull << pd.tile_q[p];
+    first &= ~(tile | skip) & ((1ull << pd.n_local) - 1);
+    int n = 0, src = 0;
+    int8_t rs[TILE_BITS + 1], rl[TILE_BITS + 1], rd[TILE_BITS + 1];
+    for (int q = 0; q < pd.n_local; ++q)
+        if ((first >> q) & 1ull) {
+            if (n > TILE_BITS) return false;
+            rs[n] = (int8_t)src; rl[n] = 1; rd[n] = (int8_t)q; ++n; ++src;
+        }
+    int q = 0;
+    const uint64_t taken = tile | skip | first;
+    while (q < pd.n_local) {
+        if ((taken >> q) & 1ull) { ++q; continue; }
+        int len = 0;
+        while (q + len < pd.n_local && !((taken >> (q + len)) & 1ull)) ++len;
+        if (n > TILE_BITS) return false;
+        rs[n] = (int8_t)src; rl[n] = (int8_t)len; rd[n] = (int8_t)q; ++n; src += len; q += len;
+    }
+    for (int r = 0; r < n; ++r) { pd.run_src[r] = rs[r]; pd.run_len[r] = rl[r]; pd.run_dst[r] = rd[r]; }
+    pd.n_runs = (int8_t)n;
+    pd.n_cta_bits = (int8_t)src;
+    return true;
+}
 #endif  // !__CUDACC_RTC__
 
 // Source of the amplitude at (new) local index i under a fused remap (PassDesc::remap_*): buffer and local index.
@@ -300,7 +335,13 @@ DVD_HD unsigned remap_sel(const PassDesc& pd, uint64_t i) {
         if (k < pd.remap_n) sel |= (unsigned)((i >> pd.remap_lq[k]) & 1ull) << k;
     return sel;
 }
-DVD_HD uint64_t remap_index(const PassDesc& pd, uint64_t i) { return (i & ~pd.remap_lmask) | pd.remap_const; }
+DVD_HD uint64_t remap_index(const PassDesc& pd, uint64_t i) {
+    uint64_t src = (i & ~pd.remap_lmask) | pd.remap_const;
+#pragma unroll
+    for (int m = 0; m < MAX_REMAP; ++m)
+        if (m < pd.remap_n_mv) src |= ((i >> pd.remap_mv_from[m]) & 1ull) << pd.remap_mv_to[m];
+    return src;
+}
 
 // Local index of element h of the half-chunk whose bit lq equals bitval (global<->local qubit swap).
 DVD_HD uint64_t half_index(uint64_t h, int lq, int bitval) {

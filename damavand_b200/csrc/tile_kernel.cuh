@@ -105,14 +105,14 @@ __device__ __forceinline__ void tile_store(cplx* amp, const PassDesc& pd, const 
 }
 // Load the tile in the group-G layout.  Support tracking (PassDesc::zero_mask): amplitudes with a bit of zero_mask set
 // are zero by construction and their memory is never read (after a reset it has not even been written).
-// With a fused remap (PassDesc::remap_n > 0) every amplitude comes from the buffer -- this rank's input or a partner
+// With a fused remap (PassDesc::remap_on) every amplitude comes from the buffer -- this rank's input or a partner
 // rank's, over NVLink -- that held it before the global<->local qubit swap(s); zero_mask then applies to the source index.
 // `toff`: the thread's offset in the group-G layout (tid_offset_arith at the start of a kernel, else the stash).
 template <int G>
 __device__ __forceinline__ void tile_load(const cplx* amp, const PassDesc& pd, cplx (&a)[NREG], uint64_t cbase, uint64_t toff) {
     const IoAddr io = io_addr<G>(pd, cbase, toff);
     const uint64_t zmask = pd.zero_mask;
-    if (pd.remap_n == 0) {
+    if (!pd.remap_on) {
         const cplx* p0 = amp + io.i0;
         const bool thread_zero = (toff & zmask) != 0;
         const int zregs = pd.zero_regbits;
@@ -142,7 +142,7 @@ template <int G>
 __device__ __forceinline__ void tile_prefetch_issue(cplx* tile, const cplx* amp, const PassDesc& pd, uint64_t cbase, int tid, uint64_t toff) {
     const IoAddr io = io_addr<G>(pd, cbase, toff);
     cplx* sp = tile + smem_slot(stage_idx(G, tid, 0));
-    if (pd.remap_n == 0) {
+    if (!pd.remap_on) {
         const cplx* p0 = amp + io.i0;
 #pragma unroll
         for (int j = 0; j < NREG; ++j) cp_async16(sp + smem_slot(j << (REG_BITS * G)), p0 + io_reg_offset(io, j));

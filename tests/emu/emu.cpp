@@ -31,25 +31,11 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits, uint64_t z
     PassDesc pd = pass.desc;
     uint64_t lmask = 0;
     if (rm && !rm->pairs.empty()) {
-        if (rm->pairs.size() > (size_t)MAX_REMAP) throw std::runtime_error("emu: too many fused swaps");
-        pd.remap_n = (int8_t)rm->pairs.size();
-        uint64_t rconst = 0;
-        for (size_t k = 0; k < rm->pairs.size(); ++k) {
-            const int j = rm->pairs[k].first - pd.n_local, lq = rm->pairs[k].second;
-            pd.remap_lq[k] = (int8_t)lq;
-            lmask |= 1ull << lq;
-            rconst |= (uint64_t)((rm->rank >> j) & 1) << lq;
-        }
-        pd.remap_lmask = lmask;
-        pd.remap_const = rconst;
-        for (unsigned sel = 0; sel < (1u << rm->pairs.size()); ++sel) {
-            int r = rm->rank;
-            for (size_t k = 0; k < rm->pairs.size(); ++k) {
-                const int j = rm->pairs[k].first - pd.n_local;
-                r = (r & ~(1 << j)) | (int)((sel >> k) & 1u) << j;
-            }
-            pd.remap_src[sel] = rm->snapshot + (uint64_t)r * rm->chunk;
-        }
+        RemapPlan rp;
+        if (!compose_remap(rm->pairs, pd.n_local, rm->rank, &rp)) throw std::runtime_error("emu: fused remap over too many positions");
+        apply_remap(rp, &pd);
+        lmask = rp.lmask;
+        for (int sel = 0; sel < (1 << rp.n_sel); ++sel) pd.remap_src[sel] = rm->snapshot + (uint64_t)rp.src_rank[sel] * rm->chunk;
     }
     pd.rank_bits = rank_bits;
     pd.tables = pass.tables.data();
@@ -63,7 +49,15 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits, uint64_t z
     for (int k = 0; k < REG_BITS; ++k) if ((zero_mask >> pd.tile_q[IO_GROUP * REG_BITS + k]) & 1ull) zregs |= 1 << k;
     pd.zero_regbits = (int8_t)zregs;
     const uint64_t skip = zero_mask & ~tile_mask & ~lmask;
-    const bool sparse = skip != 0 && fill_cta_runs_sparse(pd, skip);
+    bool sparse;
+    if (pd.remap_on) {      // engine.cu run_pass: selector bits lowest in the CTA index
+        uint64_t sel_bits = 0;
+        for (int k = 0; k < pd.remap_n; ++k) sel_bits |= 1ull << pd.remap_lq[k];
+        sparse = fill_cta_runs_ex(pd, skip, sel_bits);
+    } else {
+        sparse = skip != 0 && fill_cta_runs_sparse(pd, skip);
+    }
+    std::vector<bool> visited((size_t)1 << (pd.n_local > TILE_BITS ? pd.n_local - TILE_BITS : 0), false);
     const uint64_t ctas = 1ull << pd.n_cta_bits;
     if (!sparse && pd.n_cta_bits != pd.n_local - TILE_BITS) throw std::runtime_error("emu: n_cta_bits of the full grid");
     std::vector<cplx> tile(TILE_SLOTS);
@@ -73,6 +67,12 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits, uint64_t z
         const uint64_t base = sparse ? cta_base_runs(pd, cta) : cta_base(pd, cta);
         if (cta_base_runs(pd, cta) != base) throw std::runtime_error("emu: run-compressed CTA base differs");
         if (base & tile_mask) throw std::runtime_error("emu: CTA base overlaps the tile");
+        {   // every tile is visited at most once, whatever the order of the CTA index bits
+            uint64_t key = 0; int kb = 0;
+            for (int q = 0; q < pd.n_local; ++q) if (!((tile_mask >> q) & 1ull)) key |= ((base >> q) & 1ull) << kb++;
+            if (visited[key]) throw std::runtime_error("emu: a tile is visited twice");
+            visited[key] = true;
+        }
         if (base & zero_mask & ~lmask) { if (sparse) throw std::runtime_error("emu: sparse grid visits an all-zero tile"); continue; }
         const uint64_t gbase = base | pd.rank_bits;
         if (pd.n_tab > MAX_TABLE_OPS || pd.n_ops >= MAX_OPS_PER_PASS || (size_t)pd.n_ops != pass.ops.size())
@@ -83,7 +83,7 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits, uint64_t z
             const bool thread_zero = (tid_offset(pd, IO_GROUP, tid) & zero_mask) != 0;
             for (int j = 0; j < NREG; ++j) {
                 const uint64_t i = base + tile_offset(pd, stage_idx(IO_GROUP, tid, j));
-                if (pd.remap_n == 0) regs[tid][j] = (thread_zero || (j & pd.zero_regbits)) ? cplx{0.0, 0.0} : amp[i];
+                if (!pd.remap_on) regs[tid][j] = (thread_zero || (j & pd.zero_regbits)) ? cplx{0.0, 0.0} : amp[i];
                 else {      // tile_kernel.cuh tile_load, remap path
                     const uint64_t src = remap_index(pd, i);
                     regs[tid][j] = (src & zero_mask) ? cplx{0.0, 0.0} : pd.remap_src[remap_sel(pd, i)][src];
@@ -217,7 +217,7 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
         auto fused_pass = [&](const Pass& p) {
             snapshot.assign(amp, amp + ((uint64_t)world << n_local));
             uint64_t lmask = 0;
-            for (auto& pr : remap) lmask |= 1ull << pr.second;
+            { RemapPlan rp0; compose_remap(remap, n_local, 0, &rp0); if (!rp0.on) remap.clear(); lmask = rp0.lmask; }
             for (int r = 0; r < world; ++r) {
                 RemapEmu rm; rm.pairs = remap; rm.snapshot = snapshot.data(); rm.rank = r; rm.chunk = chunk;
                 run_pass(amp + (uint64_t)r * chunk, p, (uint64_t)r << n_local, ~support[r] & local_mask, &rm);
@@ -235,10 +235,9 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
             if (st.kind == DistStep::GLOBAL_SWAP && g_fused && n_local >= TILE_BITS) {
                 ++n_swap;
                 if (st.gq < n_local || st.gq >= n_qubits || st.lq < 0 || st.lq >= n_local) throw std::runtime_error("emu: bad swap");
-                bool disjoint = remap.size() < (size_t)MAX_REMAP;
-                for (auto& pr : remap) if (pr.first == st.gq || pr.second == st.lq) disjoint = false;
-                if (!disjoint) flush_remap();
                 remap.push_back({st.gq, st.lq});
+                RemapPlan probe;
+                if (!compose_remap(remap, n_local, 0, &probe)) { remap.pop_back(); flush_remap(); remap.push_back({st.gq, st.lq}); }
                 continue;
             }
             if (st.kind == DistStep::GLOBAL_SWAP) {

@@ -96,6 +96,13 @@ def emu_run(oracle_circ: OracleCircuit, world: int = 1, state=None, fuse: bool =
 
 
 def rel_err(a: np.ndarray, b: np.ndarray) -> float:
-    """max |a-b| relative to the largest magnitude (amplitudes of a normalised state)."""
+    """max |a-b| relative to the LARGEST magnitude of the reference state: the reading of "1e-12 relative" for the
+    amplitudes of a normalised state (an amplitude that cancels to ~0 has no meaningful relative error of its own).
+    `l2_err` is the second, norm-wise metric; the parity tests at config scale assert both."""
     scale = max(np.abs(b).max(), 1e-300)
     return float(np.abs(a - b).max() / scale)
+
+
+def l2_err(a: np.ndarray, b: np.ndarray) -> float:
+    """||a - b||_2 / ||b||_2."""
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))

@@ -78,6 +78,7 @@ def test_every_target_every_control(n):
 def test_random_circuits(n, gates, seed):
     g, o = both(n, lambda c: circuits.random_circuit(c, n, gates, seed))
     assert rel_err(g.state_numpy(), o.amplitudes()) < TOL
+    assert l2_err(g.state_numpy(), o.amplitudes()) < TOL
     assert abs(g.norm() - 1.0) < 1e-12
     st = g.stats()
     assert st["gates_applied"] == gates and st["tile_passes"] < gates and st["kernel_launches"] > 0
