@@ -10,7 +10,7 @@ import pytest
 from damavand_b200 import circuits
 from oracle import oracle
 from oracle.oracle import OracleCircuit
-from tests.helpers import Recorder, rel_err
+from tests.helpers import Recorder, l2_err, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12

@@ -134,6 +134,23 @@ def test_distributed_planner_with_fewer_local_than_rank_index_qubits():
         _check(c, 1 << (n - n_local))
 
 
+def test_distributed_sixteen_ranks_split_their_remaps():
+    """Four rank-index qubits: a swap round can involve more positions than one fused remap takes (three rank-index,
+    three local), so the engine must split it -- and a restore that cycles rank-index positions composes into one
+    load with bit moves between local positions."""
+    n = 16
+    circ = OracleCircuit(n)
+    circuits.random_circuit(circ, n, 240, seed=160)
+    stats = _check(circ, 16)
+    assert stats["swaps"] >= 4
+    circ = OracleCircuit(n)
+    for q in range(n):
+        circ.add_hadamard_gate(q)
+    for q in (15, 14, 13, 12, 15, 13):      # every rank-index qubit in turn, twice
+        circ.add_rotation_x_gate(q, 0.3 + 0.1 * q); circ.add_cnot_gate(q, (q + 5) % n)
+    _check(circ, 16)
+
+
 def test_distributed_small_chunks_use_simple_kernel():
     circ = OracleCircuit(8)
     circuits.random_circuit(circ, 8, 120, seed=3)
