@@ -30,7 +30,15 @@ pub struct dvd_stats {
     pub gate_algorithmic_bytes: c_double,
     pub plan_cache_hits: i64,
     pub jit_launches: i64,
+    pub remap_passes: i64,
+    pub remap_bytes_in: c_double,
+    pub remap_ms: c_double,
+    pub swap_ms: c_double,
+    pub pass_fp64_instr: c_double,
 }
+
+pub const DVD_SAMPLER_TREE: c_int = 0;
+pub const DVD_SAMPLER_SEQUENTIAL: c_int = 1;
 
 pub const DVD_NCCL_ID_BYTES: usize = 128;
 
@@ -77,11 +85,16 @@ extern "C" {
     // circuit_metrics.rs:12-92
     pub fn dvd_fidelity(a: *mut dvd_state, b: *mut dvd_state, out: *mut c_double) -> c_int;
     pub fn dvd_copy_state(dst: *mut dvd_state, src: *mut dvd_state) -> c_int;
+    // circuit.rs:753-769: the first state of get_fidelity_between_two_states_with_parameters stays resident
+    pub fn dvd_snapshot(src: *mut dvd_state, out: *mut *mut dvd_state) -> c_int;
+    // utils.rs:270-274: 1 = the reference's strictly sequential cumulative sums (<= 30 local qubits), 0 = pairwise tree
+    pub fn dvd_set_sampler(s: *mut dvd_state, order: c_int) -> c_int;
 
     pub fn dvd_num_qubits(s: *const dvd_state) -> c_int;
     pub fn dvd_num_local_qubits(s: *const dvd_state) -> c_int;
     pub fn dvd_rank(s: *const dvd_state) -> c_int;
     pub fn dvd_world(s: *const dvd_state) -> c_int;
+    pub fn dvd_device(s: *const dvd_state) -> c_int;
     pub fn dvd_get_stats(s: *const dvd_state, out: *mut dvd_stats) -> c_int;
     pub fn dvd_stats_reset(s: *mut dvd_state) -> c_int;
     pub fn dvd_timer_begin(s: *mut dvd_state) -> c_int;
@@ -94,4 +107,6 @@ extern "C" {
         s: *mut dvd_state, compiled: *mut i64, failed: *mut i64, pending: *mut i64,
         compile_seconds: *mut c_double, last_error: *mut c_char, cap: i64,
     ) -> c_int;
+    // out[0] structures still being measured, out[1..3] structures per chosen kernel form, out[4..6] launches per form
+    pub fn dvd_jit_forms(out: *mut i64) -> c_int;
 }

@@ -169,3 +169,24 @@ def test_jit_disk_cache(tmp_path, monkeypatch):
     assert L.dvd_jit_debug_compile(src) == a and files[0].stat().st_size == a
     monkeypatch.setenv("DVD_JIT_CACHE_DIR", "")
     assert L.dvd_jit_debug_compile(src + b" ") == a and len(list((tmp_path / "jit").glob("*"))) == 1
+
+
+def test_rust_ffi_crate_declares_the_same_abi():
+    """ffi/src/lib.rs cannot be compiled here (no cargo in the image): at least keep it in step with the header --
+    every entry point of include/damavand_b200.h (the host-only planner / generator inspection calls aside) is declared,
+    and dvd_stats has the same fields in the same order."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "damavand_b200.h")).read()
+    rs = open(os.path.join(root, "ffi", "src", "lib.rs")).read()
+    names = set(re.findall(r"^(?:int|double|int64_t|const char\*)\s+(dvd_\w+)\(", hdr, flags=re.M))
+    assert len(names) > 35
+    debug_only = {n for n in names if "debug" in n}
+    missing = sorted(n for n in names - debug_only if f"pub fn {n}(" not in rs)
+    assert missing == [], missing
+    c_fields = re.findall(r"^\s+(?:int64_t|double)\s+(\w+);", hdr[hdr.index("typedef struct {"):hdr.index("} dvd_stats;")], flags=re.M)
+    rs_fields = re.findall(r"pub (\w+): (?:i64|c_double),", rs[rs.index("pub struct dvd_stats"):rs.index("pub const DVD_SAMPLER_TREE")])
+    assert c_fields == rs_fields and len(c_fields) >= 16
+    from damavand_b200 import _lib
+    assert [f for f, _ in _lib.Stats._fields_] == c_fields
