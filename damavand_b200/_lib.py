@@ -42,6 +42,7 @@ class Stats(ctypes.Structure):
         ("remap_ms", ctypes.c_double),
         ("swap_ms", ctypes.c_double),
         ("pass_fp64_instr", ctypes.c_double),
+        ("store_remap_passes", ctypes.c_int64),
     ]
 
     def as_dict(self):

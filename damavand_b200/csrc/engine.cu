@@ -90,6 +90,8 @@ struct dvd_state {
     std::unique_ptr<Pass> ident_pass;       // empty pass for swaps with no gate pass to ride on
     cplx* d_ident_tab = nullptr;
     cplx* peer_cur(int r) const { return peer_base[r] + (size_t)cur * n_amps; }
+    cplx* peer_other(int r) const { return peer_base[r] + (size_t)(1 - cur) * n_amps; }
+    bool store_remap = true;      // DVD_STORE_REMAP=0: the layout restore always takes a pass of its own
     dvd_stats stats;
     bool unfused = false;
     // Support tracking: after a reset only amplitude 0 is stored; `support` holds the local qubits that a
@@ -106,6 +108,8 @@ struct dvd_state {
         std::vector<DistStep> steps;
         std::vector<std::vector<Pass>> plans;
         size_t total_tabs = 0;
+        int store_step = -1;                              // planner.h DistPlan: the swaps that end the schedule ride on
+        std::vector<std::pair<int, int>> store_swaps;     //   the store of the last pass of steps[store_step]
         bool valid = false;
     } cache;
     bool plan_cache = true;
@@ -211,6 +215,8 @@ static int map_peers(dvd_state* s) {
     // both chunks in place and every partner mapped: global<->local swaps ride on the next pass's load
     const char* fr = getenv("DVD_FUSED_REMAP");
     s->fused_remap = s->peer_swap && s->buf[1] != nullptr && !(fr && atoi(fr) == 0);
+    const char* sr = getenv("DVD_STORE_REMAP");
+    s->store_remap = !(sr && atoi(sr) == 0);
     return DVD_OK;
 }
 
@@ -511,33 +517,39 @@ static int flush_impl(dvd_state* s) {
     if (hit) s->stats.plan_cache_hits++;
     if (!hit) {
         s->cache.valid = false;
+        s->cache.store_step = -1;
+        s->cache.store_swaps.clear();
         std::vector<DistStep> steps;
+        // every local step is planned up front so that all phase tables go to the device in one copy; the op
+        // lists travel as kernel parameters
+        std::vector<std::vector<Pass>> plans;
+        size_t total_tabs = 0;
         try {
             // level 0 (fused mode only): CNOT-conjugated diagonal runs -> parity phases
             const std::vector<HostGate> fused = tiled ? fuse_diagonal_runs(s->pending) : s->pending;
-            if (s->world > 1) {
+            if (s->world > 1 && tiled) {
+                // the schedule with the fewest passes among the tail-deferral thresholds, with its pass plans
+                DistPlan dp = plan_distributed_tuned(fused, s->n_qubits, s->n_local, s->perm, /*restore_identity=*/true,
+                                                     /*store_side=*/s->fused_remap && s->store_remap, s->opt);
+                steps = std::move(dp.steps);
+                plans = std::move(dp.plans);
+                s->cache.store_step = dp.store_step;
+                s->cache.store_swaps = std::move(dp.store_swaps);
+            } else if (s->world > 1) {
                 steps = plan_distributed(fused, s->n_qubits, s->n_local, s->perm, /*restore_identity=*/true);
             } else {
                 DistStep st; st.kind = DistStep::LOCAL_GATES; st.gates = fused;
                 steps.push_back(std::move(st));
             }
-        } catch (const std::exception& e) {
-            return fail(DVD_ERR_INTERNAL, std::string("planner: ") + e.what());
-        }
-        // plan every local step up front so that all phase tables go to the device in one copy; the op
-        // lists travel as kernel parameters
-        std::vector<std::vector<Pass>> plans(steps.size());
-        size_t total_tabs = 0;
-        if (tiled) {
-            try {
+            plans.resize(steps.size());
+            if (tiled)
                 for (size_t i = 0; i < steps.size(); ++i)
                     if (steps[i].kind == DistStep::LOCAL_GATES) {
-                        plans[i] = plan_local(steps[i].gates, s->n_local, s->n_qubits, s->opt);
+                        if (s->world == 1) plans[i] = plan_local(steps[i].gates, s->n_local, s->n_qubits, s->opt);
                         for (auto& p : plans[i]) total_tabs += p.tables.size();
                     }
-            } catch (const std::exception& e) {
-                return fail(DVD_ERR_INTERNAL, std::string("planner: ") + e.what());
-            }
+        } catch (const std::exception& e) {
+            return fail(DVD_ERR_INTERNAL, std::string("planner: ") + e.what());
         }
         s->cache.steps = std::move(steps);
         s->cache.plans = std::move(plans);
@@ -576,7 +588,16 @@ static int flush_impl(dvd_state* s) {
     // Global<->local swaps waiting to ride on the next pass's load (fused remap): disjoint (gq, lq) pairs.
     std::vector<std::pair<int, int>> remap;
     bool fused_any = false;
-    auto run_pass = [&](Pass& p, const cplx* d_tab) -> int {
+    // store_swaps != nullptr: the pass STORES through the remap these swaps compose into (the layout restore riding on the
+    // last gate pass): it reads this rank's buffer `cur` in place and writes buffer 1 - cur of this rank and of its partners
+    auto run_pass = [&](Pass& p, const cplx* d_tab, const std::vector<std::pair<int, int>>* store_swaps = nullptr) -> int {
+        RemapPlan sp;
+        if (store_swaps) {
+            if (!remap.empty()) return fail(DVD_ERR_INTERNAL, "a pass cannot carry swaps on its load and on its store");
+            if (!compose_remap(*store_swaps, s->n_local, s->rank, &sp, /*inverse=*/true)) return fail(DVD_ERR_INTERNAL, "store-side remap over too many positions");
+            if (!sp.on) store_swaps = nullptr;      // the swaps cancel: a plain pass
+            else TRY(materialize(s));               // a store-side pass writes every amplitude of the new layout: no implied zeros
+        }
         PassParams& pp = s->pass_params;
         pp.pd = p.desc;
         pp.pd.rank_bits = s->rank_bits;
@@ -607,9 +628,17 @@ static int flush_impl(dvd_state* s) {
             // previous fused pass, which read it, lies before this barrier on every rank)
             TRY(stream_barrier(s));
         }
+        if (store_swaps) {
+            apply_remap(sp, &pp.pd, /*store_side=*/true);
+            for (int sel = 0; sel < (1 << sp.n_sel); ++sel)
+                pp.pd.remap_src[sel] = sp.src_rank[sel] == s->rank ? s->buf[1 - s->cur] : s->peer_other(sp.src_rank[sel]);
+            // nobody still reads the buffers this pass overwrites on every rank: the last pass whose load read them lies
+            // before this barrier.  The barrier that ends the flush makes the stores of all ranks visible to their owners.
+            TRY(stream_barrier(s));
+        }
         // tiles whose fixed bits make every source amplitude zero are not launched (bits of the swapped-in
         // positions are rank-index bits of the source: never implied)
-        if (pp.pd.remap_on) {
+        if (pp.pd.remap_on || pp.pd.remap_st) {
             // the index bits that select the source rank become the lowest bits of the CTA index: tiles fetched over
             // NVLink and tiles fetched from local HBM alternate in launch order (on failure the default order stays)
             uint64_t sel_bits = 0;
@@ -622,7 +651,7 @@ static int flush_impl(dvd_state* s) {
         pp.pd.tid_off = reinterpret_cast<const uint64_t*>(d_tab + p.tid_off_slot);
         std::memcpy(pp.ops, p.ops.data(), p.ops.size() * sizeof(DevOp));
         dvd_state::RemapTimer* tm = nullptr;
-        if (!remap.empty()) {
+        if (!remap.empty() || store_swaps) {
             TRY(timer_acquire(s, false, &tm));
             if (tm) CU(cudaEventRecord(tm->t0, s->stream));
         }
@@ -642,12 +671,14 @@ static int flush_impl(dvd_state* s) {
             const double tiles_bytes = (double)(1ull << pp.pd.n_cta_bits) * TILE_AMPS * sizeof(cplx);
             s->stats.pass_bytes += tiles_bytes * (1.0 + 1.0 / (double)(1ull << __builtin_popcountll(zm & tile_mask & ~lmask)));
         }
-        if (!remap.empty()) {
+        if (!remap.empty() || store_swaps) {
+            const RemapPlan& mp = store_swaps ? sp : rp;
             const double chunk = (double)s->n_amps * sizeof(cplx);
             int local_sel = 0;
-            for (int sel = 0; sel < (1 << rp.n_sel); ++sel) local_sel += rp.src_rank[sel] == s->rank;
-            const double moved = chunk * (1.0 - (double)local_sel / (double)(1 << rp.n_sel));   // pulled over NVLink (and served to the partners)
-            s->stats.global_swaps += (int64_t)remap.size();
+            for (int sel = 0; sel < (1 << mp.n_sel); ++sel) local_sel += mp.src_rank[sel] == s->rank;
+            const double moved = chunk * (1.0 - (double)local_sel / (double)(1 << mp.n_sel));   // pulled (pushed) over NVLink
+            if (store_swaps) { for (auto& sw : *store_swaps) s->stats.global_swaps += sw.first >= s->n_local; lmask = ~0ull; s->stats.store_remap_passes++; }
+            else s->stats.global_swaps += (int64_t)remap.size();
             s->stats.swap_bytes_sent += (int64_t)moved;
             s->stats.remap_passes++;
             s->stats.remap_bytes_in += moved;
@@ -692,8 +723,10 @@ static int flush_impl(dvd_state* s) {
             continue;
         }
         if (tiled) {
-            for (auto& p : plans[i]) {
-                TRY(run_pass(p, d_tabs + tat));
+            for (size_t k = 0; k < plans[i].size(); ++k) {
+                Pass& p = plans[i][k];
+                const bool store_here = (int)i == s->cache.store_step && k + 1 == plans[i].size();
+                TRY(run_pass(p, d_tabs + tat, store_here ? &s->cache.store_swaps : nullptr));
                 tat += p.tables.size();
             }
         } else {
@@ -1207,8 +1240,10 @@ int64_t dvd_plan_distributed_debug(int n_total, int n_local, const dvd_gate* gat
                                    int32_t* perm_io, int restore_identity, int32_t* out, int64_t cap) {
     try {
         std::vector<int> perm(perm_io, perm_io + n_total);
-        std::vector<DistStep> steps = plan_distributed(to_host_gates(gates, n_gates), n_total, n_local, perm,
-                                                       restore_identity != 0);
+        // the schedule the engine runs (tail deferral included; the restore stays in the step list)
+        std::vector<DistStep> steps = n_local >= TILE_BITS
+            ? plan_distributed_tuned(to_host_gates(gates, n_gates), n_total, n_local, perm, restore_identity != 0, /*store_side=*/false, PlanOptions()).steps
+            : plan_distributed(to_host_gates(gates, n_gates), n_total, n_local, perm, restore_identity != 0);
         for (int q = 0; q < n_total; ++q) perm_io[q] = perm[q];
         std::vector<int32_t> v;
         v.push_back((int32_t)steps.size());

@@ -394,7 +394,7 @@ bool jit_launch(const Pass& p, int mode, int device, cplx* amp, const PassParams
             harvest(d);
             const bool dense_full = ring_ok;
             // (a pass whose load carries a fused remap pulls half its tile over NVLink: not a fair timing sample)
-            if (dense_full && !pp.pd.remap_on && d.best_dense < 0 && (d.sig < 0 || d.sig == pp.pd.n_cta_bits)) {
+            if (dense_full && !pp.pd.remap_on && !pp.pd.remap_st && d.best_dense < 0 && (d.sig < 0 || d.sig == pp.pd.n_cta_bits)) {
                 // measuring: the usable candidate with the fewest timings (finished or in flight) runs next
                 int n_have[FORM_COUNT];
                 for (int f = 0; f < FORM_COUNT; ++f) n_have[f] = (int)d.ms[f].size();
@@ -427,8 +427,9 @@ bool jit_launch(const Pass& p, int mode, int device, cplx* amp, const PassParams
                 }
             }
             if (!pick) {
-                form = dense_full ? (d.best_dense >= 0 ? d.best_dense : FORM_CLASSIC2)
-                                  : (d.best_classic >= 0 ? d.best_classic : FORM_CLASSIC2);
+                // (the ring form is the wrong tool over NVLink: 55 against 28 ms per fused pass on 2 x B200)
+                form = dense_full && !pp.pd.remap_on && !pp.pd.remap_st ? (d.best_dense >= 0 ? d.best_dense : FORM_CLASSIC2)
+                                                                         : (d.best_classic >= 0 ? d.best_classic : FORM_CLASSIC2);
                 pick = usable(form);
                 if (!pick && form != FORM_CLASSIC2) { form = FORM_CLASSIC2; pick = usable(form); }
             }

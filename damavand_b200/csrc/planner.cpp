@@ -1,5 +1,6 @@
 // planner.cpp -- see planner.h.  Pure host C++.
 #include "planner.h"
+#include <cstdlib>
 
 #include <algorithm>
 #include <climits>
@@ -652,29 +653,36 @@ struct StageEmitter {
 
 }  // namespace
 
-static std::vector<Pass> plan_local_impl(const std::vector<HostGate>& gates_in, int n_local, int n_total, const PlanOptions& opt);
+static std::vector<Pass> plan_local_impl(const std::vector<HostGate>& gates_in, int n_local, int n_total, const PlanOptions& opt,
+                                         std::vector<int>* pass_of_gate);
 
 // Tile relabelling pays when it saves passes (chain-like circuits: hea28 80 -> 55); where it does not (random32,
 // qft30: the same pass count either way) its extra swap gates only add transposes and make untouched qubits look
 // touched to the support tracking -- measured on B200: random32 from a reset 274 -> 329 ms.  So both plans are made
 // (host time, cached with the plan) and relabelling is kept only if it needs strictly fewer passes.
-std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, int n_total, const PlanOptions& opt) {
-    if (!opt.relabel) return plan_local_impl(gates, n_local, n_total, opt);
+std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, int n_total, const PlanOptions& opt,
+                             std::vector<int>* pass_of_gate) {
+    if (!opt.relabel) return plan_local_impl(gates, n_local, n_total, opt, pass_of_gate);
     PlanOptions plain = opt;
     plain.relabel = false;
-    std::vector<Pass> a = plan_local_impl(gates, n_local, n_total, plain);
-    if (a.size() <= 1) return a;
-    std::vector<Pass> b = plan_local_impl(gates, n_local, n_total, opt);
-    return b.size() < a.size() ? b : a;
+    std::vector<int> pa, pb;
+    std::vector<Pass> a = plan_local_impl(gates, n_local, n_total, plain, pass_of_gate ? &pa : nullptr);
+    if (a.size() > 1) {
+        std::vector<Pass> b = plan_local_impl(gates, n_local, n_total, opt, pass_of_gate ? &pb : nullptr);
+        if (b.size() < a.size()) { if (pass_of_gate) pass_of_gate->swap(pb); return b; }
+    }
+    if (pass_of_gate) pass_of_gate->swap(pa);
+    return a;
 }
 
 static std::vector<Pass> plan_local_impl(const std::vector<HostGate>& gates_in, int n_local, int n_total,
-                                         const PlanOptions& opt) {
+                                         const PlanOptions& opt, std::vector<int>* pass_of_gate) {
     std::vector<HostGate> gates = gates_in;   // relabelling appends swap gates and renames qubits of the gates still to run
     if (n_local < TILE_BITS) throw std::runtime_error("plan_local: n_local < TILE_BITS");
     if (n_total > 62) throw std::runtime_error("plan_local: too many qubits");
     std::vector<Pass> passes;
     const int G = (int)gates.size();
+    if (pass_of_gate) pass_of_gate->assign((size_t)G, -1);
     const uint64_t all = n_total >= 64 ? ~0ull : ((1ull << n_total) - 1);
     for (int i = 0; i < G; ++i) {
         const HostGate& g = gates[i];
@@ -947,6 +955,8 @@ static std::vector<Pass> plan_local_impl(const std::vector<HostGate>& gates_in, 
         gate_budget = opt.max_ops_per_pass;
         pass.finish_tables();
         passes.push_back(std::move(pass));
+        if (pass_of_gate)
+            for (int gi : taken) if (gi < G) (*pass_of_gate)[gi] = (int)passes.size() - 1;
         // the pass is accepted: its swaps are now part of the state, rename the qubits of every gate still to run
         for (auto& sw : swaps)
             for (int gi : rest) {
@@ -996,7 +1006,12 @@ int estimate_fp64(const std::vector<DevOp>& ops) {
     return total;
 }
 
-bool compose_remap(const std::vector<std::pair<int, int>>& swaps, int n_local, int rank, RemapPlan* out) {
+void append_local_swap_gates(int a, int b, std::vector<HostGate>* out) {
+    const double x[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+    out->push_back(make_gate(b, a, x, -1)); out->push_back(make_gate(a, b, x, -1)); out->push_back(make_gate(b, a, x, -1));
+}
+
+bool compose_remap(const std::vector<std::pair<int, int>>& swaps, int n_local, int rank, RemapPlan* out, bool inverse) {
     // at[p] = the position whose (old) bit sits at position p after the swaps: new_bit[p] = old_bit[at[p]]
     std::vector<int> pos;      // positions involved, in order of first appearance
     auto idx_of = [&](int p) {
@@ -1015,8 +1030,11 @@ bool compose_remap(const std::vector<std::pair<int, int>>& swaps, int n_local, i
     std::vector<int> G, L;
     for (int p : pos) (p >= n_local ? G : L).push_back(p);
     rp.n_global = (int)G.size(); rp.n_local_pos = (int)L.size();
-    if ((int)G.size() > MAX_REMAP || (int)L.size() > MAX_REMAP) return false;
-    auto where = [&](int q) {          // the position the old bit q ends up at
+    if ((int)G.size() > MAX_REMAP || (int)L.size() > MAX_REMAP_LOCAL) return false;
+    // load side: the old bit q ends up at position where(q), so the source of new index i' has old_bit[q] = new_bit[where(q)];
+    // store side: the new bit at position p is old_bit[at[p]], so the destination of old index i has new_bit[p] = old_bit[at[p]]
+    auto where = [&](int q) {
+        if (inverse) { for (size_t k = 0; k < pos.size(); ++k) if (pos[k] == q) return at[k]; return q; }
         for (size_t k = 0; k < pos.size(); ++k) if (at[k] == q) return pos[k];
         return q;
     };
@@ -1051,8 +1069,9 @@ bool compose_remap(const std::vector<std::pair<int, int>>& swaps, int n_local, i
     return true;
 }
 
-void apply_remap(const RemapPlan& rp, PassDesc* pd) {
-    pd->remap_on = rp.on ? 1 : 0;
+void apply_remap(const RemapPlan& rp, PassDesc* pd, bool store_side) {
+    pd->remap_on = (rp.on && !store_side) ? 1 : 0;
+    pd->remap_st = (rp.on && store_side) ? 1 : 0;
     pd->remap_n = (int8_t)rp.n_sel;
     for (int k = 0; k < rp.n_sel; ++k) pd->remap_lq[k] = (int8_t)rp.sel_lq[k];
     pd->remap_n_mv = (int8_t)rp.n_mv;
@@ -1074,7 +1093,8 @@ Pass make_identity_pass(int n_local) {
 
 // ---------------------------------------------------------------------------------------------------
 std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n_total, int n_local,
-                                       std::vector<int>& perm, bool restore_identity) {
+                                       std::vector<int>& perm, bool restore_identity, bool local_swap_steps,
+                                       const PlanOptions* tail_opt, int defer_max_ops) {
     std::vector<DistStep> steps;
     const int G = (int)gates.size();
     std::vector<int> inv(n_total);  // physical -> logical
@@ -1101,6 +1121,12 @@ std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n
         while (mask) { const int q = __builtin_ctzll(mask); mask &= mask - 1; r |= 1ull << perm[q]; }
         return r;
     };
+    auto mapped = [&](const HostGate& g) {
+        HostGate pg = g;
+        pg.tmask = map_mask(g.tmask);
+        pg.cmask = map_mask(g.cmask);
+        return pg;
+    };
 
     // List scheduling over LOGICAL qubits: run everything that is executable with the current layout
     // and commutes past what had to wait (same rule as the pass level), and only then pay for swaps.
@@ -1108,23 +1134,44 @@ std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n
     std::vector<int> pending(G);
     for (int i = 0; i < G; ++i) pending[i] = i;
     const int first_victim = n_local > 8 ? 5 : 0;    // keep swap segments >= 512 B when there is a choice
+    const bool defer_tails = tail_opt && defer_max_ops > 0 && n_local >= TILE_BITS;
     while (!pending.empty()) {
+        size_t n_deferred = 0;       // pending[0 .. n_deferred): executable now, but kept for the next layout (see below)
         {
             Blocked blk;
-            std::vector<int> rest;
+            std::vector<int> rest, exec;
             for (int gi : pending) {
                 const HostGate& g = gates[gi];
                 const bool local = g.diag || perm[g.target()] < n_local;
-                if (local && blk.can_pass(g)) {
-                    HostGate pg = g;
-                    pg.tmask = map_mask(g.tmask);
-                    pg.cmask = map_mask(g.cmask);
-                    local_step().gates.push_back(pg);
-                } else {
-                    blk.skip(g);
-                    rest.push_back(gi);
+                if (local && blk.can_pass(g)) exec.push_back(gi);
+                else { blk.skip(g); rest.push_back(gi); }
+            }
+            // Tail deferral: what is executable under this layout rarely fills its last pass (random32 on 8 ranks: passes
+            // of 5, 3, 6 and 8 ops in front of the four swap rounds).  The gates of such a tail pass run just as well
+            // AFTER the swaps, inside the passes of the next layout -- they commute past everything that waits (that is
+            // how they got here) and the pass planner put the rest of this step in front of them -- provided their
+            // qubits stay local, which the eviction rule below sees to (they are the next uses).
+            if (defer_tails && !rest.empty() && exec.size() > 1) {
+                std::vector<HostGate> phys;
+                for (int gi : exec) phys.push_back(mapped(gates[gi]));
+                std::vector<int> pass_of;       // (the last step is never a LOCAL_GATES step here: this list IS the step)
+                const std::vector<Pass> passes = plan_local(phys, n_local, n_total, *tail_opt, &pass_of);
+                if (passes.size() >= 2 && (int)passes.back().ops.size() <= defer_max_ops) {
+                    const int last = (int)passes.size() - 1;
+                    std::vector<int> keep, tail;
+                    for (size_t k = 0; k < exec.size(); ++k) (pass_of[k] == last ? tail : keep).push_back(exec[k]);
+                    if (!tail.empty() && !keep.empty()) {
+                        exec.swap(keep);
+                        n_deferred = tail.size();
+                        std::vector<int> merged;
+                        merged.reserve(tail.size() + rest.size());
+                        for (int gi : tail) merged.push_back(gi);
+                        for (int gi : rest) merged.push_back(gi);
+                        rest.swap(merged);
+                    }
                 }
             }
+            for (int gi : exec) local_step().gates.push_back(mapped(gates[gi]));
             pending.swap(rest);
         }
         if (pending.empty()) break;
@@ -1132,7 +1179,8 @@ std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n
         std::vector<int> want;
         {
             Blocked blk;
-            for (int gi : pending) {
+            for (size_t k = n_deferred; k < pending.size(); ++k) {     // (deferred gates block nothing: they are executable)
+                const int gi = pending[k];
                 const HostGate& g = gates[gi];
                 if (!g.diag && perm[g.target()] >= n_local && blk.can_pass(g) &&
                     std::find(want.begin(), want.end(), g.target()) == want.end() &&
@@ -1176,12 +1224,90 @@ std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n
         for (int p = 0; p < n_local; ++p) {
             if (perm[p] == p) continue;
             const int x = perm[p];            // logical p lives at local position x
-            emit_local_cnot(p, x); emit_local_cnot(x, p); emit_local_cnot(p, x);
+            if (local_swap_steps) {
+                DistStep sw; sw.kind = DistStep::LOCAL_SWAP; sw.gq = p; sw.lq = x;
+                steps.push_back(std::move(sw));
+            } else {
+                emit_local_cnot(p, x); emit_local_cnot(x, p); emit_local_cnot(p, x);
+            }
             const int other = inv[p];
             perm[p] = p; perm[other] = x; inv[p] = p; inv[x] = other;
         }
     }
     return steps;
+}
+
+// The swaps that end `dp.steps` as the store-side remap of the last gate pass (planner.h: DistPlan::store_step).
+static bool take_store_side(DistPlan& dp, int n_local) {
+    int last = -1;
+    for (size_t i = 0; i < dp.steps.size(); ++i)
+        if (dp.steps[i].kind == DistStep::LOCAL_GATES && !dp.plans[i].empty()) last = (int)i;
+    if (last < 0) return false;
+    std::vector<std::pair<int, int>> pairs;
+    for (size_t i = (size_t)last + 1; i < dp.steps.size(); ++i) {
+        const DistStep& st = dp.steps[i];
+        if (st.kind == DistStep::LOCAL_GATES) { if (!st.gates.empty()) return false; continue; }
+        pairs.push_back({st.gq, st.lq});
+    }
+    if (pairs.empty()) return false;
+    RemapPlan rp;
+    if (!compose_remap(pairs, n_local, 0, &rp, /*inverse=*/true)) return false;
+    // a pass has one set of remap fields: the last pass must not be the one whose load carries the swaps in front of the step
+    const bool swaps_in_front = last > 0 && dp.steps[last - 1].kind != DistStep::LOCAL_GATES;
+    if (swaps_in_front && dp.plans[last].size() < 2) return false;
+    dp.steps.resize((size_t)last + 1);
+    dp.plans.resize((size_t)last + 1);
+    dp.store_step = last;
+    dp.store_swaps = std::move(pairs);
+    return true;
+}
+
+DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total, int n_local, std::vector<int>& perm,
+                                bool restore_identity, bool store_side, const PlanOptions& opt) {
+    static const int thresholds[] = {0, 6, 12, 20, 32};
+    const char* env = getenv("DVD_DEFER_TAILS");
+    const bool enabled = n_local >= TILE_BITS && !(env && atoi(env) == 0);
+    if (n_local < TILE_BITS) store_side = false;
+    DistPlan best;
+    std::vector<int> best_perm;
+    double best_cost = 0.0;
+    bool have = false;
+    for (int th : thresholds) {
+        if (opt.defer_max_ops >= 0) { if (th != thresholds[0]) break; th = opt.defer_max_ops; }
+        else if (th > 0 && !enabled) break;
+        DistPlan cand;
+        std::vector<int> p;
+        // with store_side the restore's local transpositions come as LOCAL_SWAP steps; if they cannot ride on the last
+        // pass's store after all, the schedule is made again with CNOT triples
+        for (int attempt = store_side ? 0 : 1; attempt < 2; ++attempt) {
+            cand = DistPlan();
+            p = perm;
+            cand.steps = plan_distributed(gates, n_total, n_local, p, restore_identity, /*local_swap_steps=*/attempt == 0, &opt, th);
+            cand.plans.resize(cand.steps.size());
+            cand.defer_max_ops = th;
+            for (size_t i = 0; i < cand.steps.size(); ++i)
+                if (cand.steps[i].kind == DistStep::LOCAL_GATES && n_local >= TILE_BITS) {
+                    cand.plans[i] = plan_local(cand.steps[i].gates, n_local, n_total, opt);
+                    cand.n_passes += (int)cand.plans[i].size();
+                }
+            if (attempt == 1 || take_store_side(cand, n_local)) break;
+        }
+        // cost in plain-pass units: a pass = 1; a round of swaps makes the load of the pass behind it (or the store of the
+        // last pass) NVLink-bound (measured on 8 x B200: 9.7 against 5.5 ms) and needs a pass of its own when no gate pass follows
+        double cost = cand.store_step >= 0 ? 0.75 : 0.0;
+        bool swaps_waiting = false;
+        for (size_t i = 0; i < cand.steps.size(); ++i) {
+            const DistStep& st = cand.steps[i];
+            if (st.kind == DistStep::GLOBAL_SWAP) { if (!swaps_waiting) cost += 0.75; swaps_waiting = true; continue; }
+            if (st.kind != DistStep::LOCAL_GATES) continue;
+            cost += (double)cand.plans[i].size();
+            if (!cand.plans[i].empty() || n_local < TILE_BITS) swaps_waiting = false;
+        }
+        if (swaps_waiting) cost += 1.0;
+        if (!have || cost < best_cost - 1e-9) { best = std::move(cand); best_perm = p; best_cost = cost; have = true; }
+    }
+    perm = best_perm;
+    return best;
 }
 
 }  // namespace dvd

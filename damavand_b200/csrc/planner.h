@@ -59,6 +59,7 @@ struct PlanOptions {
     int candidates = 12;       // tile candidates scored per pass (1 = first-come only)
     int max_ops_per_pass = 1024;   // gates taken into one pass (halved and retried while the op stream exceeds MAX_OPS_PER_PASS)
     bool macro_ops = true;     // fuse 4-op runs on the four register bits into one dispatch (OC_REALPH4, OC_TWHAD4)
+    int defer_max_ops = -1;    // distributed schedule (plan_distributed_tuned): tail-deferral threshold; -1 = the best of a few
     bool best_group = false;   // stage order: group with the most runnable work (true) or group of the first waiting gate
     bool relabel = true;       // tile relabelling (measured on B200 in round 2: hea28 80 -> 55 passes, 236 -> 204 ms; DVD_RELABEL=0 turns it off): the pinned low tile positions are
                                //   physical qubits [0, min_low), present in every tile; at the end of a pass the logical
@@ -78,8 +79,9 @@ std::vector<HostGate> fuse_diagonal_runs(const std::vector<HostGate>& gates);
 // Plan gates that are all executable locally: every non-diagonal gate has target < n_local.
 // Qubits >= n_local (rank-index qubits) may appear in control masks and in diagonal gates.
 // Requires n_local >= TILE_BITS.
+// pass_of_gate (optional): for every input gate, the index of the pass that executes it.
 std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, int n_total,
-                             const PlanOptions& opt);
+                             const PlanOptions& opt, std::vector<int>* pass_of_gate = nullptr);
 
 // fp64 instructions per thread of an op list (per-kind costs of tile_core.cuh: general 2x2 = 16 per pair, real / RX-like
 // = 8, Hadamard = 4, real + phase = 12, one complex multiply = 4).
@@ -91,34 +93,64 @@ Pass make_identity_pass(int n_local);
 
 // ---- distributed level ---------------------------------------------------------------------------
 struct DistStep {
-    enum Kind { LOCAL_GATES = 0, GLOBAL_SWAP = 1 } kind;
+    enum Kind { LOCAL_GATES = 0, GLOBAL_SWAP = 1, LOCAL_SWAP = 2 } kind;
     // LOCAL_GATES: gates rewritten to physical qubits, all locally executable
     std::vector<HostGate> gates;
     // GLOBAL_SWAP: exchange physical global qubit `gq` (>= n_local) with physical local qubit `lq`
+    // LOCAL_SWAP (only with local_swap_steps): exchange the physical LOCAL qubits `gq` and `lq` -- a transposition of the
+    //   layout restore, which the engine folds into a fused remap (or expands into three CNOTs)
     int gq = -1, lq = -1;
 };
 
 // A sequence of GLOBAL_SWAP steps composed into ONE fused remap (tile_core.cuh: PassDesc::remap_*), for rank `rank`.
-// Returns false when the sequence touches more than MAX_REMAP rank-index or more than MAX_REMAP local positions (the
+// Returns false when the sequence touches more than MAX_REMAP rank-index or more than MAX_REMAP_LOCAL local positions (the
 // caller then executes what it has and starts a new remap).  An identity composition gives on = false.
 struct RemapPlan {
     bool on = false;
     int n_sel = 0;
-    int sel_lq[MAX_REMAP];          // local positions of the NEW index whose bits select the source rank
-    int src_rank[1 << MAX_REMAP];   // source rank per selector value
+    int sel_lq[MAX_REMAP];          // local positions of the index whose bits select the other rank
+    int src_rank[1 << MAX_REMAP];   // the other rank per selector value
     int n_mv = 0;
-    int mv_from[MAX_REMAP], mv_to[MAX_REMAP];
+    int mv_from[MAX_REMAP_LOCAL], mv_to[MAX_REMAP_LOCAL];
     uint64_t lmask = 0, rconst = 0;
     int n_global = 0, n_local_pos = 0;
 };
-bool compose_remap(const std::vector<std::pair<int, int>>& swaps, int n_local, int rank, RemapPlan* out);
+// A swap is a pair of positions: (rank-index, local) or (local, local).  inverse = false: the LOAD-side form (where does
+// the amplitude at new index i come from); inverse = true: the STORE-side form (where does the amplitude at old index i go).
+bool compose_remap(const std::vector<std::pair<int, int>>& swaps, int n_local, int rank, RemapPlan* out, bool inverse = false);
 // Fill the remap fields of a pass descriptor (all but remap_src, which the caller derives from src_rank).
-void apply_remap(const RemapPlan& rp, PassDesc* pd);
+void apply_remap(const RemapPlan& rp, PassDesc* pd, bool store_side = false);
 
 // perm[logical] = physical, updated in place.  When `restore_identity` is set, trailing swaps bring
 // the layout back to perm[q] = q (needed before measure / sample / readback, whose semantics are
 // defined on the reference's contiguous-chunk layout, circuit.rs:135-136).
+// local_swap_steps: the transpositions of LOCAL positions that the restore needs are emitted as LOCAL_SWAP steps instead
+// of as CNOT triples inside a LOCAL_GATES step.
+// tail_opt + defer_max_ops > 0 (tail deferral): a step's executable gates are planned into passes, and when the last of
+// them has at most defer_max_ops ops its gates are kept back and run under the NEXT layout, after the swaps, where they
+// share passes with that layout's gates (they stay in front of everything that waits, so the order remains legal).
 std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n_total, int n_local,
-                                       std::vector<int>& perm, bool restore_identity);
+                                       std::vector<int>& perm, bool restore_identity, bool local_swap_steps = false,
+                                       const PlanOptions* tail_opt = nullptr, int defer_max_ops = 0);
+// The schedule the engine runs: plan_distributed with the tail-deferral threshold (0 = off, ...) that needs the fewest
+// passes over HBM (swap rounds weighted in), together with the pass plan of every LOCAL_GATES step (plans[i] belongs to
+// steps[i]; empty when n_local < TILE_BITS).  DVD_DEFER_TAILS=0 keeps the plain schedule.
+// store_side (the executor can let the LAST pass of the gate list store through a remap, PassDesc::remap_st): when the
+// swaps that end the schedule -- the layout restore: rank-index swaps and transpositions of local positions -- compose
+// into one remap and the last gate pass does not already carry swaps on its load, they are taken off the step list and
+// returned as store_swaps, to be executed by the store of the last pass of steps[store_step] (store_step = -1 otherwise:
+// the restore then stays in `steps`, local transpositions as CNOT triples).
+struct DistPlan {
+    std::vector<DistStep> steps;
+    std::vector<std::vector<Pass>> plans;
+    int defer_max_ops = 0;     // the threshold that won
+    int n_passes = 0;          // passes of the LOCAL_GATES steps
+    int store_step = -1;
+    std::vector<std::pair<int, int>> store_swaps;
+};
+DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total, int n_local, std::vector<int>& perm,
+                                bool restore_identity, bool store_side, const PlanOptions& opt);
+// The three CNOTs of a LOCAL_SWAP step (for executors that do not fold it into a remap).
+void append_local_swap_gates(int a, int b, std::vector<HostGate>* out);
 
 }  // namespace dvd

@@ -200,15 +200,20 @@ struct PassDesc {
     // bits of i).  remap_src[sel] is this rank's own input buffer or a partner rank's (peer memory over NVLink, mapped
     // with CUDA IPC).  remap_on == 0: plain in-place pass.  Replaces exchange_amplitudes_between_gpus + the distributed
     // gate kernel (rust_communication.cu:106-141, kernels.cu:174-230): the exchange IS the next pass's read.
-    int8_t remap_on;
+    // remap_st: the same fields describe the STORE instead (push): the amplitude this pass computes for (old) local index
+    // i is written to buffer remap_src[sel(i)] -- the second chunk of this rank or of a partner -- at the index above.
+    // Used for the swaps that END a gate list (the layout restore): they ride on the last gate pass instead of needing a
+    // pass of their own, and remote writes need no response traffic on the links.  At most one of remap_on / remap_st.
+    int8_t remap_on, remap_st;
     int8_t remap_n;
     int8_t remap_lq[3];
     int8_t remap_n_mv;
-    int8_t remap_mv_from[3], remap_mv_to[3];
+    int8_t remap_mv_from[6], remap_mv_to[6];
     uint64_t remap_lmask, remap_const;
     const cplx* remap_src[8];
 };
-constexpr int MAX_REMAP = 3;
+constexpr int MAX_REMAP = 3;         // rank-index positions (and selector bits) of one fused remap
+constexpr int MAX_REMAP_LOCAL = 6;   // local positions of one fused remap
 // Kernel parameter block: the pass description and its whole op list (<= 32764 B of parameters).
 constexpr int MAX_OPS_PER_PASS = 336;
 struct PassParams {
@@ -338,7 +343,7 @@ DVD_HD unsigned remap_sel(const PassDesc& pd, uint64_t i) {
 DVD_HD uint64_t remap_index(const PassDesc& pd, uint64_t i) {
     uint64_t src = (i & ~pd.remap_lmask) | pd.remap_const;
 #pragma unroll
-    for (int m = 0; m < MAX_REMAP; ++m)
+    for (int m = 0; m < MAX_REMAP_LOCAL; ++m)
         if (m < pd.remap_n_mv) src |= ((i >> pd.remap_mv_from[m]) & 1ull) << pd.remap_mv_to[m];
     return src;
 }

@@ -99,9 +99,19 @@ template <int G>
 __device__ __forceinline__ void tile_store(cplx* amp, const PassDesc& pd, const cplx (&a)[NREG], uint64_t cbase, const uint32_t* s_toff) {
     const Toff t{s_toff, group_tid()};       // (opaque re-read of %tid: nothing address-related stays live across the gates)
     const IoAddr io = io_addr<G>(pd, cbase, t.get(G));
-    cplx* p0 = amp + io.i0;
+    if (!pd.remap_st) {
+        cplx* p0 = amp + io.i0;
 #pragma unroll
-    for (int j = 0; j < NREG; ++j) st_stream(p0 + io_reg_offset(io, j), a[j]);
+        for (int j = 0; j < NREG; ++j) st_stream(p0 + io_reg_offset(io, j), a[j]);
+    } else {
+        // store-side remap (PassDesc::remap_st): every amplitude goes to the rank and index that hold it after the
+        // global<->local swaps -- this rank's second chunk or a partner's, written over NVLink
+#pragma unroll
+        for (int j = 0; j < NREG; ++j) {
+            const uint64_t i = io.i0 + io_reg_offset(io, j);
+            st_stream(const_cast<cplx*>(pd.remap_src[remap_sel(pd, i)]) + remap_index(pd, i), a[j]);
+        }
+    }
 }
 // Load the tile in the group-G layout.  Support tracking (PassDesc::zero_mask): amplitudes with a bit of zero_mask set
 // are zero by construction and their memory is never read (after a reset it has not even been written).

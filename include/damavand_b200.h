@@ -138,13 +138,15 @@ typedef struct {
     double gate_algorithmic_bytes;/* sum over gates of 32*2^n_local (16*2^n_local if controlled) */
     int64_t plan_cache_hits;      /* flushes that reused the previous plan (identical gate list) */
     int64_t jit_launches;         /* tile passes that ran as a structure-specialised (run-time compiled) kernel */
-    int64_t remap_passes;         /* tile passes whose load carried global<->local swaps (fused remap over NVLink peer memory) */
+    int64_t remap_passes;         /* tile passes whose load (or store) carried global<->local swaps (fused remap over NVLink peer memory) */
     double remap_bytes_in;        /* bytes those passes pulled from partner ranks over NVLink, per rank (the same amount is
                                      served to the partners in the other direction) */
     double remap_ms;              /* device time of those passes (CUDA events on the state's stream) */
     double swap_ms;               /* device time of the stand-alone exchanges (in-place peer swap / staged NCCL path) */
     double pass_fp64_instr;       /* planner's estimate of the fp64 instructions (per lane: one DADD / DMUL / DFMA of one thread) the
                                      tile passes executed: the second roofline of gate-dense passes */
+    int64_t store_remap_passes;   /* of remap_passes: passes whose STORE carried the swaps (the layout restore riding on the
+                                     last gate pass: remote writes into the partners' second chunk) */
 } dvd_stats;
 int dvd_get_stats(const dvd_state* s, dvd_stats* out);
 int dvd_stats_reset(dvd_state* s);

@@ -80,7 +80,7 @@ def main():
         dist.all_reduce(t)
         if rank == 0:
             print(f"n={n} world={world} {kind:8s} err={err:.2e} l2={l2:.2e} err_2nd_forward={err2:.2e} ez_err={ez_err:.2e} norm_err={norm_err:.1e} "
-                  f"samples_ok={s_ok} ev_ok={ev_ok} swaps={st['global_swaps']} fused_remap_passes={st['remap_passes']} "
+                  f"samples_ok={s_ok} ev_ok={ev_ok} swaps={st['global_swaps']} fused_remap_passes={st['remap_passes']} store_side={st['store_remap_passes']} "
                   f"jit_launches={st['jit_launches']} passes={st['tile_passes']} "
                   f"simple={st['simple_passes']} all_ranks_ok={int(t.item()) == 0}", flush=True)
         fails += int(t.item())

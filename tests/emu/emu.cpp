@@ -6,6 +6,7 @@
 // same op decoding.  It cannot catch missing __syncthreads, but it does catch planner, commutation,
 // tile-layout, stage-switch and control/target decoding bugs before a GPU is involved.
 // Never loaded by the product.
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -25,6 +26,7 @@ struct RemapEmu {
     const cplx* snapshot = nullptr;
     int rank = 0;
     uint64_t chunk = 0;
+    cplx* store_all = nullptr;     // store-side remap (PassDesc::remap_st): every rank's OUTPUT chunk; the pass reads `amp` in place
 };
 
 static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits, uint64_t zero_mask = 0, const RemapEmu* rm = nullptr) {
@@ -32,10 +34,17 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits, uint64_t z
     uint64_t lmask = 0;
     if (rm && !rm->pairs.empty()) {
         RemapPlan rp;
-        if (!compose_remap(rm->pairs, pd.n_local, rm->rank, &rp)) throw std::runtime_error("emu: fused remap over too many positions");
-        apply_remap(rp, &pd);
-        lmask = rp.lmask;
-        for (int sel = 0; sel < (1 << rp.n_sel); ++sel) pd.remap_src[sel] = rm->snapshot + (uint64_t)rp.src_rank[sel] * rm->chunk;
+        const bool st = rm->store_all != nullptr;
+        if (!compose_remap(rm->pairs, pd.n_local, rm->rank, &rp, st)) throw std::runtime_error("emu: fused remap over too many positions");
+        apply_remap(rp, &pd, st);
+        if (!st) lmask = rp.lmask;
+        for (int sel = 0; sel < (1 << rp.n_sel); ++sel)
+            pd.remap_src[sel] = (st ? rm->store_all : rm->snapshot) + (uint64_t)rp.src_rank[sel] * rm->chunk;
+        if (st && zero_mask) throw std::runtime_error("emu: store-side remap on a state with implied zeros");
+        if (st && !rp.on) {      // the swaps cancel: a plain copy into the output chunk
+            pd.remap_st = 1; pd.remap_n = 0; pd.remap_n_mv = 0; pd.remap_lmask = 0; pd.remap_const = 0;
+            pd.remap_src[0] = rm->store_all + (uint64_t)rm->rank * rm->chunk;
+        }
     }
     pd.rank_bits = rank_bits;
     pd.tables = pass.tables.data();
@@ -50,7 +59,7 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits, uint64_t z
     pd.zero_regbits = (int8_t)zregs;
     const uint64_t skip = zero_mask & ~tile_mask & ~lmask;
     bool sparse;
-    if (pd.remap_on) {      // engine.cu run_pass: selector bits lowest in the CTA index
+    if (pd.remap_on || pd.remap_st) {      // engine.cu run_pass: selector bits lowest in the CTA index
         uint64_t sel_bits = 0;
         for (int k = 0; k < pd.remap_n; ++k) sel_bits |= 1ull << pd.remap_lq[k];
         sparse = fill_cta_runs_ex(pd, skip, sel_bits);
@@ -134,7 +143,11 @@ static void run_pass(cplx* amp, const Pass& pass, uint64_t rank_bits, uint64_t z
         for (int tid = 0; tid < NTHREADS; ++tid) flush_phase(regs[tid], ctx[tid]);
         if (cur != pd.io_out || (cur != IO_GROUP && cur != 1)) throw std::runtime_error("emu: pass does not end in its store layout");
         for (int tid = 0; tid < NTHREADS; ++tid)
-            for (int j = 0; j < NREG; ++j) amp[base + tile_offset(pd, stage_idx(cur, tid, j))] = regs[tid][j];
+            for (int j = 0; j < NREG; ++j) {
+                const uint64_t i = base + tile_offset(pd, stage_idx(cur, tid, j));
+                if (!pd.remap_st) amp[i] = regs[tid][j];
+                else const_cast<cplx*>(pd.remap_src[remap_sel(pd, i)])[remap_index(pd, i)] = regs[tid][j];   // tile_kernel.cuh tile_store
+            }
     }
 }
 
@@ -177,6 +190,13 @@ const char* emu_error() { return g_err.c_str(); }
 static bool g_track_support = false;
 static bool g_fused = true;      // global<->local swaps ride on the next pass's load (engine default when memory allows)
 void emu_set_fused(int on) { g_fused = on != 0; }
+static bool g_store = true;      // the swaps that end the schedule ride on the store of the last gate pass
+static int g_defer = -1;         // tail-deferral threshold of the distributed schedule (-1: the planner picks)
+static int g_last_defer = 0, g_last_store = 0;
+void emu_set_store(int on) { g_store = on != 0; }
+void emu_set_defer(int th) { g_defer = th; }
+int emu_last_defer() { return g_last_defer; }     // threshold of the last emu_run's schedule
+int emu_last_store() { return g_last_store; }     // 1 if its last pass stored through a remap
 int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int fuse, double* state, int64_t* stats /*[4]*/);
 int emu_run_sparse(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int fuse, double* state, int64_t* stats) {
     g_track_support = true;
@@ -196,12 +216,21 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
         std::vector<DistStep> steps;
         std::vector<HostGate> hg = conv(gates, n_gates);
         if (fuse && n_local >= TILE_BITS) hg = fuse_diagonal_runs(hg);
-        if (world > 1) steps = plan_distributed(hg, n_qubits, n_local, perm, true);
-        else { DistStep st; st.kind = DistStep::LOCAL_GATES; st.gates = hg; steps.push_back(st); }
-        for (int q = 0; q < n_qubits; ++q) if (perm[q] != q) throw std::runtime_error("emu: layout not restored");
-        int64_t n_pass = 0, n_swap = 0, n_switch = 0, n_ops = 0;
         PlanOptions opt;
         if (const char* e = getenv("DVD_RELABEL")) opt.relabel = atoi(e) != 0;   // experimental tile relabelling
+        std::vector<std::vector<Pass>> plans;      // engine.cu flush_impl: the tuned schedule comes with its pass plans
+        int store_step = -1;
+        std::vector<std::pair<int, int>> store_swaps;
+        g_last_defer = 0; g_last_store = 0;
+        if (world > 1) {
+            opt.defer_max_ops = g_defer;
+            DistPlan dp = plan_distributed_tuned(hg, n_qubits, n_local, perm, true, g_fused && g_store, opt);
+            steps = std::move(dp.steps); plans = std::move(dp.plans);
+            store_step = dp.store_step; store_swaps = std::move(dp.store_swaps);
+            g_last_defer = dp.defer_max_ops; g_last_store = store_step >= 0;
+        } else { DistStep st; st.kind = DistStep::LOCAL_GATES; st.gates = hg; steps.push_back(st); }
+        for (int q = 0; q < n_qubits; ++q) if (perm[q] != q) throw std::runtime_error("emu: layout not restored");
+        int64_t n_pass = 0, n_swap = 0, n_switch = 0, n_ops = 0;
         // per-rank support masks (engine.cu: dvd_state::support); dense when tracking is off
         const uint64_t local_mask = chunk - 1;
         std::vector<uint64_t> support(world, (g_track_support && n_local >= TILE_BITS) ? ~local_mask : ~0ull);
@@ -231,7 +260,8 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
             ++n_pass;
             fused_pass(*ident);
         };
-        for (auto& st : steps) {
+        for (size_t si = 0; si < steps.size(); ++si) {
+            DistStep& st = steps[si];
             if (st.kind == DistStep::GLOBAL_SWAP && g_fused && n_local >= TILE_BITS) {
                 ++n_swap;
                 if (st.gq < n_local || st.gq >= n_qubits || st.lq < 0 || st.lq >= n_local) throw std::runtime_error("emu: bad swap");
@@ -258,15 +288,28 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
                 continue;
             }
             if (n_local >= TILE_BITS) {
-                std::vector<Pass> passes = plan_local(st.gates, n_local, n_qubits, opt);
+                std::vector<Pass> passes = world > 1 ? std::move(plans[si]) : plan_local(st.gates, n_local, n_qubits, opt);
                 for (auto& p : passes) { ++n_pass; n_switch += p.n_switches; n_ops += (int64_t)p.ops.size(); }
-                size_t first = 0;
+                size_t first = 0, end = passes.size();
                 if (!remap.empty() && !passes.empty()) { fused_pass(passes[0]); first = 1; }
+                const bool store_here = (int)si == store_step;
+                if (store_here) { if (end <= first) throw std::runtime_error("emu: no pass left for the store-side remap"); --end; }
                 for (int r = 0; r < world; ++r)
-                    for (size_t pi = first; pi < passes.size(); ++pi) {
+                    for (size_t pi = first; pi < end; ++pi) {
                         run_pass(amp + (uint64_t)r * chunk, passes[pi], (uint64_t)r << n_local, ~support[r] & local_mask);
                         support[r] |= passes[pi].touch_mask;
                     }
+                if (store_here) {
+                    // engine.cu run_pass, store side: implied zeros are stored first, every rank writes the other buffers
+                    for (int r = 0; r < world; ++r) materialize(r);
+                    std::vector<cplx> out((uint64_t)world << n_local, cplx{NAN, NAN});
+                    for (int r = 0; r < world; ++r) {
+                        RemapEmu rm; rm.pairs = store_swaps; rm.rank = r; rm.chunk = chunk; rm.store_all = out.data();
+                        run_pass(amp + (uint64_t)r * chunk, passes[end], (uint64_t)r << n_local, 0, &rm);
+                    }
+                    std::memcpy(amp, out.data(), out.size() * sizeof(cplx));
+                    n_swap += (int64_t)store_swaps.size();
+                }
             } else {
                 for (int r = 0; r < world; ++r) materialize(r);
                 for (int r = 0; r < world; ++r)
@@ -299,3 +342,38 @@ int emu_max_bank_conflict() {
 }
 
 }  // extern "C"
+
+// Planning only (no state): pass count of every step of the distributed schedule, as the engine would run it.
+// out: [n_steps, then per step: kind, gq, lq, n_gates, n_passes, then n_ops per pass]
+extern "C" int64_t emu_plan_only(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int32_t* out, int64_t cap) {
+    try {
+        int g = 0; while ((1 << g) < world) ++g;
+        const int n_local = n_qubits - g;
+        std::vector<int> perm(n_qubits);
+        for (int q = 0; q < n_qubits; ++q) perm[q] = q;
+        std::vector<HostGate> hg = fuse_diagonal_runs(conv(gates, n_gates));
+        std::vector<DistStep> steps;
+        PlanOptions opt;
+        if (const char* e = getenv("DVD_RELABEL")) opt.relabel = atoi(e) != 0;
+        DistPlan dp;
+        if (world > 1) { opt.defer_max_ops = g_defer; dp = plan_distributed_tuned(hg, n_qubits, n_local, perm, true, g_fused && g_store, opt); steps = dp.steps; }
+        else { DistStep st; st.kind = DistStep::LOCAL_GATES; st.gates = hg; steps.push_back(st); }
+        for (auto& sw : dp.store_swaps) { DistStep st; st.kind = sw.first >= n_local ? DistStep::GLOBAL_SWAP : DistStep::LOCAL_SWAP; st.gq = sw.first; st.lq = sw.second; steps.push_back(st); }
+        std::vector<int32_t> v;
+        v.push_back((int32_t)steps.size());
+        for (auto& st : steps) {
+            v.push_back((int32_t)st.kind); v.push_back(st.gq); v.push_back(st.lq); v.push_back((int32_t)st.gates.size());
+            if (st.kind == DistStep::LOCAL_GATES) {
+                std::vector<Pass> passes = plan_local(st.gates, n_local, n_qubits, opt);
+                v.push_back((int32_t)passes.size());
+                for (auto& p : passes) v.push_back((int32_t)p.ops.size());
+            } else v.push_back(0);
+        }
+        if ((int64_t)v.size() > cap) return -(int64_t)v.size();
+        std::memcpy(out, v.data(), v.size() * sizeof(int32_t));
+        return (int64_t)v.size();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return INT64_MIN;
+    }
+}

@@ -61,15 +61,21 @@ def emu():
         L.emu_error.restype = ctypes.c_char_p
         L.emu_max_bank_conflict.restype = ctypes.c_int
         L.emu_set_fused.argtypes = [ctypes.c_int]
+        L.emu_set_store.argtypes = [ctypes.c_int]
+        L.emu_set_defer.argtypes = [ctypes.c_int]
+        L.emu_last_defer.restype = ctypes.c_int
+        L.emu_last_store.restype = ctypes.c_int
         _emu = L
     return _emu
 
 
 def emu_run(oracle_circ: OracleCircuit, world: int = 1, state=None, fuse: bool = True, track_support: bool = False,
-            fused_remap: bool = True):
+            fused_remap: bool = True, store_side: bool = True, defer: int = -1):
     """Run the recorded gates of `oracle_circ` through the CPU replay of the CUDA path.
     fused_remap: global<->local swaps ride on the next pass's load (the engine's default when both chunks fit), else
     every swap is an exchange of its own (in-place peer swap / staged NCCL path).
+    store_side: the swaps that end the schedule (layout restore) ride on the STORE of the last gate pass when they can.
+    defer: tail-deferral threshold of the distributed schedule (-1: the planner picks the cheapest of a few).
     track_support: replay the engine's support tracking after a reset -- only amplitude 0 of every rank's chunk is
     stored, the rest of the buffer is NaN (never-written memory) and must never be read."""
     n = oracle_circ.num_qubits
@@ -89,10 +95,13 @@ def emu_run(oracle_circ: OracleCircuit, world: int = 1, state=None, fuse: bool =
     stats = (ctypes.c_int64 * 4)()
     run = emu().emu_run_sparse if track_support else emu().emu_run
     emu().emu_set_fused(int(fused_remap))
+    emu().emu_set_store(int(store_side))
+    emu().emu_set_defer(int(defer))
     rc = run(n, world, arr, ng, int(fuse), state.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stats)
     if rc != 0:
         raise RuntimeError(emu().emu_error().decode())
-    return state.view(np.complex128), dict(passes=stats[0], swaps=stats[1], switches=stats[2], ops=stats[3])
+    return state.view(np.complex128), dict(passes=stats[0], swaps=stats[1], switches=stats[2], ops=stats[3],
+                                           defer=emu().emu_last_defer(), store_side=bool(emu().emu_last_store()))
 
 
 def rel_err(a: np.ndarray, b: np.ndarray) -> float:

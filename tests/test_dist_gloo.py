@@ -133,7 +133,9 @@ def _worker(rank, world, port, n, workload, seed, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,workload", [(2, 12, "random"), (2, 13, "qft"), (4, 12, "random"), (2, 12, "hea")])
+# (n_local >= 12: the schedule comes from the tuned planner, tail deferral included)
+@pytest.mark.parametrize("world,n,workload", [(2, 12, "random"), (2, 13, "qft"), (4, 12, "random"), (2, 12, "hea"),
+                                              (2, 14, "random"), (4, 15, "hea")])
 def test_distributed_schedule_over_gloo(world, n, workload):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

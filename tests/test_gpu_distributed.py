@@ -31,7 +31,7 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize("mode", ["fused_remap_jit", "fused_remap", "in_place_peer_swap", "staged_nccl"])
+@pytest.mark.parametrize("mode", ["fused_remap_jit", "fused_remap", "fused_remap_plain_schedule", "in_place_peer_swap", "staged_nccl"])
 def test_distributed_gpu_against_oracle_on_all_visible_gpus(mode):
     world = _world()
     if world < 2:
@@ -39,6 +39,8 @@ def test_distributed_gpu_against_oracle_on_all_visible_gpus(mode):
                     "comparison in its `parity` field)")
     env = dict(os.environ)
     env.update({"DIST_CHECK_N": "14,20,22", "DIST_CHECK_QFT_MAX": "20", "DIST_CHECK_JIT": "1" if mode == "fused_remap_jit" else "0", "DVD_JIT_MIN_QUBITS": "12"})
+    if mode == "fused_remap_plain_schedule":
+        env.update({"DVD_STORE_REMAP": "0", "DVD_DEFER_TAILS": "0"})   # no tail deferral, the layout restore in a pass of its own
     if mode == "in_place_peer_swap":
         env["DVD_FUSED_REMAP"] = "0"            # every global<->local swap as a k_swap_peer exchange of its own
     if mode == "staged_nccl":
@@ -52,5 +54,7 @@ def test_distributed_gpu_against_oracle_on_all_visible_gpus(mode):
     assert len(lines) == 10 and all("all_ranks_ok=True" in l for l in lines), tail
     if mode.startswith("fused_remap"):
         assert any("fused_remap_passes=" in l and "fused_remap_passes=0 " not in l for l in lines), tail
+        # the swaps that restore the layout ride on the store of the last gate pass in some of the cases (remote writes)
+        assert any("store_side=" in l and "store_side=0 " not in l for l in lines) == (mode != "fused_remap_plain_schedule"), tail
     else:
         assert all("fused_remap_passes=0 " in l for l in lines), tail

@@ -102,6 +102,41 @@ def test_distributed_replay(world, n):
     circ = OracleCircuit(n); circuits.hea(circ, n, 3); _check(circ, world)
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_tail_deferral_and_store_side_restore(world):
+    """The two schedule transformations of round 2, forced on and off: gates of a nearly empty last pass wait for the next
+    layout (every threshold the planner tries), and the swaps that restore the layout ride on the STORE of the last gate
+    pass (PassDesc::remap_st) -- against the oracle, dense and from a reset (NaN-filled memory)."""
+    seen_defer = seen_store = False
+    for n, kind, gates, seed in ((16, "random", 200, 10 + world), (17, "random", 200, 10 + world), (18, "random", 300, 1),
+                                 (16, "hea", 0, 0), (17, "qft", 0, 0)):
+        circ = OracleCircuit(n)
+        if kind == "random":
+            circuits.random_circuit(circ, n, gates, seed=seed)
+        elif kind == "hea":
+            circuits.hea(circ, n, 3)
+        else:
+            circuits.qft_like(circ, n)
+        ref = OracleCircuit(n); ref.gates = list(circ.gates); ref.forward()
+        want = ref.amplitudes()
+        base = None
+        for defer in (-1, 0, 6, 12, 20, 32):
+            for store in (True, False):
+                got, st = emu_run(circ, world, store_side=store, defer=defer)
+                assert rel_err(got, want) < TOL, (n, kind, defer, store)
+                assert st["store_side"] in (False, store)
+                if defer == 0 and not store:
+                    base = st["passes"]
+                if defer == -1:
+                    seen_defer |= st["defer"] > 0
+                    seen_store |= st["store_side"]
+                got, _ = emu_run(circ, world, store_side=store, defer=defer, track_support=True)
+                assert not np.isnan(got.view(np.float64)).any() and rel_err(got, want) < TOL, (n, kind, defer, store, "sparse")
+        tuned = emu_run(circ, world)[1]
+        assert tuned["passes"] <= base          # the tuned schedule never needs more passes than the plain one
+    assert seen_defer and seen_store
+
+
 def test_distributed_planner_with_fewer_local_than_rank_index_qubits():
     """More rank-index qubits wanted in one round than there are local positions to evict (n_local < log2(world)):
     the planner must bring them in over several rounds instead of evicting position -1."""
