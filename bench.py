@@ -348,6 +348,7 @@ def parity_check(ranks: Ranks, jit: int, cases=None):
         s_ok = ranks.all_ok(s_ok)
         out["cases"].append({"n": n, "circuit": kind, "max_rel_err": err, "l2_rel_err": l2, "ez_err": ez_err, "norm_err": norm_err,
                              "samples_ok": s_ok, "global_swaps": int(st["global_swaps"]), "fused_remap_passes": int(st.get("remap_passes", 0)),
+                             "store_side_remap_passes": int(st.get("store_remap_passes", 0)),
                              "passes": int(st["tile_passes"]), "jit_launches": int(st["jit_launches"]), "ok": ok})
         out["ok"] = out["ok"] and ok
         out["samples_ok"] = out["samples_ok"] and s_ok
@@ -486,10 +487,12 @@ def roofline_of(m, name, n_local, n_gates, gpus):
                        "frac_of_900": nv_bytes / (nv_ms / 1e3) / 1e9 / 900.0 if nv_ms > 0 else None,
                        "frac_of_measured_770": nv_bytes / (nv_ms / 1e3) / 1e9 / 770.0 if nv_ms > 0 else None,
                        "global_swaps": st1["global_swaps"], "fused_remap_passes": st1.get("remap_passes", 0),
+                       "store_side_remap_passes": st1.get("store_remap_passes", 0),
                        "avg_fused_pass_ms": st1.get("remap_ms", 0.0) / st1["remap_passes"] if st1.get("remap_passes") else None,
                        "avg_plain_pass_ms": plain_ms,
-                       "what": "per rank and per forward; ms = device time (CUDA events) of the passes whose load carries the swaps "
-                               "(they also apply their gates: the exchange is their read) plus any stand-alone exchange"}
+                       "what": "per rank and per forward; ms = device time (CUDA events) of the passes whose load -- or, for the layout "
+                               "restore that ends the gate list, whose store -- carries the swaps (they also apply their gates: the "
+                               "exchange is their read / write) plus any stand-alone exchange"}
     return r
 
 
@@ -541,7 +544,8 @@ def cfg5_point(args, ranks: Ranks, jit: int):
     t_ez = ranks.max(time.perf_counter() - t0)
     norm = c.norm()
     out.update({"gates": ng, "forward_ms": fwd, "gates_per_sec": ng / (fwd / 1e3), "passes": st["tile_passes"], "global_swaps": st["global_swaps"],
-                "fused_remap_passes": st.get("remap_passes", 0), "nvlink_bytes_per_dir": st["swap_bytes_sent"],
+                "fused_remap_passes": st.get("remap_passes", 0), "store_side_remap_passes": st.get("store_remap_passes", 0),
+                "nvlink_bytes_per_dir": st["swap_bytes_sent"],
                 "sample_shots": shots, "sample_ms": t_sample * 1e3, "extract_expectation_values_ms": t_ev * 1e3,
                 "expectation_z_ms": t_ez * 1e3, "norm_err": abs(norm - 1.0),
                 "sampled_vs_exact_z_max_abs_diff": float(np.abs(ev_mean - ez).max()),
