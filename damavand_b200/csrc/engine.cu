@@ -239,7 +239,8 @@ static int create_common(int n_qubits, int device, int rank, int world, const vo
     s->n_qubits = n_qubits; s->n_local = n_qubits - g; s->rank = rank; s->world = world; s->device = device;
     s->n_amps = 1ull << s->n_local;
     s->rank_bits = (uint64_t)rank << s->n_local;
-    if (const char* e = getenv("DVD_PLAN_CANDIDATES")) s->opt.candidates = std::max(1, atoi(e));
+    if (const char* e = getenv("DVD_PLAN_CANDIDATES")) { s->opt.candidates = std::max(1, atoi(e)); s->opt.portfolio = false; }
+    if (const char* e = getenv("DVD_PLAN_PORTFOLIO")) s->opt.portfolio = atoi(e) != 0;
     if (const char* e = getenv("DVD_MACRO_OPS")) s->opt.macro_ops = atoi(e) != 0;
     if (const char* e = getenv("DVD_LAZY_ZERO")) s->lazy_zero = atoi(e) != 0;
     if (const char* e = getenv("DVD_BEST_GROUP")) s->opt.best_group = atoi(e) != 0;
@@ -1187,7 +1188,8 @@ int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t 
     try {
         PlanOptions opt;
         if (const char* e = getenv("DVD_BEST_GROUP")) opt.best_group = atoi(e) != 0;
-        if (const char* e = getenv("DVD_PLAN_CANDIDATES")) opt.candidates = std::max(1, atoi(e));
+        if (const char* e = getenv("DVD_PLAN_CANDIDATES")) { opt.candidates = std::max(1, atoi(e)); opt.portfolio = false; }
+        if (const char* e = getenv("DVD_PLAN_PORTFOLIO")) opt.portfolio = atoi(e) != 0;
         if (const char* e = getenv("DVD_RELABEL")) opt.relabel = atoi(e) != 0;
         std::vector<Pass> passes = plan_local(fuse ? fuse_diagonal_runs(to_host_gates(gates, n_gates)) : to_host_gates(gates, n_gates), n_local, n_total, opt);
         std::vector<int32_t> v;
@@ -1218,7 +1220,9 @@ int64_t dvd_jit_debug_source(int n_total, int n_local, const dvd_gate* gates, in
         PlanOptions opt;
         std::vector<Pass> passes = plan_local(fuse_diagonal_runs(to_host_gates(gates, n_gates)), n_local, n_total, opt);
         if (pass_index < 0 || pass_index >= (int)passes.size()) return 0;
-        const std::string src = generate_pass_source(passes[pass_index], "dvd_pass_static", form < 0 || form >= FORM_COUNT ? FORM_CLASSIC2 : form);
+        const bool st = form >= 16;      // + 16: the variant whose store goes through a remap (PassDesc::remap_st)
+        if (st) form -= 16;
+        const std::string src = generate_pass_source(passes[pass_index], "dvd_pass_static", form < 0 || form >= FORM_COUNT ? FORM_CLASSIC2 : form, st);
         if ((int64_t)src.size() + 1 > cap) return -(int64_t)(src.size() + 1);
         std::memcpy(out, src.c_str(), src.size() + 1);
         return (int64_t)src.size();

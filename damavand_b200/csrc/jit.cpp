@@ -16,10 +16,10 @@ int demacro(int code) {
 
 }  // namespace
 
-std::vector<uint32_t> pass_structure_key(const Pass& p, int form) {
+std::vector<uint32_t> pass_structure_key(const Pass& p, int form, bool store_remap) {
     std::vector<uint32_t> key;
     key.reserve(p.ops.size() + 1);
-    key.push_back(0x80000000u | ((uint32_t)form << 8) | (uint32_t)p.desc.io_out);
+    key.push_back(0x80000000u | (store_remap ? 1u << 16 : 0u) | ((uint32_t)form << 8) | (uint32_t)p.desc.io_out);
     for (const DevOp& op : p.ops) {
         uint32_t k = (uint32_t)demacro(op.code) | ((uint32_t)op.flags << 8);
         if (op.code == OC_TABLE && op.tmask != 0) k |= 1u << 16;          // pivoted table op
@@ -28,7 +28,7 @@ std::vector<uint32_t> pass_structure_key(const Pass& p, int form) {
     return key;
 }
 
-std::string generate_pass_source(const Pass& p, const std::string& fn_name, int form) {
+std::string generate_pass_source(const Pass& p, const std::string& fn_name, int form, bool store_remap) {
     std::ostringstream o;
     const bool ring = form == FORM_RING;
     const bool has_tab = !p.tab_desc.empty();
@@ -114,7 +114,7 @@ std::string generate_pass_source(const Pass& p, const std::string& fn_name, int 
         }
     }
     o << ind << "flush_phase(a, ctx);\n"
-      << ind << "tile_store<" << (int)p.desc.io_out << ">(amp, pd, a, gbase - pd.rank_bits, s_toff);\n";
+      << ind << "tile_store<" << (int)p.desc.io_out << (store_remap ? ", true" : "") << ">(amp, pd, a, gbase - pd.rank_bits, s_toff);\n";
     if (ring) o << "    }\n";
     o << "}\n";
     return o.str();

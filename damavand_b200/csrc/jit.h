@@ -24,10 +24,11 @@ namespace dvd {
 enum JitForm : int { FORM_CLASSIC2 = 0, FORM_CLASSIC3 = 1, FORM_RING = 2, FORM_COUNT = 3 };
 
 // Structure key of a pass: equal keys <=> identical generated source.
-std::vector<uint32_t> pass_structure_key(const Pass& p, int form = FORM_CLASSIC2);
+// store_remap: the variant whose store goes through a remap (PassDesc::remap_st; tile_kernel.cuh: tile_store<G, true>).
+std::vector<uint32_t> pass_structure_key(const Pass& p, int form = FORM_CLASSIC2, bool store_remap = false);
 
 // CUDA source of `extern "C" __global__ void <fn_name>(cplx*, const PassParams)`; expects tile_kernel.cuh to be
 // includable under that name.
-std::string generate_pass_source(const Pass& p, const std::string& fn_name, int form = FORM_CLASSIC2);
+std::string generate_pass_source(const Pass& p, const std::string& fn_name, int form = FORM_CLASSIC2, bool store_remap = false);
 
 }  // namespace dvd

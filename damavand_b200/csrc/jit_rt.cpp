@@ -339,16 +339,17 @@ bool jit_launch(const Pass& p, int mode, int device, cplx* amp, const PassParams
             r.sm_count[device] = n;
         }
         sms = (unsigned)r.sm_count[device];
-        std::shared_ptr<Tuner>& slot = r.tuners[pass_structure_key(p, FORM_CLASSIC2)];
+        const bool st = pp.pd.remap_st != 0;       // the store-side remap is a kernel variant of its own (never in the ring form)
+        std::shared_ptr<Tuner>& slot = r.tuners[pass_structure_key(p, FORM_CLASSIC2, st)];
         if (!slot) slot = std::make_shared<Tuner>();
         {   // queue the forms this launch may want and that nobody asked for yet (classic2 always: it can run every launch)
             const int forced = forced_form();
             bool queued = false;
             for (int f = 0; f < FORM_COUNT; ++f) {
-                if (slot->e[f] || (forced >= 0 && f != forced && f != FORM_CLASSIC2)) continue;
+                if (slot->e[f] || (forced >= 0 && f != forced && f != FORM_CLASSIC2) || (st && f == FORM_RING)) continue;
                 slot->e[f] = std::make_shared<Entry>();
                 slot->e[f]->form = f;
-                r.queue.emplace_back(slot->e[f], generate_pass_source(p, "dvd_pass_static", f));
+                r.queue.emplace_back(slot->e[f], generate_pass_source(p, "dvd_pass_static", f, st));
                 ++r.stats.pending;
                 queued = true;
             }

@@ -17,7 +17,8 @@ namespace dvd {
 // One launch = one pass: every amplitude is read once and written once; pp.ops is applied in between.
 // The op list lives in the kernel's parameter space (constant bank): op fields are warp-uniform loads.
 // SET: op classes compiled in (see OpClass); launch_tile_pass picks the smallest variant covering the pass.
-template <unsigned SET>
+// ST: the store goes through a remap (PassDesc::remap_st, tile_kernel.cuh: tile_store).
+template <unsigned SET, bool ST = false>
 __global__ void __launch_bounds__(NTHREADS, 2)
 k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -73,8 +74,8 @@ k_tile_pass(cplx* __restrict__ amp, const __grid_constant__ PassParams pp) {
     flush_phase(a, ctx);
     // the planner ends a pass in the group-2 or the group-1 layout: both store 128-byte segments per quarter warp
     // (rank bits lie above the local index bits, so gbase - rank_bits is the tile's base again)
-    if (pd.io_out == IO_GROUP) tile_store<IO_GROUP>(amp, pd, a, gbase - pd.rank_bits, s_toff);
-    else tile_store<1>(amp, pd, a, gbase - pd.rank_bits, s_toff);
+    if (pd.io_out == IO_GROUP) tile_store<IO_GROUP, ST>(amp, pd, a, gbase - pd.rank_bits, s_toff);
+    else tile_store<1, ST>(amp, pd, a, gbase - pd.rank_bits, s_toff);
 }
 
 // Two-group persistent form of the same pass (tile_kernel.cuh, "ring"): one CTA of 2 x 256 threads per SM, three
@@ -591,6 +592,10 @@ cudaError_t kernels_init() {
                                                  p ? RING_SMEM_BYTES : TILE_SLOTS * (int)sizeof(cplx));
             if (e != cudaSuccess) return e;
         }
+    {
+        cudaError_t e = cudaFuncSetAttribute(k_tile_pass<C_ALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SLOTS * (int)sizeof(cplx));
+        if (e != cudaSuccess) return e;
+    }
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
         g_sm_count = sms;
@@ -614,7 +619,9 @@ cudaError_t launch_tile_pass(cplx* amp, PassParams& pp, cudaStream_t s) {
     int v = 0;
     while (v < 3 && (need & ~VARIANTS[v])) ++v;
     if (const char* e = getenv("DVD_KERNEL_VARIANT")) v = atoi(e) & 3;   // development: force a variant (3 = all ops)
-    if (g_ring && pp.pd.zero_mask == 0 && ctas >= (uint64_t)ring_min_tiles(g_sm_count))
+    if (pp.pd.remap_st)      // the layout restore riding on this pass's store: one variant, all op classes
+        k_tile_pass<C_ALL, true><<<(unsigned)ctas, NTHREADS, TILE_SLOTS * sizeof(cplx), s>>>(amp, pp);
+    else if (g_ring && pp.pd.zero_mask == 0 && ctas >= (uint64_t)ring_min_tiles(g_sm_count))
         tile_kernel(v, true)<<<(unsigned)g_sm_count, RING_GROUPS * NTHREADS, RING_SMEM_BYTES, s>>>(amp, pp);
     else
         tile_kernel(v, false)<<<(unsigned)ctas, NTHREADS, TILE_SLOTS * sizeof(cplx), s>>>(amp, pp);

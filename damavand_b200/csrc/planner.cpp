@@ -656,23 +656,34 @@ struct StageEmitter {
 static std::vector<Pass> plan_local_impl(const std::vector<HostGate>& gates_in, int n_local, int n_total, const PlanOptions& opt,
                                          std::vector<int>* pass_of_gate);
 
-// Tile relabelling pays when it saves passes (chain-like circuits: hea28 80 -> 55); where it does not (random32,
-// qft30: the same pass count either way) its extra swap gates only add transposes and make untouched qubits look
-// touched to the support tracking -- measured on B200: random32 from a reset 274 -> 329 ms.  So both plans are made
-// (host time, cached with the plan) and relabelling is kept only if it needs strictly fewer passes.
+// A small portfolio instead of one greedy plan (host time: 1-10 ms per plan, cached with the plan).
+// * Tile relabelling pays when it saves passes (chain-like circuits: hea28 80 -> 55); where it does not (random32, qft30:
+//   the same pass count either way) its extra swap gates only add transposes and make untouched qubits look touched to
+//   the support tracking -- measured on B200: random32 from a reset 274 -> 329 ms.  So it is kept only if it needs
+//   strictly fewer passes.
+// * Taking the highest-scoring tile for every pass is not the fewest passes overall: with fewer candidates per pass
+//   (closer to first-come order) random32 needs 11 passes instead of 12.  The candidate counts below are tried in
+//   order and a later one replaces the plan only if it needs strictly fewer passes.
 std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, int n_total, const PlanOptions& opt,
                              std::vector<int>* pass_of_gate) {
-    if (!opt.relabel) return plan_local_impl(gates, n_local, n_total, opt, pass_of_gate);
-    PlanOptions plain = opt;
-    plain.relabel = false;
-    std::vector<int> pa, pb;
-    std::vector<Pass> a = plan_local_impl(gates, n_local, n_total, plain, pass_of_gate ? &pa : nullptr);
-    if (a.size() > 1) {
-        std::vector<Pass> b = plan_local_impl(gates, n_local, n_total, opt, pass_of_gate ? &pb : nullptr);
-        if (b.size() < a.size()) { if (pass_of_gate) pass_of_gate->swap(pb); return b; }
+    std::vector<Pass> best;
+    std::vector<int> best_of;
+    bool have = false;
+    const int cands[3] = {opt.candidates, 4, 2};
+    for (int ci = 0; ci < (opt.portfolio ? 3 : 1); ++ci) {
+        if (ci > 0 && cands[ci] >= opt.candidates) continue;
+        for (int rl = 0; rl < (opt.relabel ? 2 : 1); ++rl) {
+            if (have && best.size() <= 1) break;
+            PlanOptions o = opt;
+            o.candidates = cands[ci];
+            o.relabel = rl == 1;
+            std::vector<int> of;
+            std::vector<Pass> cand = plan_local_impl(gates, n_local, n_total, o, pass_of_gate ? &of : nullptr);
+            if (!have || cand.size() < best.size()) { best = std::move(cand); best_of.swap(of); have = true; }
+        }
     }
-    if (pass_of_gate) pass_of_gate->swap(pa);
-    return a;
+    if (pass_of_gate) pass_of_gate->swap(best_of);
+    return best;
 }
 
 static std::vector<Pass> plan_local_impl(const std::vector<HostGate>& gates_in, int n_local, int n_total,

@@ -57,6 +57,7 @@ struct PlanOptions {
     int min_low = 3;           // tile always contains physical qubits [0, min_low): 128 B segments
     int window = 16384;        // look-ahead (gates) when filling a pass
     int candidates = 12;       // tile candidates scored per pass (1 = first-come only)
+    bool portfolio = true;     // plan_local also tries 4 and 2 candidates per pass and keeps the plan with the fewest passes
     int max_ops_per_pass = 1024;   // gates taken into one pass (halved and retried while the op stream exceeds MAX_OPS_PER_PASS)
     bool macro_ops = true;     // fuse 4-op runs on the four register bits into one dispatch (OC_REALPH4, OC_TWHAD4)
     int defer_max_ops = -1;    // distributed schedule (plan_distributed_tuned): tail-deferral threshold; -1 = the best of a few

@@ -95,11 +95,13 @@ __device__ __forceinline__ uint64_t io_reg_offset(const IoAddr& io, int j) {
     for (int k = 0; k < REG_BITS; ++k) if ((j >> k) & 1) off += io.hs[k];
     return off;
 }
-template <int G>
+// ST: the store-side remap is a compile-time variant of the kernels (a run-time branch here costs the plain passes
+// registers: 120 -> 128 and a spill on the 30-qubit Fourier passes); the engine launches it only with pd.remap_st set.
+template <int G, bool ST = false>
 __device__ __forceinline__ void tile_store(cplx* amp, const PassDesc& pd, const cplx (&a)[NREG], uint64_t cbase, const uint32_t* s_toff) {
     const Toff t{s_toff, group_tid()};       // (opaque re-read of %tid: nothing address-related stays live across the gates)
     const IoAddr io = io_addr<G>(pd, cbase, t.get(G));
-    if (!pd.remap_st) {
+    if constexpr (!ST) {
         cplx* p0 = amp + io.i0;
 #pragma unroll
         for (int j = 0; j < NREG; ++j) st_stream(p0 + io_reg_offset(io, j), a[j]);

@@ -178,7 +178,7 @@ int64_t dvd_plan_debug(int n_total, int n_local, const dvd_gate* gates, int64_t 
 /* CUDA source of the structure-specialised kernel the engine would compile for pass `pass_index` of the same plan
  * (NUL-terminated text).  Returns its length, 0 if there is no such pass, -(needed) if cap is too small. */
 int64_t dvd_jit_debug_source(int n_total, int n_local, const dvd_gate* gates, int64_t n_gates, int pass_index,
-                             int form /* csrc/jit.h JitForm: 0, 1 or 2 */, char* out, int64_t cap);
+                             int form /* csrc/jit.h JitForm: 0, 1 or 2; + 16 = the store-side-remap variant */, char* out, int64_t cap);
 /* NVRTC-compiles such a source for sm_100a (no GPU needed): cubin size, or -1 with the log in dvd_last_error(). */
 int64_t dvd_jit_debug_compile(const char* source);
 /* Runs the distributed planner: perm_io[logical] = physical (in/out).  Output:

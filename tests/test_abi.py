@@ -150,6 +150,12 @@ def test_jit_generator_and_nvrtc_compile():
     k = L.dvd_jit_debug_source(14, 14, arr, ng, 0, 2, buf, 1 << 20)
     assert k > 0 and buf.value != srcs[0] and b"ring_fetch(ring, slot + 3" in buf.value and b"group_sync(grp)" in buf.value
     assert L.dvd_jit_debug_compile(buf.value) > 10000, L.dvd_last_error()
+    # the store-side-remap variant (the layout restore riding on the last pass of a distributed gate list): a
+    # compile-time variant, so that the plain kernels do not pay registers for it
+    assert b"true>(amp, pd" not in srcs[0]
+    k = L.dvd_jit_debug_source(14, 14, arr, ng, 0, 16, buf, 1 << 20)
+    assert k > 0 and buf.value != srcs[0] and b", true>(amp, pd, a, gbase - pd.rank_bits, s_toff)" in buf.value
+    assert L.dvd_jit_debug_compile(buf.value) > 10000, L.dvd_last_error()
 
 
 def test_jit_disk_cache(tmp_path, monkeypatch):
