@@ -488,6 +488,9 @@ def roofline_of(m, name, n_local, n_gates, gpus):
                        "frac_of_measured_770": nv_bytes / (nv_ms / 1e3) / 1e9 / 770.0 if nv_ms > 0 else None,
                        "global_swaps": st1["global_swaps"], "fused_remap_passes": st1.get("remap_passes", 0),
                        "store_side_remap_passes": st1.get("store_remap_passes", 0),
+                       "avg_store_side_pass_ms": st1.get("store_remap_ms", 0.0) / st1["store_remap_passes"] if st1.get("store_remap_passes") else None,
+                       "avg_load_side_pass_ms": (st1.get("remap_ms", 0.0) - st1.get("store_remap_ms", 0.0)) / (st1["remap_passes"] - st1.get("store_remap_passes", 0))
+                                                if st1.get("remap_passes", 0) > st1.get("store_remap_passes", 0) else None,
                        "avg_fused_pass_ms": st1.get("remap_ms", 0.0) / st1["remap_passes"] if st1.get("remap_passes") else None,
                        "avg_plain_pass_ms": plain_ms,
                        "what": "per rank and per forward; ms = device time (CUDA events) of the passes whose load -- or, for the layout "

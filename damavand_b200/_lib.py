@@ -43,6 +43,7 @@ class Stats(ctypes.Structure):
         ("swap_ms", ctypes.c_double),
         ("pass_fp64_instr", ctypes.c_double),
         ("store_remap_passes", ctypes.c_int64),
+        ("store_remap_ms", ctypes.c_double),
     ]
 
     def as_dict(self):

@@ -84,14 +84,16 @@ struct dvd_state {
     cplx* buf[2] = {nullptr, nullptr};
     int cur = 0;
     bool fused_remap = false;
-    struct RemapTimer { cudaEvent_t t0 = nullptr, t1 = nullptr; bool is_swap = false; };
+    struct RemapTimer { cudaEvent_t t0 = nullptr, t1 = nullptr; bool is_swap = false, is_store = false; };
     std::vector<RemapTimer> remap_timers;   // events around the fused passes since the last dvd_stats_reset
     size_t remap_timers_used = 0;
     std::unique_ptr<Pass> ident_pass;       // empty pass for swaps with no gate pass to ride on
     cplx* d_ident_tab = nullptr;
     cplx* peer_cur(int r) const { return peer_base[r] + (size_t)cur * n_amps; }
     cplx* peer_other(int r) const { return peer_base[r] + (size_t)(1 - cur) * n_amps; }
-    bool store_remap = true;      // DVD_STORE_REMAP=0: the layout restore always takes a pass of its own
+    int store_remap = 1;          // DVD_STORE_REMAP (planner.h DistPlan): 0 = swaps only ever ride on loads, 1 = the layout restore
+                                  //   rides on the store of the last gate pass, 2 = every swap round rides on a store where it can
+    bool pushed_pending = false;  // a store-side pass has run: its remote writes are complete on every rank only after a barrier
     dvd_stats stats;
     bool unfused = false;
     // Support tracking: after a reset only amplitude 0 is stored; `support` holds the local qubits that a
@@ -108,8 +110,8 @@ struct dvd_state {
         std::vector<DistStep> steps;
         std::vector<std::vector<Pass>> plans;
         size_t total_tabs = 0;
-        int store_step = -1;                              // planner.h DistPlan: the swaps that end the schedule ride on
-        std::vector<std::pair<int, int>> store_swaps;     //   the store of the last pass of steps[store_step]
+        std::vector<std::vector<std::pair<int, int>>> store;   // planner.h DistPlan::store: swap rounds riding on the store of the
+                                                               //   last pass of their step
         bool valid = false;
     } cache;
     bool plan_cache = true;
@@ -163,6 +165,7 @@ static int timer_acquire(dvd_state* s, bool is_swap, dvd_state::RemapTimer** out
     }
     *out = &s->remap_timers[s->remap_timers_used++];
     (*out)->is_swap = is_swap;
+    (*out)->is_store = false;
     return DVD_OK;
 }
 
@@ -216,7 +219,7 @@ static int map_peers(dvd_state* s) {
     const char* fr = getenv("DVD_FUSED_REMAP");
     s->fused_remap = s->peer_swap && s->buf[1] != nullptr && !(fr && atoi(fr) == 0);
     const char* sr = getenv("DVD_STORE_REMAP");
-    s->store_remap = !(sr && atoi(sr) == 0);
+    s->store_remap = sr ? std::max(0, std::min(2, atoi(sr))) : 1;
     return DVD_OK;
 }
 
@@ -518,8 +521,7 @@ static int flush_impl(dvd_state* s) {
     if (hit) s->stats.plan_cache_hits++;
     if (!hit) {
         s->cache.valid = false;
-        s->cache.store_step = -1;
-        s->cache.store_swaps.clear();
+        s->cache.store.clear();
         std::vector<DistStep> steps;
         // every local step is planned up front so that all phase tables go to the device in one copy; the op
         // lists travel as kernel parameters
@@ -531,11 +533,10 @@ static int flush_impl(dvd_state* s) {
             if (s->world > 1 && tiled) {
                 // the schedule with the fewest passes among the tail-deferral thresholds, with its pass plans
                 DistPlan dp = plan_distributed_tuned(fused, s->n_qubits, s->n_local, s->perm, /*restore_identity=*/true,
-                                                     /*store_side=*/s->fused_remap && s->store_remap, s->opt);
+                                                     /*store_side=*/s->fused_remap ? s->store_remap : 0, s->opt);
                 steps = std::move(dp.steps);
                 plans = std::move(dp.plans);
-                s->cache.store_step = dp.store_step;
-                s->cache.store_swaps = std::move(dp.store_swaps);
+                s->cache.store = std::move(dp.store);
             } else if (s->world > 1) {
                 steps = plan_distributed(fused, s->n_qubits, s->n_local, s->perm, /*restore_identity=*/true);
             } else {
@@ -593,6 +594,10 @@ static int flush_impl(dvd_state* s) {
     // last gate pass): it reads this rank's buffer `cur` in place and writes buffer 1 - cur of this rank and of its partners
     auto run_pass = [&](Pass& p, const cplx* d_tab, const std::vector<std::pair<int, int>>* store_swaps = nullptr) -> int {
         RemapPlan sp;
+        if (s->pushed_pending) {        // the pass in front of this one stored into other ranks' buffers: wait for all of them
+            TRY(stream_barrier(s));
+            s->pushed_pending = false;
+        }
         if (store_swaps) {
             if (!remap.empty()) return fail(DVD_ERR_INTERNAL, "a pass cannot carry swaps on its load and on its store");
             if (!compose_remap(*store_swaps, s->n_local, s->rank, &sp, /*inverse=*/true)) return fail(DVD_ERR_INTERNAL, "store-side remap over too many positions");
@@ -654,7 +659,7 @@ static int flush_impl(dvd_state* s) {
         dvd_state::RemapTimer* tm = nullptr;
         if (!remap.empty() || store_swaps) {
             TRY(timer_acquire(s, false, &tm));
-            if (tm) CU(cudaEventRecord(tm->t0, s->stream));
+            if (tm) { tm->is_store = store_swaps != nullptr; CU(cudaEventRecord(tm->t0, s->stream)); }
         }
         bool launched = false;
         if (s->jit_mode != JIT_OFF && s->n_local >= s->jit_min_qubits) {
@@ -678,7 +683,10 @@ static int flush_impl(dvd_state* s) {
             int local_sel = 0;
             for (int sel = 0; sel < (1 << mp.n_sel); ++sel) local_sel += mp.src_rank[sel] == s->rank;
             const double moved = chunk * (1.0 - (double)local_sel / (double)(1 << mp.n_sel));   // pulled (pushed) over NVLink
-            if (store_swaps) { for (auto& sw : *store_swaps) s->stats.global_swaps += sw.first >= s->n_local; lmask = ~0ull; s->stats.store_remap_passes++; }
+            if (store_swaps) {
+                for (auto& sw : *store_swaps) s->stats.global_swaps += sw.first >= s->n_local;
+                lmask = ~0ull; s->stats.store_remap_passes++; s->pushed_pending = true;
+            }
             else s->stats.global_swaps += (int64_t)remap.size();
             s->stats.swap_bytes_sent += (int64_t)moved;
             s->stats.remap_passes++;
@@ -726,8 +734,8 @@ static int flush_impl(dvd_state* s) {
         if (tiled) {
             for (size_t k = 0; k < plans[i].size(); ++k) {
                 Pass& p = plans[i][k];
-                const bool store_here = (int)i == s->cache.store_step && k + 1 == plans[i].size();
-                TRY(run_pass(p, d_tabs + tat, store_here ? &s->cache.store_swaps : nullptr));
+                const bool store_here = k + 1 == plans[i].size() && i < s->cache.store.size() && !s->cache.store[i].empty();
+                TRY(run_pass(p, d_tabs + tat, store_here ? &s->cache.store[i] : nullptr));
                 tat += p.tables.size();
             }
         } else {
@@ -743,6 +751,7 @@ static int flush_impl(dvd_state* s) {
     // every rank has finished reading this rank's buffers before anything after the flush (an observation, a load,
     // the destruction of the state) touches them
     if (fused_any) TRY(stream_barrier(s));
+    s->pushed_pending = false;
     if (tiled && total_tabs) {
         dvd_state::TabSet& ts = s->tabs[s->n_flushes & 1];
         CU(cudaEventRecord(ts.done, s->stream));
@@ -1099,16 +1108,17 @@ int dvd_get_stats(const dvd_state* cs, dvd_stats* out) {
     if (!cs || !out) return fail(DVD_ERR_ARG, "null argument");
     dvd_state* s = const_cast<dvd_state*>(cs);
     // event pairs around the fused-remap passes / stand-alone exchanges recorded since the last reset
-    double ms_remap = 0.0, ms_swap = 0.0;
+    double ms_remap = 0.0, ms_swap = 0.0, ms_store = 0.0;
     for (size_t i = 0; i < s->remap_timers_used; ++i) {
         const dvd_state::RemapTimer& t = s->remap_timers[i];
         float f = 0.f;
         if (cudaEventSynchronize(t.t1) == cudaSuccess && cudaEventElapsedTime(&f, t.t0, t.t1) == cudaSuccess)
-            (t.is_swap ? ms_swap : ms_remap) += f;
+            { (t.is_swap ? ms_swap : ms_remap) += f; if (t.is_store) ms_store += f; }
         else cudaGetLastError();
     }
     s->stats.remap_ms = ms_remap;
     s->stats.swap_ms = ms_swap;
+    s->stats.store_remap_ms = ms_store;
     *out = s->stats;
     return DVD_OK;
 }
@@ -1246,7 +1256,7 @@ int64_t dvd_plan_distributed_debug(int n_total, int n_local, const dvd_gate* gat
         std::vector<int> perm(perm_io, perm_io + n_total);
         // the schedule the engine runs (tail deferral included; the restore stays in the step list)
         std::vector<DistStep> steps = n_local >= TILE_BITS
-            ? plan_distributed_tuned(to_host_gates(gates, n_gates), n_total, n_local, perm, restore_identity != 0, /*store_side=*/false, PlanOptions()).steps
+            ? plan_distributed_tuned(to_host_gates(gates, n_gates), n_total, n_local, perm, restore_identity != 0, /*store_side=*/0, PlanOptions()).steps
             : plan_distributed(to_host_gates(gates, n_gates), n_total, n_local, perm, restore_identity != 0);
         for (int q = 0; q < n_total; ++q) perm_io[q] = perm[q];
         std::vector<int32_t> v;

@@ -1248,37 +1248,64 @@ std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n
     return steps;
 }
 
-// The swaps that end `dp.steps` as the store-side remap of the last gate pass (planner.h: DistPlan::store_step).
-static bool take_store_side(DistPlan& dp, int n_local) {
-    int last = -1;
-    for (size_t i = 0; i < dp.steps.size(); ++i)
-        if (dp.steps[i].kind == DistStep::LOCAL_GATES && !dp.plans[i].empty()) last = (int)i;
-    if (last < 0) return false;
-    std::vector<std::pair<int, int>> pairs;
-    for (size_t i = (size_t)last + 1; i < dp.steps.size(); ++i) {
-        const DistStep& st = dp.steps[i];
-        if (st.kind == DistStep::LOCAL_GATES) { if (!st.gates.empty()) return false; continue; }
-        pairs.push_back({st.gq, st.lq});
+// Hand swap rounds to the store of the pass in front of them (planner.h: DistPlan::store).  Returns false when a round
+// with LOCAL_SWAP steps -- which no executor runs as steps -- could not be taken: the caller plans again with CNOT triples.
+static bool assign_store_side(DistPlan& dp, int n_local, int mode) {
+    std::vector<DistStep> steps;
+    std::vector<std::vector<Pass>> plans;
+    std::vector<std::vector<std::pair<int, int>>> store;
+    int last_local = -1;            // index (new lists) of the last LOCAL_GATES step with passes
+    bool first_pass_pulls = false;  //   its first pass loads through the swaps in front of it
+    bool has_store = false;         //   its last pass already stores through a round
+    bool pull_pending = false;      // swaps kept in the step list since that step
+    const size_t n = dp.steps.size();
+    size_t i = 0;
+    while (i < n) {
+        if (dp.steps[i].kind == DistStep::LOCAL_GATES) {
+            steps.push_back(std::move(dp.steps[i]));
+            plans.push_back(std::move(dp.plans[i]));
+            store.emplace_back();
+            if (!plans.back().empty()) { last_local = (int)steps.size() - 1; first_pass_pulls = pull_pending; has_store = false; pull_pending = false; }
+            ++i;
+            continue;
+        }
+        size_t j = i;
+        std::vector<std::pair<int, int>> pairs;
+        bool local_swaps = false;
+        while (j < n && dp.steps[j].kind != DistStep::LOCAL_GATES) {
+            pairs.push_back({dp.steps[j].gq, dp.steps[j].lq});
+            local_swaps |= dp.steps[j].kind == DistStep::LOCAL_SWAP;
+            ++j;
+        }
+        bool ends_schedule = true;
+        for (size_t k = j; k < n; ++k) if (dp.steps[k].kind != DistStep::LOCAL_GATES || !dp.steps[k].gates.empty()) ends_schedule = false;
+        RemapPlan rp;
+        const bool take = mode >= 1 && (mode >= 2 || ends_schedule) && last_local >= 0 && !has_store && !pull_pending &&
+                          (!first_pass_pulls || plans[last_local].size() >= 2) &&
+                          compose_remap(pairs, n_local, 0, &rp, /*inverse=*/true);
+        if (take) {
+            store[last_local] = std::move(pairs);
+            has_store = true;
+            ++dp.n_store;
+        } else {
+            if (local_swaps) return false;
+            for (size_t k = i; k < j; ++k) { steps.push_back(std::move(dp.steps[k])); plans.emplace_back(); store.emplace_back(); }
+            pull_pending = true;
+        }
+        i = j;
     }
-    if (pairs.empty()) return false;
-    RemapPlan rp;
-    if (!compose_remap(pairs, n_local, 0, &rp, /*inverse=*/true)) return false;
-    // a pass has one set of remap fields: the last pass must not be the one whose load carries the swaps in front of the step
-    const bool swaps_in_front = last > 0 && dp.steps[last - 1].kind != DistStep::LOCAL_GATES;
-    if (swaps_in_front && dp.plans[last].size() < 2) return false;
-    dp.steps.resize((size_t)last + 1);
-    dp.plans.resize((size_t)last + 1);
-    dp.store_step = last;
-    dp.store_swaps = std::move(pairs);
+    dp.steps = std::move(steps);
+    dp.plans = std::move(plans);
+    dp.store = std::move(store);
     return true;
 }
 
 DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total, int n_local, std::vector<int>& perm,
-                                bool restore_identity, bool store_side, const PlanOptions& opt) {
+                                bool restore_identity, int store_side, const PlanOptions& opt) {
     static const int thresholds[] = {0, 6, 12, 20, 32};
     const char* env = getenv("DVD_DEFER_TAILS");
     const bool enabled = n_local >= TILE_BITS && !(env && atoi(env) == 0);
-    if (n_local < TILE_BITS) store_side = false;
+    if (n_local < TILE_BITS) store_side = 0;
     DistPlan best;
     std::vector<int> best_perm;
     double best_cost = 0.0;
@@ -1301,11 +1328,12 @@ DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total,
                     cand.plans[i] = plan_local(cand.steps[i].gates, n_local, n_total, opt);
                     cand.n_passes += (int)cand.plans[i].size();
                 }
-            if (attempt == 1 || take_store_side(cand, n_local)) break;
+            if (assign_store_side(cand, n_local, attempt == 0 ? store_side : (store_side >= 2 ? 2 : 0))) break;
         }
         // cost in plain-pass units: a pass = 1; a round of swaps makes the load of the pass behind it (or the store of the
-        // last pass) NVLink-bound (measured on 8 x B200: 9.7 against 5.5 ms) and needs a pass of its own when no gate pass follows
-        double cost = cand.store_step >= 0 ? 0.75 : 0.0;
+        // pass in front of it) NVLink-bound (measured on 8 x B200: 9.7 against 5.5 ms) and needs a pass of its own when it
+        // has no gate pass to ride on
+        double cost = 0.75 * cand.n_store;
         bool swaps_waiting = false;
         for (size_t i = 0; i < cand.steps.size(); ++i) {
             const DistStep& st = cand.steps[i];

@@ -136,21 +136,25 @@ std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n
 // The schedule the engine runs: plan_distributed with the tail-deferral threshold (0 = off, ...) that needs the fewest
 // passes over HBM (swap rounds weighted in), together with the pass plan of every LOCAL_GATES step (plans[i] belongs to
 // steps[i]; empty when n_local < TILE_BITS).  DVD_DEFER_TAILS=0 keeps the plain schedule.
-// store_side (the executor can let the LAST pass of the gate list store through a remap, PassDesc::remap_st): when the
-// swaps that end the schedule -- the layout restore: rank-index swaps and transpositions of local positions -- compose
-// into one remap and the last gate pass does not already carry swaps on its load, they are taken off the step list and
-// returned as store_swaps, to be executed by the store of the last pass of steps[store_step] (store_step = -1 otherwise:
-// the restore then stays in `steps`, local transpositions as CNOT triples).
+// store_side: the executor can let the last pass of a LOCAL_GATES step STORE through a remap (PassDesc::remap_st: remote
+// writes into the other chunk of this rank and of its partners) instead of the next pass LOADING through one.
+//   0  never: every swap round rides on the load of the pass behind it (an empty pass if there is none);
+//   1  the swaps that END the schedule -- the layout restore: rank-index swaps and transpositions of local positions,
+//      which need a pass of their own otherwise -- ride on the store of the last gate pass;
+//   2  every swap round rides on the store of the pass in front of it where it can.
+// A round that is taken leaves the step list and is returned as store[i] for the LOCAL_GATES step i whose last pass
+// carries it.  It can be taken when it composes into one remap (compose_remap) and the pass in front of it exists and
+// is not the only pass of a step whose load already carries the previous round (one set of remap fields per pass).
 struct DistPlan {
     std::vector<DistStep> steps;
     std::vector<std::vector<Pass>> plans;
+    std::vector<std::vector<std::pair<int, int>>> store;     // per step; empty = a plain store
     int defer_max_ops = 0;     // the threshold that won
     int n_passes = 0;          // passes of the LOCAL_GATES steps
-    int store_step = -1;
-    std::vector<std::pair<int, int>> store_swaps;
+    int n_store = 0;           // swap rounds that ride on a store
 };
 DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total, int n_local, std::vector<int>& perm,
-                                bool restore_identity, bool store_side, const PlanOptions& opt);
+                                bool restore_identity, int store_side, const PlanOptions& opt);
 // The three CNOTs of a LOCAL_SWAP step (for executors that do not fold it into a remap).
 void append_local_swap_gates(int a, int b, std::vector<HostGate>* out);
 

@@ -36,6 +36,7 @@ pub struct dvd_stats {
     pub swap_ms: c_double,
     pub pass_fp64_instr: c_double,
     pub store_remap_passes: i64,
+    pub store_remap_ms: c_double,
 }
 
 pub const DVD_SAMPLER_TREE: c_int = 0;

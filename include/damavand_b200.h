@@ -147,6 +147,7 @@ typedef struct {
                                      tile passes executed: the second roofline of gate-dense passes */
     int64_t store_remap_passes;   /* of remap_passes: passes whose STORE carried the swaps (the layout restore riding on the
                                      last gate pass: remote writes into the partners' second chunk) */
+    double store_remap_ms;        /* of remap_ms: device time of those */
 } dvd_stats;
 int dvd_get_stats(const dvd_state* s, dvd_stats* out);
 int dvd_stats_reset(dvd_state* s);

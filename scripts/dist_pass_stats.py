@@ -8,6 +8,7 @@ from tests.helpers import gate_array
 
 
 def load():
+    """DVD_STORE_REMAP=0/1/2 selects the store-side mode (default 1), DVD_DEFER_TAILS=0 turns tail deferral off."""
     so = os.path.join(ROOT, "tests", "emu", "libdvd_emu.so")
     src = os.path.join(ROOT, "tests", "emu", "emu.cpp")
     deps = [src] + [os.path.join(ROOT, "damavand_b200", "csrc", f) for f in ("planner.cpp", "planner.h", "tile_core.cuh")]
@@ -16,6 +17,7 @@ def load():
     L = ctypes.CDLL(so)
     L.emu_plan_only.restype = ctypes.c_int64
     L.emu_error.restype = ctypes.c_char_p
+    L.emu_set_store(int(os.environ.get("DVD_STORE_REMAP", "1")))
     return L
 
 
@@ -36,7 +38,8 @@ def stats(L, name, world):
             desc.append(f"L{ngt}:{ops}")
             total += npass
         else:
-            desc.append(f"{'S' if kind == 1 else 'X'}({a},{b})"); swaps += kind == 1
+            # S = swap riding on the next load, X = local transposition (restore); P / PX = the same riding on the store of the pass in front
+            desc.append(f"{ {1: 'S', 2: 'X', 3: 'P', 4: 'PX'}[kind]}({a},{b})"); swaps += kind in (1, 3)
     print(f"{name} world={world}: gates {ng}, passes {total}, swaps {swaps}")
     print("   " + " ".join(desc))
     return total

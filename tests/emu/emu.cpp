@@ -190,13 +190,13 @@ const char* emu_error() { return g_err.c_str(); }
 static bool g_track_support = false;
 static bool g_fused = true;      // global<->local swaps ride on the next pass's load (engine default when memory allows)
 void emu_set_fused(int on) { g_fused = on != 0; }
-static bool g_store = true;      // the swaps that end the schedule ride on the store of the last gate pass
+static int g_store = 1;          // planner.h DistPlan: 0 = swaps ride on loads only, 1 = the layout restore rides on the last pass's store, 2 = every round where it can
 static int g_defer = -1;         // tail-deferral threshold of the distributed schedule (-1: the planner picks)
 static int g_last_defer = 0, g_last_store = 0;
-void emu_set_store(int on) { g_store = on != 0; }
+void emu_set_store(int mode) { g_store = mode; }
 void emu_set_defer(int th) { g_defer = th; }
 int emu_last_defer() { return g_last_defer; }     // threshold of the last emu_run's schedule
-int emu_last_store() { return g_last_store; }     // 1 if its last pass stored through a remap
+int emu_last_store() { return g_last_store; }     // swap rounds of that schedule that rode on a store
 int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int fuse, double* state, int64_t* stats /*[4]*/);
 int emu_run_sparse(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int fuse, double* state, int64_t* stats) {
     g_track_support = true;
@@ -219,15 +219,13 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
         PlanOptions opt;
         if (const char* e = getenv("DVD_RELABEL")) opt.relabel = atoi(e) != 0;   // experimental tile relabelling
         std::vector<std::vector<Pass>> plans;      // engine.cu flush_impl: the tuned schedule comes with its pass plans
-        int store_step = -1;
-        std::vector<std::pair<int, int>> store_swaps;
+        std::vector<std::vector<std::pair<int, int>>> store;
         g_last_defer = 0; g_last_store = 0;
         if (world > 1) {
             opt.defer_max_ops = g_defer;
-            DistPlan dp = plan_distributed_tuned(hg, n_qubits, n_local, perm, true, g_fused && g_store, opt);
-            steps = std::move(dp.steps); plans = std::move(dp.plans);
-            store_step = dp.store_step; store_swaps = std::move(dp.store_swaps);
-            g_last_defer = dp.defer_max_ops; g_last_store = store_step >= 0;
+            DistPlan dp = plan_distributed_tuned(hg, n_qubits, n_local, perm, true, g_fused ? g_store : 0, opt);
+            steps = std::move(dp.steps); plans = std::move(dp.plans); store = std::move(dp.store);
+            g_last_defer = dp.defer_max_ops; g_last_store = dp.n_store;
         } else { DistStep st; st.kind = DistStep::LOCAL_GATES; st.gates = hg; steps.push_back(st); }
         for (int q = 0; q < n_qubits; ++q) if (perm[q] != q) throw std::runtime_error("emu: layout not restored");
         int64_t n_pass = 0, n_swap = 0, n_switch = 0, n_ops = 0;
@@ -292,7 +290,8 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
                 for (auto& p : passes) { ++n_pass; n_switch += p.n_switches; n_ops += (int64_t)p.ops.size(); }
                 size_t first = 0, end = passes.size();
                 if (!remap.empty() && !passes.empty()) { fused_pass(passes[0]); first = 1; }
-                const bool store_here = (int)si == store_step;
+                const bool store_here = si < store.size() && !store[si].empty();
+                const std::vector<std::pair<int, int>>& store_swaps = store_here ? store[si] : std::vector<std::pair<int, int>>();
                 if (store_here) { if (end <= first) throw std::runtime_error("emu: no pass left for the store-side remap"); --end; }
                 for (int r = 0; r < world; ++r)
                     for (size_t pi = first; pi < end; ++pi) {
@@ -308,7 +307,7 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
                         run_pass(amp + (uint64_t)r * chunk, passes[end], (uint64_t)r << n_local, 0, &rm);
                     }
                     std::memcpy(amp, out.data(), out.size() * sizeof(cplx));
-                    n_swap += (int64_t)store_swaps.size();
+                    for (auto& sw : store_swaps) n_swap += sw.first >= n_local;
                 }
             } else {
                 for (int r = 0; r < world; ++r) materialize(r);
@@ -356,9 +355,14 @@ extern "C" int64_t emu_plan_only(int n_qubits, int world, const dvd_gate* gates,
         PlanOptions opt;
         if (const char* e = getenv("DVD_RELABEL")) opt.relabel = atoi(e) != 0;
         DistPlan dp;
-        if (world > 1) { opt.defer_max_ops = g_defer; dp = plan_distributed_tuned(hg, n_qubits, n_local, perm, true, g_fused && g_store, opt); steps = dp.steps; }
-        else { DistStep st; st.kind = DistStep::LOCAL_GATES; st.gates = hg; steps.push_back(st); }
-        for (auto& sw : dp.store_swaps) { DistStep st; st.kind = sw.first >= n_local ? DistStep::GLOBAL_SWAP : DistStep::LOCAL_SWAP; st.gq = sw.first; st.lq = sw.second; steps.push_back(st); }
+        if (world > 1) {      // (rounds that ride on a store are shown behind their step, as kind 3 / 4)
+            opt.defer_max_ops = g_defer;
+            dp = plan_distributed_tuned(hg, n_qubits, n_local, perm, true, g_fused ? g_store : 0, opt);
+            for (size_t i = 0; i < dp.steps.size(); ++i) {
+                steps.push_back(dp.steps[i]);
+                for (auto& sw : dp.store[i]) { DistStep st; st.kind = (DistStep::Kind)(sw.first >= n_local ? 3 : 4); st.gq = sw.first; st.lq = sw.second; steps.push_back(st); }
+            }
+        } else { DistStep st; st.kind = DistStep::LOCAL_GATES; st.gates = hg; steps.push_back(st); }
         std::vector<int32_t> v;
         v.push_back((int32_t)steps.size());
         for (auto& st : steps) {

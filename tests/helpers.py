@@ -70,11 +70,12 @@ def emu():
 
 
 def emu_run(oracle_circ: OracleCircuit, world: int = 1, state=None, fuse: bool = True, track_support: bool = False,
-            fused_remap: bool = True, store_side: bool = True, defer: int = -1):
+            fused_remap: bool = True, store_side: int = 1, defer: int = -1):
     """Run the recorded gates of `oracle_circ` through the CPU replay of the CUDA path.
     fused_remap: global<->local swaps ride on the next pass's load (the engine's default when both chunks fit), else
     every swap is an exchange of its own (in-place peer swap / staged NCCL path).
-    store_side: the swaps that end the schedule (layout restore) ride on the STORE of the last gate pass when they can.
+    store_side: 0 = swaps ride on loads only, 1 = the swaps that end the schedule (layout restore) ride on the STORE of the
+    last gate pass when they can (the engine's default), 2 = every swap round rides on a store where it can.
     defer: tail-deferral threshold of the distributed schedule (-1: the planner picks the cheapest of a few).
     track_support: replay the engine's support tracking after a reset -- only amplitude 0 of every rank's chunk is
     stored, the rest of the buffer is NaN (never-written memory) and must never be read."""
@@ -101,7 +102,7 @@ def emu_run(oracle_circ: OracleCircuit, world: int = 1, state=None, fuse: bool =
     if rc != 0:
         raise RuntimeError(emu().emu_error().decode())
     return state.view(np.complex128), dict(passes=stats[0], swaps=stats[1], switches=stats[2], ops=stats[3],
-                                           defer=emu().emu_last_defer(), store_side=bool(emu().emu_last_store()))
+                                           defer=emu().emu_last_defer(), store_side=emu().emu_last_store())
 
 
 def rel_err(a: np.ndarray, b: np.ndarray) -> float:

@@ -19,7 +19,7 @@ class StubCircuit:
         self.gates, self.observables = [], []
         self._st = dict(gates_applied=0, kernel_launches=0, tile_passes=0, simple_passes=0, stage_switches=0, global_swaps=0,
                         swap_bytes_sent=0, pass_bytes=0.0, gate_algorithmic_bytes=0.0, plan_cache_hits=0, jit_launches=0,
-                        remap_passes=0, remap_bytes_in=0.0, remap_ms=0.0, swap_ms=0.0, pass_fp64_instr=0.0, store_remap_passes=0)
+                        remap_passes=0, remap_bytes_in=0.0, remap_ms=0.0, swap_ms=0.0, pass_fp64_instr=0.0, store_remap_passes=0, store_remap_ms=0.0)
         self._t = 0.0
         self._t0 = 0.0
         self.closed = False

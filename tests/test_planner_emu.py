@@ -105,9 +105,10 @@ def test_distributed_replay(world, n):
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_tail_deferral_and_store_side_restore(world):
     """The two schedule transformations of round 2, forced on and off: gates of a nearly empty last pass wait for the next
-    layout (every threshold the planner tries), and the swaps that restore the layout ride on the STORE of the last gate
-    pass (PassDesc::remap_st) -- against the oracle, dense and from a reset (NaN-filled memory)."""
-    seen_defer = seen_store = False
+    layout (every threshold the planner tries), and swap rounds ride on the STORE of the pass in front of them
+    (PassDesc::remap_st): only the layout restore (mode 1, the default) or every round that can (mode 2) -- against the
+    oracle, dense and from a reset (NaN-filled memory)."""
+    seen_defer = seen_store = seen_push = False
     for n, kind, gates, seed in ((16, "random", 200, 10 + world), (17, "random", 200, 10 + world), (18, "random", 300, 1),
                                  (16, "hea", 0, 0), (17, "qft", 0, 0)):
         circ = OracleCircuit(n)
@@ -121,20 +122,21 @@ def test_tail_deferral_and_store_side_restore(world):
         want = ref.amplitudes()
         base = None
         for defer in (-1, 0, 6, 12, 20, 32):
-            for store in (True, False):
+            for store in (1, 0, 2):
                 got, st = emu_run(circ, world, store_side=store, defer=defer)
                 assert rel_err(got, want) < TOL, (n, kind, defer, store)
-                assert st["store_side"] in (False, store)
+                assert st["store_side"] <= (0, 1, 99)[store]
                 if defer == 0 and not store:
                     base = st["passes"]
                 if defer == -1:
                     seen_defer |= st["defer"] > 0
-                    seen_store |= st["store_side"]
+                    seen_store |= store == 1 and st["store_side"] == 1
+                    seen_push |= store == 2 and st["store_side"] >= 2
                 got, _ = emu_run(circ, world, store_side=store, defer=defer, track_support=True)
                 assert not np.isnan(got.view(np.float64)).any() and rel_err(got, want) < TOL, (n, kind, defer, store, "sparse")
         tuned = emu_run(circ, world)[1]
         assert tuned["passes"] <= base          # the tuned schedule never needs more passes than the plain one
-    assert seen_defer and seen_store
+    assert seen_defer and seen_store and seen_push
 
 
 def test_distributed_planner_with_fewer_local_than_rank_index_qubits():
