@@ -772,6 +772,11 @@ static std::vector<Pass> plan_local_impl(const std::vector<HostGate>& gates_in, 
             select(best, tile, tile_n, &taken, &rest);
         }
         if (taken.empty()) throw std::runtime_error("plan_local: no progress");
+        // last pass of a relabelled plan: free tile positions go to the homes of the displaced qubits first, so that they
+        // return in this pass's permuting transpose instead of in a pass of their own
+        if (opt.relabel && rest.empty())
+            for (int sl = 0; sl < min_low && tile_n < TILE_BITS; ++sl)
+                if (partner[sl] != sl && !((tile >> partner[sl]) & 1)) { tile |= 1ull << partner[sl]; ++tile_n; }
         // pad the tile with the lowest unused local qubits (keeps segments long)
         for (int q = 0; q < n_local && tile_n < TILE_BITS; ++q)
             if (!((tile >> q) & 1)) { tile |= 1ull << q; ++tile_n; }
@@ -1250,7 +1255,7 @@ std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n
 
 // Hand swap rounds to the store of the pass in front of them (planner.h: DistPlan::store).  Returns false when a round
 // with LOCAL_SWAP steps -- which no executor runs as steps -- could not be taken: the caller plans again with CNOT triples.
-static bool assign_store_side(DistPlan& dp, int n_local, int mode) {
+static bool assign_store_side(DistPlan& dp, int n_local, int mode, uint64_t zero_mask) {
     std::vector<DistStep> steps;
     std::vector<std::vector<Pass>> plans;
     std::vector<std::vector<std::pair<int, int>>> store;
@@ -1266,6 +1271,7 @@ static bool assign_store_side(DistPlan& dp, int n_local, int mode) {
             plans.push_back(std::move(dp.plans[i]));
             store.emplace_back();
             if (!plans.back().empty()) { last_local = (int)steps.size() - 1; first_pass_pulls = pull_pending; has_store = false; pull_pending = false; }
+            for (const Pass& p : plans.back()) zero_mask &= ~p.touch_mask;      // engine.cu run_pass: support |= touch_mask
             ++i;
             continue;
         }
@@ -1280,16 +1286,20 @@ static bool assign_store_side(DistPlan& dp, int n_local, int mode) {
         bool ends_schedule = true;
         for (size_t k = j; k < n; ++k) if (dp.steps[k].kind != DistStep::LOCAL_GATES || !dp.steps[k].gates.empty()) ends_schedule = false;
         RemapPlan rp;
-        const bool take = mode >= 1 && (mode >= 2 || ends_schedule) && last_local >= 0 && !has_store && !pull_pending &&
+        const bool take = mode >= 1 && (ends_schedule || (mode >= 2 && zero_mask == 0)) && last_local >= 0 && !has_store && !pull_pending &&
                           (!first_pass_pulls || plans[last_local].size() >= 2) &&
                           compose_remap(pairs, n_local, 0, &rp, /*inverse=*/true);
         if (take) {
             store[last_local] = std::move(pairs);
             has_store = true;
+            zero_mask = 0;                       // the engine stores the implied zeros in front of a storing pass
             ++dp.n_store;
         } else {
             if (local_swaps) return false;
-            for (size_t k = i; k < j; ++k) { steps.push_back(std::move(dp.steps[k])); plans.emplace_back(); store.emplace_back(); }
+            for (size_t k = i; k < j; ++k) {
+                if (dp.steps[k].lq >= 0 && dp.steps[k].lq < n_local) zero_mask &= ~(1ull << dp.steps[k].lq);   // rebuilt positions: never implied
+                steps.push_back(std::move(dp.steps[k])); plans.emplace_back(); store.emplace_back();
+            }
             pull_pending = true;
         }
         i = j;
@@ -1301,7 +1311,7 @@ static bool assign_store_side(DistPlan& dp, int n_local, int mode) {
 }
 
 DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total, int n_local, std::vector<int>& perm,
-                                bool restore_identity, int store_side, const PlanOptions& opt) {
+                                bool restore_identity, int store_side, const PlanOptions& opt, uint64_t start_zero_mask) {
     static const int thresholds[] = {0, 6, 12, 20, 32};
     const char* env = getenv("DVD_DEFER_TAILS");
     const bool enabled = n_local >= TILE_BITS && !(env && atoi(env) == 0);
@@ -1328,12 +1338,12 @@ DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total,
                     cand.plans[i] = plan_local(cand.steps[i].gates, n_local, n_total, opt);
                     cand.n_passes += (int)cand.plans[i].size();
                 }
-            if (assign_store_side(cand, n_local, attempt == 0 ? store_side : (store_side >= 2 ? 2 : 0))) break;
+            if (assign_store_side(cand, n_local, attempt == 0 ? store_side : (store_side >= 2 ? 2 : 0), start_zero_mask)) break;
         }
         // cost in plain-pass units: a pass = 1; a round of swaps makes the load of the pass behind it (or the store of the
         // pass in front of it) NVLink-bound (measured on 8 x B200: 9.7 against 5.5 ms) and needs a pass of its own when it
         // has no gate pass to ride on
-        double cost = 0.75 * cand.n_store;
+        double cost = 0.25 * cand.n_store;     // (remote writes hide behind the pass: 24.5 against 28.0 ms for a pulling pass on 2 x B200)
         bool swaps_waiting = false;
         for (size_t i = 0; i < cand.steps.size(); ++i) {
             const DistStep& st = cand.steps[i];

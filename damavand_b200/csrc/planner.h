@@ -153,8 +153,13 @@ struct DistPlan {
     int n_passes = 0;          // passes of the LOCAL_GATES steps
     int n_store = 0;           // swap rounds that ride on a store
 };
+// start_zero_mask: local qubits that are still |0> in every populated basis state when the schedule starts (the engine's
+// support tracking after a reset; 0 = dense).  A storing pass writes every amplitude of the new layout, so the implied
+// zeros must be stored first and the passes behind it run dense: a round in the middle of the schedule rides on a store
+// only once every local qubit has been touched (measured on 2 x B200, random32 from a reset: 165 ms with the early
+// round on a load, 219 ms with it on a store); until then it rides on the next load, which keeps the zeros implied.
 DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total, int n_local, std::vector<int>& perm,
-                                bool restore_identity, int store_side, const PlanOptions& opt);
+                                bool restore_identity, int store_side, const PlanOptions& opt, uint64_t start_zero_mask = 0);
 // The three CNOTs of a LOCAL_SWAP step (for executors that do not fold it into a remap).
 void append_local_swap_gates(int a, int b, std::vector<HostGate>* out);
 

@@ -8,7 +8,7 @@ from tests.helpers import gate_array
 
 
 def load():
-    """DVD_STORE_REMAP=0/1/2 selects the store-side mode (default 1), DVD_DEFER_TAILS=0 turns tail deferral off."""
+    """DVD_STORE_REMAP=0/1/2 selects the store-side mode (default 2), DVD_DEFER_TAILS=0 turns tail deferral off."""
     so = os.path.join(ROOT, "tests", "emu", "libdvd_emu.so")
     src = os.path.join(ROOT, "tests", "emu", "emu.cpp")
     deps = [src] + [os.path.join(ROOT, "damavand_b200", "csrc", f) for f in ("planner.cpp", "planner.h", "tile_core.cuh")]
@@ -17,7 +17,7 @@ def load():
     L = ctypes.CDLL(so)
     L.emu_plan_only.restype = ctypes.c_int64
     L.emu_error.restype = ctypes.c_char_p
-    L.emu_set_store(int(os.environ.get("DVD_STORE_REMAP", "1")))
+    L.emu_set_store(int(os.environ.get("DVD_STORE_REMAP", "2")))
     return L
 
 

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <memory>
 #include <stdexcept>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -190,7 +191,7 @@ const char* emu_error() { return g_err.c_str(); }
 static bool g_track_support = false;
 static bool g_fused = true;      // global<->local swaps ride on the next pass's load (engine default when memory allows)
 void emu_set_fused(int on) { g_fused = on != 0; }
-static int g_store = 1;          // planner.h DistPlan: 0 = swaps ride on loads only, 1 = the layout restore rides on the last pass's store, 2 = every round where it can
+static int g_store = 2;          // planner.h DistPlan: 0 = swaps ride on loads only, 1 = the layout restore rides on the last pass's store, 2 = every round where it can
 static int g_defer = -1;         // tail-deferral threshold of the distributed schedule (-1: the planner picks)
 static int g_last_defer = 0, g_last_store = 0;
 void emu_set_store(int mode) { g_store = mode; }
@@ -223,7 +224,9 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
         g_last_defer = 0; g_last_store = 0;
         if (world > 1) {
             opt.defer_max_ops = g_defer;
-            DistPlan dp = plan_distributed_tuned(hg, n_qubits, n_local, perm, true, g_fused ? g_store : 0, opt);
+            // engine.cu flush_impl: the schedule knows which local qubits are still |0> (every rank has the same mask)
+            DistPlan dp = plan_distributed_tuned(hg, n_qubits, n_local, perm, true, g_fused ? g_store : 0, opt,
+                                                 (g_track_support && n_local >= TILE_BITS) ? (chunk - 1) : 0);
             steps = std::move(dp.steps); plans = std::move(dp.plans); store = std::move(dp.store);
             g_last_defer = dp.defer_max_ops; g_last_store = dp.n_store;
         } else { DistStep st; st.kind = DistStep::LOCAL_GATES; st.gates = hg; steps.push_back(st); }
@@ -371,6 +374,14 @@ extern "C" int64_t emu_plan_only(int n_qubits, int world, const dvd_gate* gates,
                 std::vector<Pass> passes = plan_local(st.gates, n_local, n_qubits, opt);
                 v.push_back((int32_t)passes.size());
                 for (auto& p : passes) v.push_back((int32_t)p.ops.size());
+                if (getenv("DVD_PLAN_DUMP"))
+                    for (auto& p : passes) {
+                        fprintf(stderr, "  pass tile [");
+                        for (int k = 0; k < TILE_BITS; ++k) fprintf(stderr, "%d ", p.desc.tile_q[k]);
+                        fprintf(stderr, "] ops:");
+                        for (auto& op : p.ops) fprintf(stderr, " %d(g%d)", op.code, op.gate_idx);
+                        fprintf(stderr, "\n");
+                    }
             } else v.push_back(0);
         }
         if ((int64_t)v.size() > cap) return -(int64_t)v.size();

@@ -70,12 +70,12 @@ def emu():
 
 
 def emu_run(oracle_circ: OracleCircuit, world: int = 1, state=None, fuse: bool = True, track_support: bool = False,
-            fused_remap: bool = True, store_side: int = 1, defer: int = -1):
+            fused_remap: bool = True, store_side: int = 2, defer: int = -1):
     """Run the recorded gates of `oracle_circ` through the CPU replay of the CUDA path.
     fused_remap: global<->local swaps ride on the next pass's load (the engine's default when both chunks fit), else
     every swap is an exchange of its own (in-place peer swap / staged NCCL path).
     store_side: 0 = swaps ride on loads only, 1 = the swaps that end the schedule (layout restore) ride on the STORE of the
-    last gate pass when they can (the engine's default), 2 = every swap round rides on a store where it can.
+    last gate pass when they can, 2 = every swap round rides on a store where it can (the engine's default).
     defer: tail-deferral threshold of the distributed schedule (-1: the planner picks the cheapest of a few).
     track_support: replay the engine's support tracking after a reset -- only amplitude 0 of every rank's chunk is
     stored, the rest of the buffer is NaN (never-written memory) and must never be read."""
