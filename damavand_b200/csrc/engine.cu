@@ -510,7 +510,7 @@ static int flush_impl(dvd_state* s) {
     std::vector<uint64_t> key;
     if (s->plan_cache) {
         key.reserve(s->pending.size() * 11 + 2);
-        key.push_back((tiled ? 1 : 0) | (s->world > 1 ? s->zero_mask() << 1 : 0));   // (the distributed schedule depends on what is known to be zero)
+        key.push_back((tiled ? 1 : 0) | (s->zero_mask() << 1));   // (plans are chosen by the traffic they need given what is known to be zero)
         key.push_back((uint64_t)s->pending.size());
         for (const HostGate& g : s->pending) {
             key.push_back(g.tmask); key.push_back(g.cmask ^ (g.diag ? 1ull << 63 : 0));
@@ -548,7 +548,11 @@ static int flush_impl(dvd_state* s) {
             if (tiled)
                 for (size_t i = 0; i < steps.size(); ++i)
                     if (steps[i].kind == DistStep::LOCAL_GATES) {
-                        if (s->world == 1) plans[i] = plan_local(steps[i].gates, s->n_local, s->n_qubits, s->opt);
+                        if (s->world == 1) {
+                            PlanOptions o = s->opt;
+                            o.zero_mask = s->zero_mask();      // after a reset: the plan whose early passes visit the fewest tiles
+                            plans[i] = plan_local(steps[i].gates, s->n_local, s->n_qubits, o);
+                        }
                         for (auto& p : plans[i]) total_tabs += p.tables.size();
                     }
         } catch (const std::exception& e) {

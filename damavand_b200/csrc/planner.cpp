@@ -663,11 +663,30 @@ static std::vector<Pass> plan_local_impl(const std::vector<HostGate>& gates_in, 
 //   strictly fewer passes.
 // * Taking the highest-scoring tile for every pass is not the fewest passes overall: with fewer candidates per pass
 //   (closer to first-come order) random32 needs 11 passes instead of 12.  The candidate counts below are tried in
-//   order and a later one replaces the plan only if it needs strictly fewer passes.
+//   order and a later one replaces the plan only if it needs strictly less HBM traffic (plan_traffic: the number of passes
+//   on a dense state; after a reset the passes that run while qubits are still |0> only visit a fraction of the tiles, and
+//   the plan whose early passes stay small wins).
+double plan_traffic(const std::vector<Pass>& passes, uint64_t* zero_mask) {
+    double total = 0.0;
+    uint64_t zm = *zero_mask;
+    for (const Pass& p : passes) {
+        uint64_t tile = 0;
+        for (int k = 0; k < TILE_BITS; ++k) tile |= 1ull << p.desc.tile_q[k];
+        const double launched = std::ldexp(1.0, -__builtin_popcountll(zm & ~tile));
+        const double read = std::ldexp(1.0, -__builtin_popcountll(zm & tile));
+        total += launched * 0.5 * (1.0 + read);
+        zm &= ~p.touch_mask;
+    }
+    *zero_mask = zm;
+    return total;
+}
+
 std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, int n_total, const PlanOptions& opt,
                              std::vector<int>* pass_of_gate) {
     std::vector<Pass> best;
     std::vector<int> best_of;
+    double best_cost = 0.0;
+    const uint64_t zm0 = opt.zero_mask & ((1ull << n_local) - 1);
     bool have = false;
     const int cands[3] = {opt.candidates, 4, 2};
     for (int ci = 0; ci < (opt.portfolio ? 3 : 1); ++ci) {
@@ -679,7 +698,9 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
             o.relabel = rl == 1;
             std::vector<int> of;
             std::vector<Pass> cand = plan_local_impl(gates, n_local, n_total, o, pass_of_gate ? &of : nullptr);
-            if (!have || cand.size() < best.size()) { best = std::move(cand); best_of.swap(of); have = true; }
+            uint64_t zm = zm0;
+            const double cost = plan_traffic(cand, &zm);      // dense: the number of passes
+            if (!have || cost < best_cost - 1e-9) { best = std::move(cand); best_of.swap(of); best_cost = cost; have = true; }
         }
     }
     if (pass_of_gate) pass_of_gate->swap(best_of);
@@ -1325,6 +1346,7 @@ DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total,
         else if (th > 0 && !enabled) break;
         DistPlan cand;
         std::vector<int> p;
+        double traffic = 0.0;      // HBM traffic of the gate passes, in full passes (plan_traffic)
         // with store_side the restore's local transpositions come as LOCAL_SWAP steps; if they cannot ride on the last
         // pass's store after all, the schedule is made again with CNOT triples
         for (int attempt = store_side ? 0 : 1; attempt < 2; ++attempt) {
@@ -1333,14 +1355,24 @@ DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total,
             cand.steps = plan_distributed(gates, n_total, n_local, p, restore_identity, /*local_swap_steps=*/attempt == 0, &opt, th);
             cand.plans.resize(cand.steps.size());
             cand.defer_max_ops = th;
-            for (size_t i = 0; i < cand.steps.size(); ++i)
-                if (cand.steps[i].kind == DistStep::LOCAL_GATES && n_local >= TILE_BITS) {
-                    cand.plans[i] = plan_local(cand.steps[i].gates, n_local, n_total, opt);
+            traffic = 0.0;
+            uint64_t zm = start_zero_mask & ((1ull << n_local) - 1);
+            for (size_t i = 0; i < cand.steps.size(); ++i) {
+                const DistStep& st = cand.steps[i];
+                if (st.kind == DistStep::LOCAL_GATES && n_local >= TILE_BITS) {
+                    PlanOptions o = opt;
+                    o.zero_mask = zm;
+                    cand.plans[i] = plan_local(st.gates, n_local, n_total, o);
                     cand.n_passes += (int)cand.plans[i].size();
+                    traffic += plan_traffic(cand.plans[i], &zm);
+                } else if (st.kind != DistStep::LOCAL_GATES) {      // positions a swap rebuilds are never implied zero
+                    if (st.lq >= 0 && st.lq < n_local) zm &= ~(1ull << st.lq);
+                    if (st.gq >= 0 && st.gq < n_local) zm &= ~(1ull << st.gq);
                 }
+            }
             if (assign_store_side(cand, n_local, attempt == 0 ? store_side : (store_side >= 2 ? 2 : 0), start_zero_mask)) break;
         }
-        // cost in plain-pass units: a pass = 1; a round of swaps makes the load of the pass behind it (or the store of the
+        // cost in plain-pass units: a pass = 1 (less while qubits are still |0>: plan_traffic); a round of swaps makes the load of the pass behind it (or the store of the
         // pass in front of it) NVLink-bound (measured on 8 x B200: 9.7 against 5.5 ms) and needs a pass of its own when it
         // has no gate pass to ride on
         double cost = 0.25 * cand.n_store;     // (remote writes hide behind the pass: 24.5 against 28.0 ms for a pulling pass on 2 x B200)
@@ -1349,9 +1381,9 @@ DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total,
             const DistStep& st = cand.steps[i];
             if (st.kind == DistStep::GLOBAL_SWAP) { if (!swaps_waiting) cost += 0.75; swaps_waiting = true; continue; }
             if (st.kind != DistStep::LOCAL_GATES) continue;
-            cost += (double)cand.plans[i].size();
             if (!cand.plans[i].empty() || n_local < TILE_BITS) swaps_waiting = false;
         }
+        cost += traffic;
         if (swaps_waiting) cost += 1.0;
         if (!have || cost < best_cost - 1e-9) { best = std::move(cand); best_perm = p; best_cost = cost; have = true; }
     }

@@ -60,6 +60,9 @@ struct PlanOptions {
     bool portfolio = true;     // plan_local also tries 4 and 2 candidates per pass and keeps the plan with the fewest passes
     int max_ops_per_pass = 1024;   // gates taken into one pass (halved and retried while the op stream exceeds MAX_OPS_PER_PASS)
     bool macro_ops = true;     // fuse 4-op runs on the four register bits into one dispatch (OC_REALPH4, OC_TWHAD4)
+    uint64_t zero_mask = 0;    // local qubits still |0> in every populated basis state when the plan starts (the engine's support
+                               //   tracking after a reset; 0 = dense): candidate plans are compared by the HBM traffic of their
+                               //   passes (plan_traffic), and a pass neither launches nor reads what is zero by construction
     int defer_max_ops = -1;    // distributed schedule (plan_distributed_tuned): tail-deferral threshold; -1 = the best of a few
     bool best_group = false;   // stage order: group with the most runnable work (true) or group of the first waiting gate
     bool relabel = true;       // tile relabelling (measured on B200 in round 2: hea28 80 -> 55 passes, 236 -> 204 ms; DVD_RELABEL=0 turns it off): the pinned low tile positions are
@@ -83,6 +86,12 @@ std::vector<HostGate> fuse_diagonal_runs(const std::vector<HostGate>& gates);
 // pass_of_gate (optional): for every input gate, the index of the pass that executes it.
 std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, int n_total,
                              const PlanOptions& opt, std::vector<int>* pass_of_gate = nullptr);
+
+// HBM traffic of a plan in units of one full pass (read + write of every local amplitude), as the engine executes it
+// with support tracking (engine.cu run_pass): a pass launches the tiles whose fixed bits avoid *zero_mask, reads the part
+// of a tile that can be non-zero, writes the tile in full, and its non-diagonal targets leave the mask.  Dense: the
+// number of passes.  zero_mask is updated to the state after the plan.
+double plan_traffic(const std::vector<Pass>& passes, uint64_t* zero_mask);
 
 // fp64 instructions per thread of an op list (per-kind costs of tile_core.cuh: general 2x2 = 16 per pair, real / RX-like
 // = 8, Hadamard = 4, real + phase = 12, one complex multiply = 4).

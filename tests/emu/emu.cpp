@@ -289,6 +289,7 @@ int emu_run(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int
                 continue;
             }
             if (n_local >= TILE_BITS) {
+                if (world == 1) opt.zero_mask = ~support[0] & local_mask;      // engine.cu flush_impl
                 std::vector<Pass> passes = world > 1 ? std::move(plans[si]) : plan_local(st.gates, n_local, n_qubits, opt);
                 for (auto& p : passes) { ++n_pass; n_switch += p.n_switches; n_ops += (int64_t)p.ops.size(); }
                 size_t first = 0, end = passes.size();
@@ -390,5 +391,39 @@ extern "C" int64_t emu_plan_only(int n_qubits, int world, const dvd_gate* gates,
     } catch (const std::exception& e) {
         g_err = e.what();
         return INT64_MIN;
+    }
+}
+
+// Planning only: HBM traffic (in full passes over the local chunk) of the gate passes of a workload's schedule, from a
+// reset (from_reset != 0: every local qubit still |0>) or on a dense state; *n_passes = its pass count.
+extern "C" double emu_plan_traffic(int n_qubits, int world, const dvd_gate* gates, int64_t n_gates, int from_reset, int* n_passes) {
+    try {
+        int g = 0; while ((1 << g) < world) ++g;
+        const int n_local = n_qubits - g;
+        std::vector<int> perm(n_qubits);
+        for (int q = 0; q < n_qubits; ++q) perm[q] = q;
+        std::vector<HostGate> hg = fuse_diagonal_runs(conv(gates, n_gates));
+        PlanOptions opt;
+        if (const char* e = getenv("DVD_PLAN_PORTFOLIO")) opt.portfolio = atoi(e) != 0;
+        uint64_t zm = from_reset ? (1ull << n_local) - 1 : 0;
+        double traffic = 0.0;
+        int np = 0;
+        if (world > 1) {
+            DistPlan dp = plan_distributed_tuned(hg, n_qubits, n_local, perm, true, g_fused ? g_store : 0, opt, zm);
+            for (size_t i = 0; i < dp.steps.size(); ++i) {
+                if (dp.steps[i].kind == DistStep::LOCAL_GATES) { traffic += plan_traffic(dp.plans[i], &zm); np += (int)dp.plans[i].size(); if (!dp.store[i].empty()) zm = 0; }
+                else if (dp.steps[i].lq >= 0 && dp.steps[i].lq < n_local) zm &= ~(1ull << dp.steps[i].lq);
+            }
+        } else {
+            opt.zero_mask = zm;
+            std::vector<Pass> passes = plan_local(hg, n_local, n_qubits, opt);
+            traffic = plan_traffic(passes, &zm);
+            np = (int)passes.size();
+        }
+        if (n_passes) *n_passes = np;
+        return traffic;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1.0;
     }
 }
