@@ -104,8 +104,9 @@ struct dvd_state {
     uint64_t support = ~0ull;     // all ones = dense (nothing implied)
     bool lazy_zero = true;
     uint64_t zero_mask() const { return ~support & (n_amps - 1); }
-    // last plan, reused when the same gate list is flushed again (sampling loops re-run one circuit):
-    // key = the queued gates, bit for bit, plus the mode they were planned in
+    // the last few plans, reused when the same gate list is flushed again from the same kind of state (sampling loops
+    // re-run one circuit; a reset + forward and a forward on the dense state it leaves are planned differently):
+    // key = the queued gates, bit for bit, plus the mode they were planned in and what was known to be zero
     struct PlanCache {
         std::vector<uint64_t> key;
         std::vector<DistStep> steps;
@@ -114,7 +115,11 @@ struct dvd_state {
         std::vector<std::vector<std::pair<int, int>>> store;   // planner.h DistPlan::store: swap rounds riding on the store of the
                                                                //   last pass of their step
         bool valid = false;
-    } cache;
+        uint64_t stamp = 0;      // last use (least recently used entry is replaced)
+    };
+    static constexpr size_t PLAN_CACHE_ENTRIES = 4;
+    std::vector<PlanCache> caches;
+    uint64_t cache_clock = 0;
     bool plan_cache = true;
     // structure-specialised kernels (jit_rt.h): off / background compile / compile on first use
     int jit_mode = JIT_OFF;
@@ -518,11 +523,16 @@ static int flush_impl(dvd_state* s) {
             key.push_back((uint64_t)(int64_t)g.gate_idx);
         }
     }
-    const bool hit = s->plan_cache && s->cache.valid && s->cache.key == key;
+    dvd_state::PlanCache* entry = nullptr;
+    if (s->plan_cache)
+        for (auto& c : s->caches) if (c.valid && c.key == key) entry = &c;
+    const bool hit = entry != nullptr;
     if (hit) s->stats.plan_cache_hits++;
     if (!hit) {
-        s->cache.valid = false;
-        s->cache.store.clear();
+        if (s->caches.size() < dvd_state::PLAN_CACHE_ENTRIES) { s->caches.emplace_back(); entry = &s->caches.back(); }
+        else { entry = &s->caches[0]; for (auto& c : s->caches) if (!c.valid || c.stamp < entry->stamp) entry = &c; }
+        entry->valid = false;
+        entry->store.clear();
         std::vector<DistStep> steps;
         // every local step is planned up front so that all phase tables go to the device in one copy; the op
         // lists travel as kernel parameters
@@ -537,7 +547,7 @@ static int flush_impl(dvd_state* s) {
                                                      /*store_side=*/s->fused_remap ? s->store_remap : 0, s->opt, s->zero_mask());
                 steps = std::move(dp.steps);
                 plans = std::move(dp.plans);
-                s->cache.store = std::move(dp.store);
+                entry->store = std::move(dp.store);
             } else if (s->world > 1) {
                 steps = plan_distributed(fused, s->n_qubits, s->n_local, s->perm, /*restore_identity=*/true);
             } else {
@@ -558,15 +568,16 @@ static int flush_impl(dvd_state* s) {
         } catch (const std::exception& e) {
             return fail(DVD_ERR_INTERNAL, std::string("planner: ") + e.what());
         }
-        s->cache.steps = std::move(steps);
-        s->cache.plans = std::move(plans);
-        s->cache.total_tabs = total_tabs;
-        s->cache.key = std::move(key);
-        s->cache.valid = s->plan_cache;
+        entry->steps = std::move(steps);
+        entry->plans = std::move(plans);
+        entry->total_tabs = total_tabs;
+        entry->key = std::move(key);
+        entry->valid = s->plan_cache;
     }
-    std::vector<DistStep>& steps = s->cache.steps;
-    std::vector<std::vector<Pass>>& plans = s->cache.plans;
-    const size_t total_tabs = s->cache.total_tabs;
+    entry->stamp = ++s->cache_clock;
+    std::vector<DistStep>& steps = entry->steps;
+    std::vector<std::vector<Pass>>& plans = entry->plans;
+    const size_t total_tabs = entry->total_tabs;
     if (tiled) {
         if (total_tabs) {
             dvd_state::TabSet& ts = s->tabs[s->n_flushes & 1];
@@ -739,8 +750,8 @@ static int flush_impl(dvd_state* s) {
         if (tiled) {
             for (size_t k = 0; k < plans[i].size(); ++k) {
                 Pass& p = plans[i][k];
-                const bool store_here = k + 1 == plans[i].size() && i < s->cache.store.size() && !s->cache.store[i].empty();
-                TRY(run_pass(p, d_tabs + tat, store_here ? &s->cache.store[i] : nullptr));
+                const bool store_here = k + 1 == plans[i].size() && i < entry->store.size() && !entry->store[i].empty();
+                TRY(run_pass(p, d_tabs + tat, store_here ? &entry->store[i] : nullptr));
                 tat += p.tables.size();
             }
         } else {
