@@ -139,6 +139,24 @@ def test_tail_deferral_and_store_side_restore(world):
     assert seen_defer and seen_store and seen_push
 
 
+@pytest.mark.parametrize("kind,n,arg,world", [("random", 19, 640, 8), ("hea", 19, 10, 8)])
+def test_config_twins_of_the_multi_gpu_workloads(kind, n, arg, world):
+    """Twins of BASELINE configs 4 and 5 (the same generators, gate counts and rank counts at 19 qubits): the schedule
+    the engine derives for them -- deferred tails, several swap rounds on stores, the restore with local transpositions --
+    replayed on emulated ranks, dense and from a reset."""
+    c = OracleCircuit(n)
+    if kind == "random":
+        circuits.random_circuit(c, n, arg)
+    else:
+        circuits.hea(c, n, arg)
+    got, st = emu_run(c, world)
+    got_sp, st_sp = emu_run(c, world, track_support=True)
+    c.forward()
+    assert rel_err(got, c.amplitudes()) < TOL and rel_err(got_sp, c.amplitudes()) < TOL
+    assert st["store_side"] >= 2 and st_sp["store_side"] >= 1      # rounds ride on stores; fewer of them while qubits are still |0>
+    assert st_sp["store_side"] <= st["store_side"]
+
+
 def test_distributed_planner_with_fewer_local_than_rank_index_qubits():
     """More rank-index qubits wanted in one round than there are local positions to evict (n_local < log2(world)):
     the planner must bring them in over several rounds instead of evicting position -1."""
