@@ -689,9 +689,13 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
     const uint64_t zm0 = opt.zero_mask & ((1ull << n_local) - 1);
     bool have = false;
     const int cands[3] = {opt.candidates, 4, 2};
+    PlanChoices* ch = opt.choices;
+    int forced = -1, best_idx = 0;
+    if (ch && ch->replay) forced = ch->pos < ch->tape.size() ? ch->tape[ch->pos++] : 0;
     for (int ci = 0; ci < (opt.portfolio ? 3 : 1); ++ci) {
         if (ci > 0 && cands[ci] >= opt.candidates) continue;
         for (int rl = 0; rl < (opt.relabel ? 2 : 1); ++rl) {
+            if (forced >= 0 && ci * 2 + rl != forced) continue;
             if (have && best.size() <= 1) break;
             PlanOptions o = opt;
             o.candidates = cands[ci];
@@ -700,9 +704,15 @@ std::vector<Pass> plan_local(const std::vector<HostGate>& gates, int n_local, in
             std::vector<Pass> cand = plan_local_impl(gates, n_local, n_total, o, pass_of_gate ? &of : nullptr);
             uint64_t zm = zm0;
             const double cost = plan_traffic(cand, &zm);      // dense: the number of passes
-            if (!have || cost < best_cost - 1e-9) { best = std::move(cand); best_of.swap(of); best_cost = cost; have = true; }
+            if (!have || cost < best_cost - 1e-9) { best = std::move(cand); best_of.swap(of); best_cost = cost; have = true; best_idx = ci * 2 + rl; }
         }
     }
+    if (!have) {      // a recorded choice that this option set does not offer: the plain plan
+        PlanOptions o = opt;
+        o.relabel = false;
+        best = plan_local_impl(gates, n_local, n_total, o, pass_of_gate ? &best_of : nullptr);
+    }
+    if (ch && !ch->replay) ch->tape.push_back(best_idx);
     if (pass_of_gate) pass_of_gate->swap(best_of);
     return best;
 }
@@ -1332,7 +1342,7 @@ static bool assign_store_side(DistPlan& dp, int n_local, int mode, uint64_t zero
 }
 
 DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total, int n_local, std::vector<int>& perm,
-                                bool restore_identity, int store_side, const PlanOptions& opt, uint64_t start_zero_mask) {
+                                bool restore_identity, int store_side, const PlanOptions& opt_in, uint64_t start_zero_mask) {
     static const int thresholds[] = {0, 6, 12, 20, 32};
     const char* env = getenv("DVD_DEFER_TAILS");
     const bool enabled = n_local >= TILE_BITS && !(env && atoi(env) == 0);
@@ -1341,9 +1351,18 @@ DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total,
     std::vector<int> best_perm;
     double best_cost = 0.0;
     bool have = false;
+    PlanChoices* const ch = opt_in.choices;
+    const bool replay = ch && ch->replay && ch->threshold >= 0;
+    PlanChoices best_tape;
     for (int th : thresholds) {
-        if (opt.defer_max_ops >= 0) { if (th != thresholds[0]) break; th = opt.defer_max_ops; }
+        if (replay) { if (th != thresholds[0]) break; th = ch->threshold; }
+        else if (opt_in.defer_max_ops >= 0) { if (th != thresholds[0]) break; th = opt_in.defer_max_ops; }
         else if (th > 0 && !enabled) break;
+        // every threshold's run records (or replays) its own sequence of plan_local winners
+        PlanChoices tape;
+        if (replay) { tape = *ch; tape.pos = 0; }
+        PlanOptions opt = opt_in;
+        opt.choices = ch ? &tape : nullptr;
         DistPlan cand;
         std::vector<int> p;
         double traffic = 0.0;      // HBM traffic of the gate passes, in full passes (plan_traffic)
@@ -1385,8 +1404,12 @@ DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total,
         }
         cost += traffic;
         if (swaps_waiting) cost += 1.0;
-        if (!have || cost < best_cost - 1e-9) { best = std::move(cand); best_perm = p; best_cost = cost; have = true; }
+        if (!have || cost < best_cost - 1e-9) {
+            best = std::move(cand); best_perm = p; best_cost = cost; have = true;
+            best_tape = std::move(tape); best_tape.threshold = th;
+        }
     }
+    if (ch && !replay) { ch->tape = std::move(best_tape.tape); ch->threshold = best_tape.threshold; ch->pos = 0; }
     perm = best_perm;
     return best;
 }

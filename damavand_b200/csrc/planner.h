@@ -53,6 +53,18 @@ struct Pass {
                                //   |0> can turn into a superposition in this pass (support tracking in the engine)
 };
 
+// The planners try a few variants and keep the cheapest (plan_local: tile candidates per pass x relabelling;
+// plan_distributed_tuned: tail-deferral thresholds).  Which variant wins depends on the STRUCTURE of the gate list
+// (qubits, controls, matrix classes), not on its angles, so a variational loop that flushes the same circuit with new
+// parameters need not search again: the winners of one planning run are recorded here, in call order, and a later run
+// with replay = true plans only those (any recorded choice yields a valid plan; a stale one is merely not the cheapest).
+struct PlanChoices {
+    std::vector<int> tape;     // plan_local: winning variant index per call
+    size_t pos = 0;
+    bool replay = false;
+    int threshold = -1;        // plan_distributed_tuned: winning tail-deferral threshold
+};
+
 struct PlanOptions {
     int min_low = 3;           // tile always contains physical qubits [0, min_low): 128 B segments
     int window = 16384;        // look-ahead (gates) when filling a pass
@@ -63,6 +75,7 @@ struct PlanOptions {
     uint64_t zero_mask = 0;    // local qubits still |0> in every populated basis state when the plan starts (the engine's support
                                //   tracking after a reset; 0 = dense): candidate plans are compared by the HBM traffic of their
                                //   passes (plan_traffic), and a pass neither launches nor reads what is zero by construction
+    PlanChoices* choices = nullptr;   // record / replay of the portfolio winners (see PlanChoices)
     int defer_max_ops = -1;    // distributed schedule (plan_distributed_tuned): tail-deferral threshold; -1 = the best of a few
     bool best_group = false;   // stage order: group with the most runnable work (true) or group of the first waiting gate
     bool relabel = true;       // tile relabelling (measured on B200 in round 2: hea28 80 -> 55 passes, 236 -> 204 ms; DVD_RELABEL=0 turns it off): the pinned low tile positions are

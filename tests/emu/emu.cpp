@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <ctime>
 #include <memory>
 #include <stdexcept>
 #include <cstdio>
@@ -425,5 +426,59 @@ extern "C" double emu_plan_traffic(int n_qubits, int world, const dvd_gate* gate
     } catch (const std::exception& e) {
         g_err = e.what();
         return -1.0;
+    }
+}
+
+// Record / replay of the planners' portfolio choices (planner.h: PlanChoices): searches a schedule for `gates` (recording
+// the winners), replays them on `gates2` (the same circuit with other angles; null = the same gates), and compares the
+// replayed schedule op for op with the one a fresh search finds for `gates2`.  Returns 0 if they are identical, > 0
+// otherwise, < 0 on a planner error; ms[0] / ms[1] = host time of the first search and of the replaying run.
+extern "C" int emu_plan_replay_check(int n_qubits, int world, const dvd_gate* gates, const dvd_gate* gates2, int64_t n_gates, int from_reset, double* ms) {
+    try {
+        int g = 0; while ((1 << g) < world) ++g;
+        const int n_local = n_qubits - g;
+        const std::vector<HostGate> hg_a = fuse_diagonal_runs(conv(gates, n_gates));
+        const std::vector<HostGate> hg_b = fuse_diagonal_runs(conv(gates2 ? gates2 : gates, n_gates));
+        const uint64_t zm = from_reset ? (1ull << n_local) - 1 : 0;
+        PlanChoices ch, fresh;
+        std::vector<std::vector<Pass>> plans[3];
+        std::vector<DistStep> steps[3];
+        for (int run = 0; run < 3; ++run) {      // 0: search on A (record), 1: replay on B, 2: search on B
+            const std::vector<HostGate>& hg = run == 0 ? hg_a : hg_b;
+            PlanOptions opt;
+            opt.choices = run == 2 ? &fresh : &ch;
+            ch.replay = run == 1;
+            ch.pos = 0;
+            std::vector<int> perm(n_qubits);
+            for (int q = 0; q < n_qubits; ++q) perm[q] = q;
+            struct timespec t0, t1;
+            clock_gettime(CLOCK_MONOTONIC, &t0);
+            if (world > 1) {
+                DistPlan dp = plan_distributed_tuned(hg, n_qubits, n_local, perm, true, g_fused ? g_store : 0, opt, zm);
+                plans[run] = std::move(dp.plans); steps[run] = std::move(dp.steps);
+            } else {
+                opt.zero_mask = zm;
+                plans[run].push_back(plan_local(hg, n_local, n_qubits, opt));
+            }
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            if (ms && run < 2) ms[run] = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+        }
+        if (ch.tape.empty()) return 1000;
+        if (plans[2].size() != plans[1].size() || steps[2].size() != steps[1].size()) return 1;
+        for (size_t i = 0; i < steps[2].size(); ++i)
+            if (steps[2][i].kind != steps[1][i].kind || steps[2][i].gq != steps[1][i].gq || steps[2][i].lq != steps[1][i].lq) return 2;
+        for (size_t i = 0; i < plans[2].size(); ++i) {
+            if (plans[2][i].size() != plans[1][i].size()) return 3;
+            for (size_t k = 0; k < plans[2][i].size(); ++k) {
+                const Pass& a = plans[2][i][k]; const Pass& b = plans[1][i][k];
+                if (a.ops.size() != b.ops.size() || std::memcmp(a.desc.tile_q, b.desc.tile_q, sizeof a.desc.tile_q)) return 4;
+                for (size_t o = 0; o < a.ops.size(); ++o)
+                    if (a.ops[o].code != b.ops[o].code || std::memcmp(a.ops[o].m, b.ops[o].m, sizeof a.ops[o].m)) return 5;
+            }
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
     }
 }

@@ -65,6 +65,9 @@ def emu():
         L.emu_set_defer.argtypes = [ctypes.c_int]
         L.emu_last_defer.restype = ctypes.c_int
         L.emu_last_store.restype = ctypes.c_int
+        L.emu_plan_replay_check.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(_lib.Gate), ctypes.POINTER(_lib.Gate), ctypes.c_int64,
+                                            ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+        L.emu_plan_replay_check.restype = ctypes.c_int
         _emu = L
     return _emu
 

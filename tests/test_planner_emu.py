@@ -157,6 +157,40 @@ def test_config_twins_of_the_multi_gpu_workloads(kind, n, arg, world):
     assert st_sp["store_side"] <= st["store_side"]
 
 
+def test_planner_choices_record_and_replay():
+    """The planners search a small portfolio (tile candidates x relabelling per plan, tail-deferral thresholds per
+    schedule); the winners are recorded per gate-list structure and replayed when the same circuit comes back with new
+    angles (planner.h: PlanChoices, engine.cu: ChoiceMemo).  A replayed run must reproduce the searched schedule op for
+    op -- on one rank and on emulated ranks, dense and from a reset -- and a second parameter set must replay to the
+    plan a fresh search finds for it."""
+    import ctypes
+    from tests.helpers import gate_array
+    L = emu()
+    for kind, n, arg in (("random", 16, 300), ("hea", 17, 4), ("qft", 16, 0), ("layered", 15, 3)):
+        c = OracleCircuit(n)
+        if kind == "random":
+            circuits.random_circuit(c, n, arg, seed=3)
+        elif kind == "hea":
+            circuits.hea(c, n, arg)
+        elif kind == "qft":
+            circuits.qft_like(c, n)
+        else:
+            circuits.layered(c, n, arg)
+        arr, ng = gate_array(c)
+        for g in c.gates:                      # the same circuit with other angles (a variational step)
+            if g.parameter is not None:
+                g.parameter = 0.37 + 1.7 * g.parameter
+        arr2, ng2 = gate_array(c)
+        assert ng2 == ng
+        for world in (1, 2, 8):
+            if n - (world.bit_length() - 1) < 12:
+                continue
+            for from_reset in (0, 1):
+                ms = (ctypes.c_double * 2)()
+                assert L.emu_plan_replay_check(n, world, arr, None, ng, from_reset, ms) == 0, (kind, n, world, from_reset, L.emu_error())
+                assert L.emu_plan_replay_check(n, world, arr, arr2, ng, from_reset, ms) == 0, (kind, n, world, from_reset, L.emu_error())
+
+
 def test_distributed_planner_with_fewer_local_than_rank_index_qubits():
     """More rank-index qubits wanted in one round than there are local positions to evict (n_local < log2(world)):
     the planner must bring them in over several rounds instead of evicting position -1."""
