@@ -121,7 +121,7 @@ def test_tail_deferral_and_store_side_restore(world):
         ref = OracleCircuit(n); ref.gates = list(circ.gates); ref.forward()
         want = ref.amplitudes()
         base = None
-        for defer in (-1, 0, 6, 12, 20, 32):
+        for defer in (-1, 0, 12, 32):
             for store in (1, 0, 2):
                 got, st = emu_run(circ, world, store_side=store, defer=defer)
                 assert rel_err(got, want) < TOL, (n, kind, defer, store)
@@ -132,8 +132,9 @@ def test_tail_deferral_and_store_side_restore(world):
                     seen_defer |= st["defer"] > 0
                     seen_store |= store == 1 and st["store_side"] == 1
                     seen_push |= store == 2 and st["store_side"] >= 2
-                got, _ = emu_run(circ, world, store_side=store, defer=defer, track_support=True)
-                assert not np.isnan(got.view(np.float64)).any() and rel_err(got, want) < TOL, (n, kind, defer, store, "sparse")
+                if defer in (-1, 12):
+                    got, _ = emu_run(circ, world, store_side=store, defer=defer, track_support=True)
+                    assert not np.isnan(got.view(np.float64)).any() and rel_err(got, want) < TOL, (n, kind, defer, store, "sparse")
         tuned = emu_run(circ, world)[1]
         assert tuned["passes"] <= base          # the tuned schedule never needs more passes than the plain one
     assert seen_defer and seen_store and seen_push
