@@ -1,5 +1,6 @@
 // planner.cpp -- see planner.h.  Pure host C++.
 #include "planner.h"
+#include <cstdio>
 #include <cstdlib>
 
 #include <algorithm>
@@ -1157,6 +1158,7 @@ std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n
         DistStep s; s.kind = DistStep::GLOBAL_SWAP; s.gq = gq; s.lq = lq;
         steps.push_back(std::move(s));
         const int a = inv[gq], b = inv[lq];
+        if (getenv("DVD_PLAN_DUMP")) fprintf(stderr, "  swap: logical %d (at global position %d) comes in, logical %d (at local position %d) goes out\n", a, gq, b, lq);
         perm[a] = lq; perm[b] = gq; inv[gq] = b; inv[lq] = a;
     };
     auto emit_local_cnot = [&](int pc, int pt) {
@@ -1241,18 +1243,37 @@ std::vector<DistStep> plan_distributed(const std::vector<HostGate>& gates, int n
         std::vector<int> next_use(n_total, G + 1);
         for (int k = (int)pending.size() - 1; k >= 0; --k)
             if (!gates[pending[k]].diag) next_use[gates[pending[k]].target()] = k;
-        for (int lqbit : want) {
+        // the rank-index positions this round vacates, and one victim per swap-in
+        std::vector<int> vacated, victims;
+        for (int lqbit : want) vacated.push_back(perm[lqbit]);
+        std::vector<char> taken_pos(n_local, 0);
+        for (size_t k = 0; k < want.size(); ++k) {
             int victim = -1, best = -1;
+            bool best_home = false;
             for (int pass = 0; pass < 2 && victim < 0; ++pass)
                 for (int p = n_local - 1; p >= (pass == 0 ? first_victim : 0); --p) {   // ties: prefer high local positions
                     const int lq = inv[p];
-                    if (std::find(want.begin(), want.end(), lq) != want.end()) continue;
-                    if (next_use[lq] > best) { best = next_use[lq]; victim = p; }
+                    if (taken_pos[p] || std::find(want.begin(), want.end(), lq) != want.end()) continue;
+                    // ... and, first of all, a displaced rank-index qubit whose home is vacated in this round: it goes
+                    // home now and the layout restore has one swap less to do
+                    const bool home = lq >= n_local && std::find(vacated.begin(), vacated.end(), lq) != vacated.end();
+                    if (next_use[lq] > best || (next_use[lq] == best && home && !best_home)) { best = next_use[lq]; victim = p; best_home = home; }
                 }
             if (victim < 0) throw std::runtime_error("plan_distributed: no local position left to evict");
-            emit_swap(perm[lqbit], victim);
-            next_use[lqbit] = -1;    // just swapped in: not a victim for the rest of this round
+            taken_pos[victim] = 1;
+            victims.push_back(victim);
         }
+        // pairing: a victim lands on the rank-index position it is swapped with -- its home where that is on offer
+        std::vector<int> pos_of_victim(victims.size(), -1);
+        std::vector<char> pos_used(vacated.size(), 0);
+        for (size_t v = 0; v < victims.size(); ++v)
+            for (size_t k = 0; k < vacated.size(); ++k)
+                if (!pos_used[k] && vacated[k] == inv[victims[v]]) { pos_of_victim[v] = vacated[k]; pos_used[k] = 1; break; }
+        for (size_t v = 0; v < victims.size(); ++v)
+            if (pos_of_victim[v] < 0)
+                for (size_t k = 0; k < vacated.size(); ++k)
+                    if (!pos_used[k]) { pos_of_victim[v] = vacated[k]; pos_used[k] = 1; break; }
+        for (size_t v = 0; v < victims.size(); ++v) emit_swap(pos_of_victim[v], victims[v]);
     }
 
     if (restore_identity) {
