@@ -1054,11 +1054,6 @@ int estimate_fp64(const std::vector<DevOp>& ops) {
     return total;
 }
 
-void append_local_swap_gates(int a, int b, std::vector<HostGate>* out) {
-    const double x[8] = {0, 0, 1, 0, 1, 0, 0, 0};
-    out->push_back(make_gate(b, a, x, -1)); out->push_back(make_gate(a, b, x, -1)); out->push_back(make_gate(b, a, x, -1));
-}
-
 bool compose_remap(const std::vector<std::pair<int, int>>& swaps, int n_local, int rank, RemapPlan* out, bool inverse) {
     // at[p] = the position whose (old) bit sits at position p after the swaps: new_bit[p] = old_bit[at[p]]
     std::vector<int> pos;      // positions involved, in order of first appearance

@@ -121,7 +121,8 @@ struct DistStep {
     std::vector<HostGate> gates;
     // GLOBAL_SWAP: exchange physical global qubit `gq` (>= n_local) with physical local qubit `lq`
     // LOCAL_SWAP (only with local_swap_steps): exchange the physical LOCAL qubits `gq` and `lq` -- a transposition of the
-    //   layout restore, which the engine folds into a fused remap (or expands into three CNOTs)
+    //   layout restore, which plan_distributed_tuned folds into the remap that rides on the last pass's store (it plans
+    //   again with CNOT triples where it cannot: no executor runs a LOCAL_SWAP as a step)
     int gq = -1, lq = -1;
 };
 
@@ -182,7 +183,5 @@ struct DistPlan {
 // round on a load, 219 ms with it on a store); until then it rides on the next load, which keeps the zeros implied.
 DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total, int n_local, std::vector<int>& perm,
                                 bool restore_identity, int store_side, const PlanOptions& opt, uint64_t start_zero_mask = 0);
-// The three CNOTs of a LOCAL_SWAP step (for executors that do not fold it into a remap).
-void append_local_swap_gates(int a, int b, std::vector<HostGate>* out);
 
 }  // namespace dvd
