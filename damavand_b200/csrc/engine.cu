@@ -122,9 +122,7 @@ struct dvd_state {
     uint64_t cache_clock = 0;
     // the planners' portfolio winners per gate-list STRUCTURE (planner.h: PlanChoices): a variational loop flushes the
     // same circuit with new angles every iteration -- the plan cache misses, but the search need not be repeated
-    struct ChoiceMemo { std::vector<uint64_t> skey; PlanChoices ch; uint64_t stamp = 0; };
-    static constexpr size_t CHOICE_MEMO_ENTRIES = 8;
-    std::vector<ChoiceMemo> memos;
+    ChoiceMemoTable memos;
     bool plan_cache = true;
     // structure-specialised kernels (jit_rt.h): off / background compile / compile on first use
     int jit_mode = JIT_OFF;
@@ -538,31 +536,9 @@ static int flush_impl(dvd_state* s) {
         else { entry = &s->caches[0]; for (auto& c : s->caches) if (!c.valid || c.stamp < entry->stamp) entry = &c; }
         entry->valid = false;
         entry->store.clear();
-        // structure key: what the planners' choices depend on (qubits, controls, matrix classes), not the angles
-        std::vector<uint64_t> skey;
-        skey.reserve(s->pending.size() * 3 + 2);
-        skey.push_back((tiled ? 1 : 0) | (s->zero_mask() << 1));
-        skey.push_back((uint64_t)s->pending.size());
-        for (const HostGate& g : s->pending) {
-            int32_t kind = 0; int8_t d0 = 0;
-            classify_gate(g.m, &kind, &d0);
-            skey.push_back(g.tmask); skey.push_back(g.cmask ^ (g.diag ? 1ull << 63 : 0));
-            skey.push_back((uint64_t)(uint32_t)kind | ((uint64_t)(uint8_t)d0 << 32));
-        }
-        dvd_state::ChoiceMemo* memo = nullptr;
-        for (auto& m : s->memos) if (m.skey == skey) memo = &m;
-        const bool known = memo != nullptr;
-        if (!memo) {
-            if (s->memos.size() < dvd_state::CHOICE_MEMO_ENTRIES) { s->memos.emplace_back(); memo = &s->memos.back(); }
-            else { memo = &s->memos[0]; for (auto& m : s->memos) if (m.stamp < memo->stamp) memo = &m; }
-            memo->skey = std::move(skey);
-            memo->ch = PlanChoices();
-        }
-        memo->stamp = ++s->cache_clock;
-        memo->ch.replay = known && !memo->ch.tape.empty();
-        memo->ch.pos = 0;
+        // the portfolio winners of this gate-list structure, if it was planned before (new angles of the same circuit)
         PlanOptions popt = s->opt;
-        popt.choices = &memo->ch;
+        popt.choices = s->memos.begin(s->pending, (tiled ? 1 : 0) | (s->zero_mask() << 1));
         std::vector<DistStep> steps;
         // every local step is planned up front so that all phase tables go to the device in one copy; the op
         // lists travel as kernel parameters

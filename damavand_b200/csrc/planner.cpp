@@ -667,6 +667,34 @@ static std::vector<Pass> plan_local_impl(const std::vector<HostGate>& gates_in, 
 //   order and a later one replaces the plan only if it needs strictly less HBM traffic (plan_traffic: the number of passes
 //   on a dense state; after a reset the passes that run while qubits are still |0> only visit a fraction of the tiles, and
 //   the plan whose early passes stay small wins).
+PlanChoices* ChoiceMemoTable::begin(const std::vector<HostGate>& gates, uint64_t flags) {
+    std::vector<uint64_t> skey;
+    skey.reserve(gates.size() * 3 + 2);
+    skey.push_back(flags);
+    skey.push_back((uint64_t)gates.size());
+    for (const HostGate& g : gates) {
+        int32_t kind = 0;
+        int8_t d0 = 0;
+        classify_gate(g.m, &kind, &d0);
+        skey.push_back(g.tmask);
+        skey.push_back(g.cmask ^ (g.diag ? 1ull << 63 : 0));
+        skey.push_back((uint64_t)(uint32_t)kind | ((uint64_t)(uint8_t)d0 << 32));
+    }
+    Entry* e = nullptr;
+    for (Entry& x : entries_) if (x.skey == skey) e = &x;
+    const bool known = e != nullptr;
+    if (!e) {
+        if (entries_.size() < capacity_ || entries_.empty()) { entries_.emplace_back(); e = &entries_.back(); }
+        else { e = &entries_[0]; for (Entry& x : entries_) if (x.stamp < e->stamp) e = &x; }
+        e->skey = std::move(skey);
+        e->ch = PlanChoices();
+    }
+    e->stamp = ++clock_;
+    e->ch.replay = known && !e->ch.tape.empty();
+    e->ch.pos = 0;
+    return &e->ch;
+}
+
 double plan_traffic(const std::vector<Pass>& passes, uint64_t* zero_mask) {
     double total = 0.0;
     uint64_t zm = *zero_mask;

@@ -65,6 +65,22 @@ struct PlanChoices {
     int threshold = -1;        // plan_distributed_tuned: winning tail-deferral threshold
 };
 
+// The recorded choices of the last few gate-list structures (least recently used replaced).  begin() returns the entry
+// of the structure of `gates` -- (qubits, controls, matrix classes) plus `flags`, whatever else the plans depend on --
+// set up to replay if that structure was planned before, to record otherwise.  The pointer stays valid until the next
+// begin().
+class ChoiceMemoTable {
+public:
+    explicit ChoiceMemoTable(size_t capacity = 8) : capacity_(capacity) {}
+    PlanChoices* begin(const std::vector<HostGate>& gates, uint64_t flags);
+    size_t size() const { return entries_.size(); }
+private:
+    struct Entry { std::vector<uint64_t> skey; PlanChoices ch; uint64_t stamp = 0; };
+    std::vector<Entry> entries_;
+    size_t capacity_;
+    uint64_t clock_ = 0;
+};
+
 struct PlanOptions {
     int min_low = 3;           // tile always contains physical qubits [0, min_low): 128 B segments
     int window = 16384;        // look-ahead (gates) when filling a pass

@@ -437,18 +437,25 @@ extern "C" int emu_plan_replay_check(int n_qubits, int world, const dvd_gate* ga
     try {
         int g = 0; while ((1 << g) < world) ++g;
         const int n_local = n_qubits - g;
-        const std::vector<HostGate> hg_a = fuse_diagonal_runs(conv(gates, n_gates));
-        const std::vector<HostGate> hg_b = fuse_diagonal_runs(conv(gates2 ? gates2 : gates, n_gates));
+        const std::vector<HostGate> raw_a = conv(gates, n_gates), raw_b = conv(gates2 ? gates2 : gates, n_gates);
+        const std::vector<HostGate> hg_a = fuse_diagonal_runs(raw_a), hg_b = fuse_diagonal_runs(raw_b);
         const uint64_t zm = from_reset ? (1ull << n_local) - 1 : 0;
-        PlanChoices ch, fresh;
+        ChoiceMemoTable table(2), other(2);       // engine.cu flush_impl: dvd_state::memos
+        {   // unrelated structures in between must not disturb the entry (and the table must not grow past its capacity)
+            std::vector<HostGate> x = raw_a;
+            for (int k = 0; k < 3; ++k) { x.pop_back(); other.begin(x, zm); }
+            if (other.size() != 2) return 1001;
+        }
+        PlanChoices ch;
         std::vector<std::vector<Pass>> plans[3];
         std::vector<DistStep> steps[3];
         for (int run = 0; run < 3; ++run) {      // 0: search on A (record), 1: replay on B, 2: search on B
             const std::vector<HostGate>& hg = run == 0 ? hg_a : hg_b;
             PlanOptions opt;
-            opt.choices = run == 2 ? &fresh : &ch;
-            ch.replay = run == 1;
-            ch.pos = 0;
+            PlanChoices* c = run == 2 ? other.begin(raw_b, zm << 1 | 1) : table.begin(run == 0 ? raw_a : raw_b, zm << 1 | 1);
+            if (c->replay != (run == 1)) return 1002;      // same structure, other angles: known; a fresh table: not
+            opt.choices = c;
+            if (run == 1) ch = *c;
             std::vector<int> perm(n_qubits);
             for (int q = 0; q < n_qubits; ++q) perm[q] = q;
             struct timespec t0, t1;
@@ -463,7 +470,7 @@ extern "C" int emu_plan_replay_check(int n_qubits, int world, const dvd_gate* ga
             clock_gettime(CLOCK_MONOTONIC, &t1);
             if (ms && run < 2) ms[run] = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
         }
-        if (ch.tape.empty()) return 1000;
+        if (ch.tape.empty() || !ch.replay) return 1000;
         if (plans[2].size() != plans[1].size() || steps[2].size() != steps[1].size()) return 1;
         for (size_t i = 0; i < steps[2].size(); ++i)
             if (steps[2][i].kind != steps[1][i].kind || steps[2][i].gq != steps[1][i].gq || steps[2][i].lq != steps[1][i].lq) return 2;
