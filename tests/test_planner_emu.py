@@ -163,7 +163,7 @@ def test_config_twins_of_the_multi_gpu_workloads(kind, n, arg, world):
 def test_planner_choices_record_and_replay():
     """The planners search a small portfolio (tile candidates x relabelling per plan, tail-deferral thresholds per
     schedule); the winners are recorded per gate-list structure and replayed when the same circuit comes back with new
-    angles (planner.h: PlanChoices, engine.cu: ChoiceMemo).  A replayed run must reproduce the searched schedule op for
+    angles (planner.h: PlanChoices, planner.h: ChoiceMemoTable).  A replayed run must reproduce the searched schedule op for
     op -- on one rank and on emulated ranks, dense and from a reset -- and a second parameter set must replay to the
     plan a fresh search finds for it."""
     import ctypes
