@@ -1,6 +1,7 @@
 """Randomised check of the planner + tile-kernel logic + support tracking through the CPU replay (no GPU):
-random dense and sparse circuits at 12-16 qubits on 1 / 2 / 4 emulated ranks against the oracle.
-Usage: python scripts/fuzz_replay.py [seed] [seconds]   (414 circuits passed on 4 seeds x 150 s in round 1)"""
+random dense and sparse circuits at 12-18 qubits on 1 / 2 / 4 / 8 emulated ranks against the oracle, with a random
+store-side mode (swap rounds on loads / the restore on a store / every round on a store) and tail-deferral threshold.
+Usage: python scripts/fuzz_replay.py [seed] [seconds]   (round 1: 414 circuits on 4 seeds x 150 s; round 2, with the store modes and thresholds: 726 circuits on 6 seeds x 600 s)"""
 import sys, time
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -10,9 +11,10 @@ from tests.helpers import emu_run, rel_err
 rng=np.random.default_rng(int(sys.argv[1]) if len(sys.argv)>1 else 0)
 t0=time.time(); n_ok=0
 while time.time()-t0 < float(sys.argv[2] if len(sys.argv)>2 else 120):
-    n=int(rng.integers(12,17)); world=int(rng.choice([1,1,2,4])); 
-    if n-(world.bit_length()-1) < 12: world=1
-    gates=int(rng.integers(1,120)); seed=int(rng.integers(0,1<<30))
+    n=int(rng.integers(12,19)); world=int(rng.choice([1,2,4,8]));
+    while n-(world.bit_length()-1) < 12: world//=2
+    gates=int(rng.integers(1,120 if rng.random()<0.6 else 400)); seed=int(rng.integers(0,1<<30))
+    store=int(rng.integers(0,3)); defer=int(rng.choice([-1,-1,0,6,12,20,32]))
     c=OracleCircuit(n)
     # sparse-ish circuits: restrict to a random subset of qubits half of the time
     if rng.random()<0.5:
@@ -30,11 +32,11 @@ while time.time()-t0 < float(sys.argv[2] if len(sys.argv)>2 else 120):
                 if ctl!=t: c.add_cnot_gate(ctl,t)
     else:
         circuits.random_circuit(c,n,gates,seed)
-    got,_=emu_run(c,world,track_support=True)
-    got2,_=emu_run(c,world)
+    got,_=emu_run(c,world,track_support=True,store_side=store,defer=defer)
+    got2,_=emu_run(c,world,store_side=store,defer=defer)
     c.forward()
     e1=rel_err(got,c.amplitudes()); e2=rel_err(got2,c.amplitudes())
     if not (e1<1e-12 and e2<1e-12) or np.isnan(got.view(np.float64)).any():
-        print('FAIL',n,world,gates,seed,e1,e2); sys.exit(1)
+        print('FAIL',n,world,gates,seed,store,defer,e1,e2); sys.exit(1)
     n_ok+=1
 print('ok',n_ok,'circuits')
