@@ -1385,11 +1385,81 @@ static bool assign_store_side(DistPlan& dp, int n_local, int mode, uint64_t zero
     return true;
 }
 
+// Spread a round of k >= 2 swaps over the stores of the last k passes of the step in front of it, one swap each.
+// A round moves (1 - 2^-k) of the chunk over NVLink in ONE pass, which is then bound by the links (measured on 4 x B200:
+// 12.9 GB per direction = 22 ms in a pass that otherwise takes 13 ms), while a single swap moves half a chunk in about
+// the time the pass needs anyway.  A swap can leave as soon as the last pass that targets its local qubit is over; the
+// gates of the passes behind it are renamed to the layout it leaves (its local position now holds the qubit that came in,
+// which nothing uses before the round is complete) and become steps of their own.  pass_of[i][g] = pass of gate g of step i.
+static std::vector<DistStep> split_swap_rounds(const std::vector<DistStep>& in, const std::vector<std::vector<Pass>>& plans,
+                                               const std::vector<std::vector<int>>& pass_of) {
+    std::vector<DistStep> out;
+    const size_t n = in.size();
+    size_t i = 0;
+    while (i < n) {
+        const DistStep& st = in[i];
+        size_t j = i + 1;
+        bool pure = st.kind == DistStep::LOCAL_GATES;
+        if (pure) while (j < n && in[j].kind != DistStep::LOCAL_GATES) { pure = pure && in[j].kind == DistStep::GLOBAL_SWAP; ++j; }
+        const int k = (int)(j - i) - 1, m = (int)plans[i].size();
+        struct Sw { int gq, lq, last, at; };
+        std::vector<Sw> sw;
+        if (pure && k >= 2 && m >= 2 && pass_of[i].size() == st.gates.size()) {
+            for (size_t s2 = i + 1; s2 < j; ++s2) {
+                Sw x{in[s2].gq, in[s2].lq, -1, 0};
+                for (size_t g = 0; g < st.gates.size(); ++g)
+                    if (!st.gates[g].diag && st.gates[g].target() == x.lq) x.last = std::max(x.last, pass_of[i][g]);
+                sw.push_back(x);
+            }
+            std::stable_sort(sw.begin(), sw.end(), [](const Sw& a, const Sw& b) { return a.last > b.last; });
+            int pos = m - 1;
+            for (Sw& x : sw) { x.at = std::max(std::max(pos, x.last), 0); pos = x.at - 1; }
+        }
+        bool split = false;
+        for (const Sw& x : sw) if (x.at != m - 1) split = true;
+        if (!split) {
+            for (size_t s2 = i; s2 < j; ++s2) out.push_back(in[s2]);
+            i = j;
+            continue;
+        }
+        // sub-steps: the gates of the passes up to each cut (in list order), then the swaps that leave there
+        std::vector<HostGate> gates = st.gates;
+        int from = 0;
+        for (int cut = 0; cut < m; ++cut) {
+            bool here = false;
+            for (const Sw& x : sw) if (x.at == cut) here = true;
+            if (!here && cut != m - 1) continue;
+            DistStep sub;
+            sub.kind = DistStep::LOCAL_GATES;
+            for (size_t g = 0; g < gates.size(); ++g)
+                if (pass_of[i][g] >= from && pass_of[i][g] <= cut) sub.gates.push_back(gates[g]);
+            out.push_back(std::move(sub));
+            for (const Sw& x : sw) {
+                if (x.at != cut) continue;
+                DistStep s3; s3.kind = DistStep::GLOBAL_SWAP; s3.gq = x.gq; s3.lq = x.lq;
+                out.push_back(std::move(s3));
+                for (size_t g = 0; g < gates.size(); ++g) {      // the layout behind this swap
+                    if (pass_of[i][g] <= cut) continue;
+                    for (uint64_t* mask : {&gates[g].tmask, &gates[g].cmask}) {
+                        const uint64_t bl = (*mask >> x.lq) & 1ull, bg = (*mask >> x.gq) & 1ull;
+                        if (bl != bg) *mask ^= (1ull << x.lq) | (1ull << x.gq);
+                    }
+                }
+            }
+            from = cut + 1;
+        }
+        i = j;
+    }
+    return out;
+}
+
 DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total, int n_local, std::vector<int>& perm,
                                 bool restore_identity, int store_side, const PlanOptions& opt_in, uint64_t start_zero_mask) {
     static const int thresholds[] = {0, 6, 12, 20, 32};
     const char* env = getenv("DVD_DEFER_TAILS");
     const bool enabled = n_local >= TILE_BITS && !(env && atoi(env) == 0);
+    const char* env_split = getenv("DVD_SPLIT_ROUNDS");
+    const bool split_rounds = n_local >= TILE_BITS && store_side >= 2 && !(env_split && atoi(env_split) == 0);
     if (n_local < TILE_BITS) store_side = 0;
     DistPlan best;
     std::vector<int> best_perm;
@@ -1407,47 +1477,81 @@ DistPlan plan_distributed_tuned(const std::vector<HostGate>& gates, int n_total,
         if (replay) { tape = *ch; tape.pos = 0; }
         PlanOptions opt = opt_in;
         opt.choices = ch ? &tape : nullptr;
+        // pass plans of every LOCAL_GATES step, with the zero mask as it evolves; returns the HBM traffic in full passes
+        auto plan_steps = [&](DistPlan& d, std::vector<std::vector<int>>* pass_of) {
+            double traffic = 0.0;
+            d.plans.assign(d.steps.size(), {});
+            d.n_passes = 0;
+            if (pass_of) pass_of->assign(d.steps.size(), {});
+            uint64_t zm = start_zero_mask & ((1ull << n_local) - 1);
+            for (size_t i = 0; i < d.steps.size(); ++i) {
+                const DistStep& st = d.steps[i];
+                if (st.kind == DistStep::LOCAL_GATES && n_local >= TILE_BITS) {
+                    PlanOptions o = opt;
+                    o.zero_mask = zm;
+                    d.plans[i] = plan_local(st.gates, n_local, n_total, o, pass_of ? &(*pass_of)[i] : nullptr);
+                    d.n_passes += (int)d.plans[i].size();
+                    traffic += plan_traffic(d.plans[i], &zm);
+                } else if (st.kind != DistStep::LOCAL_GATES) {      // positions a swap rebuilds are never implied zero
+                    if (st.lq >= 0 && st.lq < n_local) zm &= ~(1ull << st.lq);
+                    if (st.gq >= 0 && st.gq < n_local) zm &= ~(1ull << st.gq);
+                }
+            }
+            return traffic;
+        };
+        // Cost of the swap rounds in plain-pass units.  A pass takes about 0.45 of the time the links need for a whole chunk
+        // (4 x B200: 13.2 ms against 17.2 GB / 587 GB/s; 8: 6.5 against 14.8; 2: 24.5 against 49), so a round of k swaps,
+        // (1 - 2^-k) of a chunk, costs its pass max(0, 2.2 f - 1) passes extra: next to nothing for one swap, 0.65 for two,
+        // 0.93 for three; pulling costs a little more than pushing (28.0 against 24.5 ms on 2 x B200), and a round with no
+        // pass to ride on needs one of its own.
+        auto extra = [](int k) { const double f = 1.0 - std::ldexp(1.0, -k); return std::max(0.0, 2.2 * f - 1.0) + 0.05; };
+        auto rounds_cost = [&](const DistPlan& d) {
+            double cost = 0.0;
+            int waiting = 0;
+            for (size_t i = 0; i < d.steps.size(); ++i) {
+                const DistStep& st = d.steps[i];
+                if (st.kind == DistStep::GLOBAL_SWAP) { ++waiting; continue; }
+                if (st.kind != DistStep::LOCAL_GATES) continue;
+                if (waiting && (!d.plans[i].empty() || n_local < TILE_BITS)) { cost += extra(waiting) + 0.15; waiting = 0; }
+                int k = 0;
+                for (auto& sw : d.store[i]) k += sw.first >= n_local;
+                if (!d.store[i].empty()) cost += extra(std::max(k, 1));
+            }
+            if (waiting) cost += 1.0 + extra(waiting);
+            return cost;
+        };
         DistPlan cand;
         std::vector<int> p;
-        double traffic = 0.0;      // HBM traffic of the gate passes, in full passes (plan_traffic)
+        double cost = 0.0;
         // with store_side the restore's local transpositions come as LOCAL_SWAP steps; if they cannot ride on the last
         // pass's store after all, the schedule is made again with CNOT triples
         for (int attempt = store_side ? 0 : 1; attempt < 2; ++attempt) {
             cand = DistPlan();
             p = perm;
             cand.steps = plan_distributed(gates, n_total, n_local, p, restore_identity, /*local_swap_steps=*/attempt == 0, &opt, th);
-            cand.plans.resize(cand.steps.size());
             cand.defer_max_ops = th;
-            traffic = 0.0;
-            uint64_t zm = start_zero_mask & ((1ull << n_local) - 1);
-            for (size_t i = 0; i < cand.steps.size(); ++i) {
-                const DistStep& st = cand.steps[i];
-                if (st.kind == DistStep::LOCAL_GATES && n_local >= TILE_BITS) {
-                    PlanOptions o = opt;
-                    o.zero_mask = zm;
-                    cand.plans[i] = plan_local(st.gates, n_local, n_total, o);
-                    cand.n_passes += (int)cand.plans[i].size();
-                    traffic += plan_traffic(cand.plans[i], &zm);
-                } else if (st.kind != DistStep::LOCAL_GATES) {      // positions a swap rebuilds are never implied zero
-                    if (st.lq >= 0 && st.lq < n_local) zm &= ~(1ull << st.lq);
-                    if (st.gq >= 0 && st.gq < n_local) zm &= ~(1ull << st.gq);
+            std::vector<std::vector<int>> pass_of;
+            double traffic = plan_steps(cand, split_rounds ? &pass_of : nullptr);
+            const int mode = attempt == 0 ? store_side : (store_side >= 2 ? 2 : 0);
+            DistPlan alt;
+            double alt_traffic = 0.0;
+            bool have_alt = false;
+            if (split_rounds) {      // the same schedule with its rounds of several swaps spread over several passes
+                alt.steps = split_swap_rounds(cand.steps, cand.plans, pass_of);
+                if (alt.steps.size() != cand.steps.size()) {
+                    alt.defer_max_ops = th;
+                    alt_traffic = plan_steps(alt, nullptr);
+                    have_alt = assign_store_side(alt, n_local, mode, start_zero_mask);
                 }
             }
-            if (assign_store_side(cand, n_local, attempt == 0 ? store_side : (store_side >= 2 ? 2 : 0), start_zero_mask)) break;
+            if (!assign_store_side(cand, n_local, mode, start_zero_mask)) continue;
+            cost = traffic + rounds_cost(cand);
+            if (have_alt && alt.n_passes <= cand.n_passes) {      // (never at the price of more passes: the model is too coarse for that trade)
+                const double alt_cost = alt_traffic + rounds_cost(alt);
+                if (alt_cost < cost - 1e-9) { cand = std::move(alt); cost = alt_cost; }
+            }
+            break;
         }
-        // cost in plain-pass units: a pass = 1 (less while qubits are still |0>: plan_traffic); a round of swaps makes the load of the pass behind it (or the store of the
-        // pass in front of it) NVLink-bound (measured on 8 x B200: 9.7 against 5.5 ms) and needs a pass of its own when it
-        // has no gate pass to ride on
-        double cost = 0.25 * cand.n_store;     // (remote writes hide behind the pass: 24.5 against 28.0 ms for a pulling pass on 2 x B200)
-        bool swaps_waiting = false;
-        for (size_t i = 0; i < cand.steps.size(); ++i) {
-            const DistStep& st = cand.steps[i];
-            if (st.kind == DistStep::GLOBAL_SWAP) { if (!swaps_waiting) cost += 0.75; swaps_waiting = true; continue; }
-            if (st.kind != DistStep::LOCAL_GATES) continue;
-            if (!cand.plans[i].empty() || n_local < TILE_BITS) swaps_waiting = false;
-        }
-        cost += traffic;
-        if (swaps_waiting) cost += 1.0;
         if (!have || cost < best_cost - 1e-9) {
             best = std::move(cand); best_perm = p; best_cost = cost; have = true;
             best_tape = std::move(tape); best_tape.threshold = th;

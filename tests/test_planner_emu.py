@@ -160,6 +160,25 @@ def test_config_twins_of_the_multi_gpu_workloads(kind, n, arg, world):
     assert st_sp["store_side"] <= st["store_side"]
 
 
+def test_swap_rounds_spread_over_several_passes(monkeypatch):
+    """A round of several swaps makes its pass NVLink-bound; where the victims' last uses allow, the swaps leave one per
+    pass from the last passes of the step in front of the round (planner.cpp: split_swap_rounds) -- more, smaller rounds,
+    never more passes than the same schedule unsplit.  Both schedules against the oracle."""
+    n, world = 16, 8
+    circ = OracleCircuit(n)
+    circuits.random_circuit(circ, n, 500, seed=2)
+    ref = OracleCircuit(n); ref.gates = list(circ.gates); ref.forward()
+    stats = {}
+    for split in ("1", "0"):
+        monkeypatch.setenv("DVD_SPLIT_ROUNDS", split)
+        got, st = emu_run(circ, world)
+        got_sp, _ = emu_run(circ, world, track_support=True)
+        assert rel_err(got, ref.amplitudes()) < TOL and rel_err(got_sp, ref.amplitudes()) < TOL, split
+        stats[split] = st
+    assert stats["1"]["store_side"] > stats["0"]["store_side"]        # more rounds ...
+    assert stats["1"]["swaps"] == stats["0"]["swaps"]                  # ... of the same swaps
+
+
 def test_planner_choices_record_and_replay():
     """The planners search a small portfolio (tile candidates x relabelling per plan, tail-deferral thresholds per
     schedule); the winners are recorded per gate-list structure and replayed when the same circuit comes back with new
