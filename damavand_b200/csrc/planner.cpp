@@ -1404,7 +1404,9 @@ static std::vector<DistStep> split_swap_rounds(const std::vector<DistStep>& in, 
         const int k = (int)(j - i) - 1, m = (int)plans[i].size();
         struct Sw { int gq, lq, last, at; };
         std::vector<Sw> sw;
-        if (pure && k >= 2 && m >= 2 && pass_of[i].size() == st.gates.size()) {
+        bool mapped = pure && pass_of[i].size() == st.gates.size();
+        if (mapped) for (int pg : pass_of[i]) if (pg < 0 || pg >= m) mapped = false;      // every gate has its pass
+        if (mapped && k >= 2 && m >= 2) {
             for (size_t s2 = i + 1; s2 < j; ++s2) {
                 Sw x{in[s2].gq, in[s2].lq, -1, 0};
                 for (size_t g = 0; g < st.gates.size(); ++g)
