@@ -1,7 +1,7 @@
 """Randomised check of the planner + tile-kernel logic + support tracking through the CPU replay (no GPU):
 random dense and sparse circuits at 12-18 qubits on 1 / 2 / 4 / 8 emulated ranks against the oracle, with a random
 store-side mode (swap rounds on loads / the restore on a store / every round on a store) and tail-deferral threshold.
-Usage: python scripts/fuzz_replay.py [seed] [seconds]   (round 1: 414 circuits on 4 seeds x 150 s; round 2, with the store modes and thresholds: 726 circuits on 6 seeds x 600 s)"""
+Usage: python scripts/fuzz_replay.py [seed] [seconds]   (round 1: 414 circuits on 4 seeds x 150 s; round 2, with the store modes, thresholds, home-going and split swap rounds: 1073 circuits on 8 seeds x 900 s)"""
 import sys, time
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
